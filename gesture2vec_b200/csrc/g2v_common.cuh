@@ -1,0 +1,87 @@
+// Shared declarations for the sm_100a vector-quantizer kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/g2v_vq.h"
+
+namespace g2v {
+
+// ---------------------------------------------------------------------------------------------
+// Codebook aux buffer ("cb"): header + ||e||^2 + fp16 operand copy.  Layout in bytes:
+//   [0, 256)                       CbHeader
+//   [256, 256 + 4*Kp)              e2[Kp] fp32 (fp64-accumulated, rounded once; +inf for k >= K)
+//   [off16, off16 + 2*Kp*Dp)       E16[Kp][Dp] fp16, zero padded, scaled by header.scale_e
+// Kp = K rounded up to 256, Dp = D rounded up to 16.
+// ---------------------------------------------------------------------------------------------
+struct CbHeader {
+  float e2max;      // max_k ||e_k||^2
+  float q4max;      // max_k (sum_j e_kj^4)^(1/2)    (variance bound of the fp16 rounding error)
+  float amax;       // max |e_kj|
+  float scale_e;    // power of two the fp16 copy was multiplied by (1 unless amax is huge/tiny)
+  int K, D, Kp, Dp;
+  int magic;
+  int pad[55];
+};
+static_assert(sizeof(CbHeader) == 256, "CbHeader must be 256 bytes");
+constexpr int kCbMagic = 0x67327631;  // "g2v1"
+
+__host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+inline size_t cb_e2_offset() { return 256; }
+inline size_t cb_e16_offset(int K) { return 256 + (size_t)round_up(K, 256) * 4; }  // multiple of 1024
+inline size_t cb_total_bytes(int K, int D) {
+  return cb_e16_offset(K) + (size_t)round_up(K, 256) * round_up(D, 16) * 2;
+}
+
+// error recording (thread local), defined in g2v_api.cu
+void set_error_detail(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define G2V_CUDA_CHECK(expr)                                   \
+  do {                                                         \
+    cudaError_t _e = (expr);                                   \
+    if (_e != cudaSuccess) return ::g2v::cuda_fail(_e, #expr); \
+  } while (0)
+
+#define G2V_LAUNCH_CHECK(name)                                  \
+  do {                                                          \
+    cudaError_t _e = cudaGetLastError();                        \
+    if (_e != cudaSuccess) return ::g2v::cuda_fail(_e, name);   \
+  } while (0)
+
+int num_sms();
+
+// ---- launchers implemented in g2v_simt.cu ----------------------------------------------------
+int launch_codebook_prepare(const float* E, int K, int D, void* cb, cudaStream_t st);
+// fp32 CUDA-core search over all rows (row_list == nullptr) or over the rows listed in
+// row_list[0 .. *row_count).
+int launch_search_simt(const float* z, const float* E, const void* cb, int64_t N, int K, int D,
+                       const int32_t* row_list, const int32_t* row_count, int32_t* idx,
+                       unsigned long long* stats, cudaStream_t st);
+int launch_apply(const float* x, const float* zs, const float* E, const int32_t* idx, int64_t N, int K,
+                 int D, float* out, double* sse, int32_t* counts, float* dwr, cudaStream_t st);
+int launch_stats_pack(const int32_t* counts, const double* sse, int64_t N, int K, int D, float* packed,
+                      cudaStream_t st);
+int launch_stats_finalize(const float* packed, int K, int D, float coef_codebook, float coef_commit,
+                          float* loss, float* ppl, cudaStream_t st);
+int launch_ema_update(float* cs, float* ema_w, const float* E_old, float* E_new, const float* packed,
+                      float decay, float eps, int K, int D, cudaStream_t st);
+int launch_backward(const float* x, const float* E, const int32_t* idx, const float* g_out,
+                    const float* g_loss, float coef_x, int64_t N, int K, int D, float* g_x,
+                    cudaStream_t st);
+int launch_grad_codebook(const float* dwr, const float* g_loss, float coef_e, int K, int D, float* g_E,
+                         cudaStream_t st);
+int launch_onehot(const int32_t* idx, int64_t N, int K, float* enc, cudaStream_t st);
+int launch_convert_rows_f32(const void* src, int dtype, int64_t n_elems, float* dst, cudaStream_t st);
+
+// ---- tensor-core path, implemented in g2v_tc.cu ---------------------------------------------
+bool tc_supported(int K, int D);
+size_t tc_workspace_bytes(int64_t N, int K, int D, int z_dtype);
+int launch_search_tc(const void* z, int z_dtype, const float* E, const void* cb, int64_t N, int K, int D,
+                     int32_t* idx, unsigned long long* stats, void* ws, size_t ws_bytes, unsigned flags,
+                     cudaStream_t st);
+
+}  // namespace g2v

@@ -1,0 +1,666 @@
+// CUDA-core (fp32 / fp64) kernels of the vector-quantizer path, sm_100a.
+//
+//   search_simt_kernel   register-tiled fp32 distance sweep with a fused running top-2 and an
+//                        in-kernel exact (fp64) re-rank of the rows whose top-2 gap is inside the
+//                        fp32 error bound.  General fallback (any K, D), and the second stage of
+//                        the tensor-core path for the rows it cannot certify.
+//   apply_kernel         gather + straight-through value + SSE + histogram + EMA residual sums.
+//   backward_kernel      g_x = g_out + c*(x - E[idx]).
+//   ema_* / stats_*      codebook update and scalar outputs.
+//   onehot_kernel        dense one-hot the reference returns.
+//
+// Everything here is bandwidth- or CUDA-core-bound by nature; the tensor-core search lives in
+// g2v_tc.cu.
+#include "g2v_common.cuh"
+
+#include <float.h>
+#include <math.h>
+
+namespace g2v {
+
+namespace {
+
+constexpr float kU32 = 5.9604645e-8f;  // 2^-24, fp32 unit roundoff
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// codebook preparation
+// ------------------------------------------------------------------------------------------
+__global__ void cb_rows_kernel(const float* __restrict__ E, int K, int D, int Kp, CbHeader* hdr,
+                               float* __restrict__ e2) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= Kp) return;
+  if (warp >= K) {
+    if (lane == 0) e2[warp] = INFINITY;
+    return;
+  }
+  const float* row = E + (size_t)warp * D;
+  double s2 = 0.0, s4 = 0.0;
+  float am = 0.f;
+  for (int j = lane; j < D; j += 32) {
+    float v = row[j];
+    double v2 = (double)v * (double)v;
+    s2 += v2;
+    s4 += v2 * v2;
+    am = fmaxf(am, fabsf(v));
+  }
+  s2 = warp_sum(s2);
+  s4 = warp_sum(s4);
+  am = warp_max(am);
+  if (lane == 0) {
+    float f2 = (float)s2;
+    e2[warp] = f2;
+    // non-negative floats order like their bit patterns
+    atomicMax(reinterpret_cast<int*>(&hdr->e2max), __float_as_int(f2));
+    atomicMax(reinterpret_cast<int*>(&hdr->q4max), __float_as_int((float)sqrt(s4)));
+    atomicMax(reinterpret_cast<int*>(&hdr->amax), __float_as_int(am));
+  }
+}
+
+__global__ void cb_header_kernel(CbHeader* hdr, int K, int D, int Kp, int Dp) {
+  float am = hdr->amax;
+  float sc = 1.f;
+  if (am > 0.f && isfinite(am)) {
+    int e;
+    frexpf(am, &e);            // am = m * 2^e, m in [0.5,1)  ->  am*2^(9-e) in [256,512)
+    sc = ldexpf(1.f, 9 - e);
+  }
+  hdr->scale_e = sc;
+  hdr->K = K; hdr->D = D; hdr->Kp = Kp; hdr->Dp = Dp;
+  hdr->magic = kCbMagic;
+}
+
+__global__ void cb_fp16_kernel(const float* __restrict__ E, int K, int D, int Kp, int Dp,
+                               const CbHeader* __restrict__ hdr, __half* __restrict__ E16) {
+  float sc = hdr->scale_e;
+  size_t total = (size_t)Kp * Dp;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int k = (int)(i / Dp), j = (int)(i % Dp);
+    float v = (k < K && j < D) ? E[(size_t)k * D + j] * sc : 0.f;
+    E16[i] = __float2half_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 search with fused top-2 and exact re-rank
+// ------------------------------------------------------------------------------------------
+constexpr int BM = 128, BN = 128, BK = 16, NT = 256, LDS = BM + 4;
+
+struct SearchSmem {
+  float As[2][BK][LDS];
+  float Bs[2][BK][LDS];
+  float e2s[BN];
+  float z2p[2][BM];
+  int rows[BM];
+  int flagged[BM];
+  int nflag;
+  double red_v[NT / 32];
+  int red_i[NT / 32];
+};
+
+template <bool VEC>
+__device__ __forceinline__ void load8(const float* __restrict__ base, long long row, int D, int col,
+                                      float (&v)[8]) {
+  if (row < 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    return;
+  }
+  const float* p = base + (size_t)row * D + col;
+  if (VEC && col + 8 <= D) {
+    float4 a = ldg4(p), b = ldg4(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (col + i < D) ? __ldg(p + i) : 0.f;
+  }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(NT) search_simt_kernel(
+    const float* __restrict__ z, const float* __restrict__ E, const float* __restrict__ e2,
+    const CbHeader* __restrict__ hdr, long long N, int K, int D, const int* __restrict__ row_list,
+    const int* __restrict__ row_count, int* __restrict__ idx_out, unsigned long long* stats) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SearchSmem& S = *reinterpret_cast<SearchSmem*>(smem_raw);
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int lrow = t & (BM - 1), lhalf = t >> 7;  // loader mapping: row, which 8 of the 16 columns
+  const long long n_rows = row_list ? (long long)*row_count : N;
+  const int nk = (D + BK - 1) / BK;
+  const int n_ctile = (K + BN - 1) / BN;
+  const float e2max = hdr->e2max;
+
+  for (long long tile = blockIdx.x; tile * BM < n_rows; tile += gridDim.x) {
+    __syncthreads();  // previous tile fully done with smem
+    if (t < BM) {
+      long long r = tile * BM + t;
+      S.rows[t] = (r < n_rows) ? (row_list ? row_list[r] : (int)r) : -1;
+    }
+    if (t == 0) S.nflag = 0;
+    __syncthreads();
+    const long long grow = S.rows[lrow];
+
+    float m1[8], m2[8];
+    int i1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { m1[i] = INFINITY; m2[i] = INFINITY; i1[i] = 0; }
+    float zsq = 0.f;
+
+    for (int ct = 0; ct < n_ctile; ++ct) {
+      const int kb = ct * BN;
+      const long long crow = (kb + lrow < K) ? (kb + lrow) : -1;
+      float acc[8][8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+      float ra[8], rb[8];
+      load8<VEC>(z, grow, D, lhalf * 8, ra);
+      load8<VEC>(E, crow, D, lhalf * 8, rb);
+      if (t < BN) S.e2s[t] = (kb + t < K) ? e2[kb + t] : INFINITY;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        S.As[0][lhalf * 8 + i][lrow] = ra[i];
+        S.Bs[0][lhalf * 8 + i][lrow] = rb[i];
+      }
+      if (ct == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) zsq = fmaf(ra[i], ra[i], zsq);
+      }
+      __syncthreads();
+
+      for (int kc = 0; kc < nk; ++kc) {
+        const int buf = kc & 1;
+        if (kc + 1 < nk) {
+          load8<VEC>(z, grow, D, (kc + 1) * BK + lhalf * 8, ra);
+          load8<VEC>(E, crow, D, (kc + 1) * BK + lhalf * 8, rb);
+        }
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+          float4 a0 = *reinterpret_cast<const float4*>(&S.As[buf][k][ty * 4]);
+          float4 a1 = *reinterpret_cast<const float4*>(&S.As[buf][k][64 + ty * 4]);
+          float4 b0 = *reinterpret_cast<const float4*>(&S.Bs[buf][k][tx * 4]);
+          float4 b1 = *reinterpret_cast<const float4*>(&S.Bs[buf][k][64 + tx * 4]);
+          float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+          float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (kc + 1 < nk) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            S.As[buf ^ 1][lhalf * 8 + i][lrow] = ra[i];
+            S.Bs[buf ^ 1][lhalf * 8 + i][lrow] = rb[i];
+          }
+          if (ct == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) zsq = fmaf(ra[i], ra[i], zsq);
+          }
+        }
+        __syncthreads();
+      }
+
+      // fused running top-2 (ascending code order inside a thread, strict '<' keeps the first)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = (j < 4) ? (tx * 4 + j) : (64 + tx * 4 + j - 4);
+        const float ek = S.e2s[c];
+        const int k = kb + c;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float d = fmaf(-2.f, acc[i][j], ek);
+          bool lt = d < m1[i];
+          m2[i] = fminf(m2[i], fmaxf(d, m1[i]));
+          i1[i] = lt ? k : i1[i];
+          m1[i] = fminf(m1[i], d);
+        }
+      }
+      __syncthreads();  // e2s / smem buffers are rewritten by the next code tile
+    }
+
+    // row norms for the error bound
+    S.z2p[lhalf][lrow] = zsq;
+    // merge the 16 column-threads of each row (they are one half-warp)
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float om1 = __shfl_xor_sync(0xffffffffu, m1[i], o);
+        float om2 = __shfl_xor_sync(0xffffffffu, m2[i], o);
+        int oi1 = __shfl_xor_sync(0xffffffffu, i1[i], o);
+        bool take = (om1 < m1[i]) || (om1 == m1[i] && oi1 < i1[i]);
+        float nm2 = take ? fminf(m1[i], om2) : fminf(m2[i], om1);
+        m1[i] = take ? om1 : m1[i];
+        i1[i] = take ? oi1 : i1[i];
+        m2[i] = nm2;
+      }
+    }
+    __syncthreads();
+    if (tx == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = (i < 4) ? (ty * 4 + i) : (64 + ty * 4 + i - 4);
+        const int g = S.rows[r];
+        if (g < 0) continue;
+        idx_out[g] = i1[i];
+        // |d_hat - d| <= 2*D*u*|z||e| + u*e2 + u*|d_hat| per code; the gap of two codes can be
+        // off by twice that.
+        float z2 = S.z2p[0][r] + S.z2p[1][r];
+        float tau = 4.f * (float)D * kU32 * sqrtf(z2 * e2max) + 4.f * kU32 * (e2max + fabsf(m1[i]));
+        if (!(m2[i] - m1[i] > tau)) {
+          int slot = atomicAdd(&S.nflag, 1);
+          S.flagged[slot] = r;
+        }
+      }
+    }
+    __syncthreads();
+
+    // exact re-rank of the uncertified rows: whole distance row in fp64, first index on ties
+    const int nflag = S.nflag;
+    for (int f = 0; f < nflag; ++f) {
+      const int g = S.rows[S.flagged[f]];
+      const float* zr = z + (size_t)g * D;
+      double best = INFINITY;
+      int besti = 0x7fffffff;
+      for (int k = t; k < K; k += NT) {
+        const float* er = E + (size_t)k * D;
+        double s = 0.0;
+        for (int j = 0; j < D; ++j) {
+          double df = (double)__ldg(zr + j) - (double)__ldg(er + j);
+          s = fma(df, df, s);
+        }
+        if (s < best) { best = s; besti = k; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (ov < best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+      }
+      if ((t & 31) == 0) { S.red_v[t >> 5] = best; S.red_i[t >> 5] = besti; }
+      __syncthreads();
+      if (t == 0) {
+        for (int w = 1; w < NT / 32; ++w)
+          if (S.red_v[w] < best || (S.red_v[w] == best && S.red_i[w] < besti)) { best = S.red_v[w]; besti = S.red_i[w]; }
+        idx_out[g] = besti;
+      }
+      __syncthreads();
+    }
+    if (t == 0 && stats) {
+      if (nflag) atomicAdd(stats + G2V_STAT_FULL_RECHECK, (unsigned long long)nflag);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// gather + STE value + statistics
+// ------------------------------------------------------------------------------------------
+constexpr int APPLY_WARPS = 8;
+
+template <bool VEC>
+__global__ void __launch_bounds__(APPLY_WARPS * 32) apply_kernel(
+    const float* __restrict__ x, const float* __restrict__ zs, const float* __restrict__ E,
+    const int* __restrict__ idx, long long N, int K, int D, float* __restrict__ out, double* sse,
+    int* counts, float* dwr, int use_hist) {
+  extern __shared__ int hist[];
+  __shared__ double wsum[APPLY_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (use_hist) {
+    for (int k = threadIdx.x; k < K; k += blockDim.x) hist[k] = 0;
+    __syncthreads();
+  }
+  float acc = 0.f;
+  const long long stride = (long long)gridDim.x * APPLY_WARPS;
+  for (long long row = (long long)blockIdx.x * APPLY_WARPS + warp; row < N; row += stride) {
+    int k = __ldg(idx + row);
+    k = min(max(k, 0), K - 1);
+    const float* xr = x + (size_t)row * D;
+    const float* er = E + (size_t)k * D;
+    const float* zr = zs ? zs + (size_t)row * D : nullptr;
+    float* orow = out ? out + (size_t)row * D : nullptr;
+    float* drow = dwr ? dwr + (size_t)k * D : nullptr;
+    if (VEC) {
+      for (int c = lane * 4; c < D; c += 128) {
+        float4 xv = ldg4(xr + c), ev = ldg4(er + c);
+        float4 d = make_float4(ev.x - xv.x, ev.y - xv.y, ev.z - xv.z, ev.w - xv.w);
+        acc = fmaf(d.x, d.x, acc); acc = fmaf(d.y, d.y, acc);
+        acc = fmaf(d.z, d.z, acc); acc = fmaf(d.w, d.w, acc);
+        if (orow) {
+          float4 o = make_float4(xv.x + d.x, xv.y + d.y, xv.z + d.z, xv.w + d.w);
+          __stcs(reinterpret_cast<float4*>(orow + c), o);
+        }
+        if (drow) {
+          if (zr) {
+            float4 zv = ldg4(zr + c);
+            red_add_v4(drow + c, zv.x - ev.x, zv.y - ev.y, zv.z - ev.z, zv.w - ev.w);
+          } else {
+            red_add_v4(drow + c, -d.x, -d.y, -d.z, -d.w);
+          }
+        }
+      }
+    } else {
+      for (int c = lane; c < D; c += 32) {
+        float xv = __ldg(xr + c), ev = __ldg(er + c);
+        float d = ev - xv;
+        acc = fmaf(d, d, acc);
+        if (orow) orow[c] = xv + d;
+        if (drow) atomicAdd(drow + c, (zr ? __ldg(zr + c) : xv) - ev);
+      }
+    }
+    if (lane == 0 && counts) {
+      if (use_hist) atomicAdd(&hist[k], 1);
+      else atomicAdd(counts + k, 1);
+    }
+  }
+  if (sse) {
+    double s = warp_sum((double)acc);
+    if (lane == 0) wsum[warp] = s;
+  }
+  __syncthreads();
+  if (sse && threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < APPLY_WARPS; ++w) s += wsum[w];
+    atomicAdd(sse, s);
+  }
+  if (use_hist && counts) {
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      int v = hist[k];
+      if (v) atomicAdd(counts + k, v);
+    }
+  }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) backward_kernel(const float* __restrict__ x, const float* __restrict__ E,
+                                                       const int* __restrict__ idx,
+                                                       const float* __restrict__ g_out,
+                                                       const float* __restrict__ g_loss, float coef_x,
+                                                       long long N, int K, int D, float* __restrict__ g_x) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float c = __ldg(g_loss) * coef_x;
+  const long long stride = (long long)gridDim.x * 8;
+  for (long long row = (long long)blockIdx.x * 8 + warp; row < N; row += stride) {
+    int k = __ldg(idx + row);
+    k = min(max(k, 0), K - 1);
+    const float* xr = x + (size_t)row * D;
+    const float* er = E + (size_t)k * D;
+    const float* gr = g_out ? g_out + (size_t)row * D : nullptr;
+    float* o = g_x + (size_t)row * D;
+    if (VEC) {
+      for (int j = lane * 4; j < D; j += 128) {
+        float4 xv = ldg4(xr + j), ev = ldg4(er + j);
+        float4 g = gr ? ldg4(gr + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 r = make_float4(fmaf(c, xv.x - ev.x, g.x), fmaf(c, xv.y - ev.y, g.y),
+                               fmaf(c, xv.z - ev.z, g.z), fmaf(c, xv.w - ev.w, g.w));
+        __stcs(reinterpret_cast<float4*>(o + j), r);
+      }
+    } else {
+      for (int j = lane; j < D; j += 32) {
+        float g = gr ? __ldg(gr + j) : 0.f;
+        o[j] = fmaf(c, __ldg(xr + j) - __ldg(er + j), g);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// scalar outputs / EMA / misc
+// ------------------------------------------------------------------------------------------
+__global__ void stats_pack_kernel(const int* __restrict__ counts, const double* __restrict__ sse, long long N,
+                                  int K, int D, float* __restrict__ packed) {
+  float* tail = packed + (size_t)K * D;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K + 2; k += gridDim.x * blockDim.x) {
+    if (k < K) tail[k] = counts ? (float)counts[k] : 0.f;
+    else if (k == K) tail[k] = sse ? (float)(*sse) : 0.f;
+    else tail[k] = (float)N;
+  }
+}
+
+__device__ double block_sum_1024(double v, double* sh) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sh[w];
+  return s;
+}
+
+__global__ void __launch_bounds__(1024) stats_finalize_kernel(const float* __restrict__ packed, int K, int D,
+                                                              float coef_codebook, float coef_commit,
+                                                              float* loss, float* ppl) {
+  __shared__ double sh[32];
+  const float* tail = packed + (size_t)K * D;
+  const float rows = tail[K + 1];
+  double h = 0.0;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float p = tail[k] / rows;                 // avg_probs = mean(encodings, 0)
+    h += (double)(p * logf(p + 1e-10f));
+  }
+  h = block_sum_1024(h, sh);
+  if (threadIdx.x == 0) {
+    if (ppl) *ppl = expf(-(float)h);
+    if (loss) {
+      float mse = (float)((double)tail[K] / ((double)rows * (double)D));
+      *loss = __fadd_rn(__fmul_rn(coef_codebook, mse), __fmul_rn(coef_commit, mse));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024) ema_cs_kernel(float* __restrict__ cs, const float* __restrict__ packed,
+                                                      float decay, float one_m, float eps, float keps,
+                                                      int K, int D) {
+  __shared__ double sh[32];
+  const float* counts = packed + (size_t)K * D;
+  double part = 0.0;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float v = __fadd_rn(__fmul_rn(cs[k], decay), __fmul_rn(one_m, counts[k]));
+    cs[k] = v;
+    part += (double)v;
+  }
+  const float n = (float)block_sum_1024(part, sh);
+  const float den = __fadd_rn(n, keps);
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float v = __fadd_rn(cs[k], eps);
+    cs[k] = __fmul_rn(__fdiv_rn(v, den), n);   // (cs + eps) / (n + K*eps) * n
+  }
+}
+
+__global__ void ema_w_kernel(const float* __restrict__ cs, float* __restrict__ ema_w, const float* E_old,
+                             float* E_new, const float* __restrict__ packed, float decay, float one_m, int K,
+                             int D) {
+  const float* counts = packed + (size_t)K * D;
+  const size_t total = (size_t)K * D;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int k = (int)(i / D);
+    float dw = fmaf(counts[k], E_old[i], packed[i]);   // sum of rows = residual sum + count * code
+    float w = __fadd_rn(__fmul_rn(ema_w[i], decay), __fmul_rn(one_m, dw));
+    ema_w[i] = w;
+    E_new[i] = __fdiv_rn(w, cs[k]);
+  }
+}
+
+__global__ void grad_codebook_kernel(const float* __restrict__ dwr, const float* __restrict__ g_loss,
+                                     float coef_e, size_t total, float* __restrict__ g_E) {
+  const float c = -__ldg(g_loss) * coef_e;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    g_E[i] = c * dwr[i];
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) onehot_kernel(const int* __restrict__ idx, long long N, int K,
+                                                     float* __restrict__ enc) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long stride = (long long)gridDim.x * 8;
+  for (long long row = (long long)blockIdx.x * 8 + warp; row < N; row += stride) {
+    const int k = __ldg(idx + row);
+    float* o = enc + (size_t)row * K;
+    if (VEC) {
+      for (int c = lane * 4; c < K; c += 128) {
+        float4 v = make_float4(c == k ? 1.f : 0.f, c + 1 == k ? 1.f : 0.f, c + 2 == k ? 1.f : 0.f,
+                               c + 3 == k ? 1.f : 0.f);
+        __stcs(reinterpret_cast<float4*>(o + c), v);
+      }
+    } else {
+      for (int c = lane; c < K; c += 32) o[c] = (c == k) ? 1.f : 0.f;
+    }
+  }
+}
+
+template <typename T>
+__global__ void convert_f32_kernel(const T* __restrict__ src, size_t n, float* __restrict__ dst) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = (float)src[i];
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+inline int grid_for(long long work_items, int per_block, int cap_mult) {
+  long long g = (work_items + per_block - 1) / per_block;
+  long long cap = (long long)num_sms() * cap_mult;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+int launch_codebook_prepare(const float* E, int K, int D, void* cb, cudaStream_t st) {
+  const int Kp = round_up(K, 256), Dp = round_up(D, 16);
+  auto* hdr = reinterpret_cast<CbHeader*>(cb);
+  float* e2 = reinterpret_cast<float*>(reinterpret_cast<char*>(cb) + cb_e2_offset());
+  __half* e16 = reinterpret_cast<__half*>(reinterpret_cast<char*>(cb) + cb_e16_offset(K));
+  G2V_CUDA_CHECK(cudaMemsetAsync(hdr, 0, sizeof(CbHeader), st));
+  cb_rows_kernel<<<(Kp * 32 + 255) / 256, 256, 0, st>>>(E, K, D, Kp, hdr, e2);
+  G2V_LAUNCH_CHECK("cb_rows_kernel");
+  cb_header_kernel<<<1, 1, 0, st>>>(hdr, K, D, Kp, Dp);
+  G2V_LAUNCH_CHECK("cb_header_kernel");
+  cb_fp16_kernel<<<grid_for((long long)Kp * Dp, 256, 8), 256, 0, st>>>(E, K, D, Kp, Dp, hdr, e16);
+  G2V_LAUNCH_CHECK("cb_fp16_kernel");
+  return G2V_OK;
+}
+
+int launch_search_simt(const float* z, const float* E, const void* cb, int64_t N, int K, int D,
+                       const int32_t* row_list, const int32_t* row_count, int32_t* idx,
+                       unsigned long long* stats, cudaStream_t st) {
+  const auto* hdr = reinterpret_cast<const CbHeader*>(cb);
+  const float* e2 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_e2_offset());
+  const bool vec = (D % 4 == 0) && aligned16(z) && aligned16(E);
+  const size_t smem = sizeof(SearchSmem);
+  // persistent grid: a few CTAs per SM, each walks row tiles
+  long long tiles = (N + BM - 1) / BM;
+  int grid = (int)((tiles < (long long)num_sms() * 2) ? (tiles > 0 ? tiles : 1) : (long long)num_sms() * 2);
+  if (vec) {
+    G2V_CUDA_CHECK(cudaFuncSetAttribute(search_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    search_simt_kernel<true><<<grid, NT, smem, st>>>(z, E, e2, hdr, N, K, D, row_list, row_count, idx, stats);
+  } else {
+    G2V_CUDA_CHECK(cudaFuncSetAttribute(search_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    search_simt_kernel<false><<<grid, NT, smem, st>>>(z, E, e2, hdr, N, K, D, row_list, row_count, idx, stats);
+  }
+  G2V_LAUNCH_CHECK("search_simt_kernel");
+  return G2V_OK;
+}
+
+int launch_apply(const float* x, const float* zs, const float* E, const int32_t* idx, int64_t N, int K, int D,
+                 float* out, double* sse, int32_t* counts, float* dwr, cudaStream_t st) {
+  const bool vec = (D % 4 == 0) && aligned16(x) && aligned16(E) && (!zs || aligned16(zs)) &&
+                   (!out || aligned16(out)) && (!dwr || aligned16(dwr));
+  const int use_hist = (counts && K <= 8192) ? 1 : 0;
+  const size_t smem = use_hist ? (size_t)K * sizeof(int) : 0;
+  const int grid = grid_for(N, APPLY_WARPS, 8);
+  if (vec)
+    apply_kernel<true><<<grid, APPLY_WARPS * 32, smem, st>>>(x, zs, E, idx, N, K, D, out, sse, counts, dwr, use_hist);
+  else
+    apply_kernel<false><<<grid, APPLY_WARPS * 32, smem, st>>>(x, zs, E, idx, N, K, D, out, sse, counts, dwr, use_hist);
+  G2V_LAUNCH_CHECK("apply_kernel");
+  return G2V_OK;
+}
+
+int launch_stats_pack(const int32_t* counts, const double* sse, int64_t N, int K, int D, float* packed,
+                      cudaStream_t st) {
+  stats_pack_kernel<<<(K + 2 + 255) / 256, 256, 0, st>>>(counts, sse, N, K, D, packed);
+  G2V_LAUNCH_CHECK("stats_pack_kernel");
+  return G2V_OK;
+}
+
+int launch_ema_update(float* cs, float* ema_w, const float* E_old, float* E_new, const float* packed,
+                      float decay, float eps, int K, int D, cudaStream_t st) {
+  const float one_m = (float)(1.0 - (double)decay);
+  const float keps = (float)((double)K * (double)eps);
+  ema_cs_kernel<<<1, 1024, 0, st>>>(cs, packed, decay, one_m, eps, keps, K, D);
+  G2V_LAUNCH_CHECK("ema_cs_kernel");
+  ema_w_kernel<<<grid_for((long long)K * D, 256, 8), 256, 0, st>>>(cs, ema_w, E_old, E_new, packed, decay, one_m, K, D);
+  G2V_LAUNCH_CHECK("ema_w_kernel");
+  return G2V_OK;
+}
+
+int launch_backward(const float* x, const float* E, const int32_t* idx, const float* g_out, const float* g_loss,
+                    float coef_x, int64_t N, int K, int D, float* g_x, cudaStream_t st) {
+  const bool vec = (D % 4 == 0) && aligned16(x) && aligned16(E) && aligned16(g_x) && (!g_out || aligned16(g_out));
+  const int grid = grid_for(N, 8, 8);
+  if (vec) backward_kernel<true><<<grid, 256, 0, st>>>(x, E, idx, g_out, g_loss, coef_x, N, K, D, g_x);
+  else backward_kernel<false><<<grid, 256, 0, st>>>(x, E, idx, g_out, g_loss, coef_x, N, K, D, g_x);
+  G2V_LAUNCH_CHECK("backward_kernel");
+  return G2V_OK;
+}
+
+int launch_grad_codebook(const float* dwr, const float* g_loss, float coef_e, int K, int D, float* g_E,
+                         cudaStream_t st) {
+  const size_t total = (size_t)K * D;
+  grad_codebook_kernel<<<grid_for((long long)total, 256, 8), 256, 0, st>>>(dwr, g_loss, coef_e, total, g_E);
+  G2V_LAUNCH_CHECK("grad_codebook_kernel");
+  return G2V_OK;
+}
+
+int launch_onehot(const int32_t* idx, int64_t N, int K, float* enc, cudaStream_t st) {
+  const bool vec = (K % 4 == 0) && aligned16(enc);
+  const int grid = grid_for(N, 8, 16);
+  if (vec) onehot_kernel<true><<<grid, 256, 0, st>>>(idx, N, K, enc);
+  else onehot_kernel<false><<<grid, 256, 0, st>>>(idx, N, K, enc);
+  G2V_LAUNCH_CHECK("onehot_kernel");
+  return G2V_OK;
+}
+
+int launch_convert_rows_f32(const void* src, int dtype, int64_t n, float* dst, cudaStream_t st) {
+  const int grid = grid_for(n, 256 * 4, 16);
+  if (dtype == G2V_BF16)
+    convert_f32_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), (size_t)n, dst);
+  else if (dtype == G2V_F16)
+    convert_f32_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(src), (size_t)n, dst);
+  else
+    return G2V_ERR_DTYPE;
+  G2V_LAUNCH_CHECK("convert_f32_kernel");
+  return G2V_OK;
+}
+
+int launch_stats_finalize(const float* packed, int K, int D, float coef_codebook, float coef_commit,
+                          float* loss, float* ppl, cudaStream_t st) {
+  stats_finalize_kernel<<<1, 1024, 0, st>>>(packed, K, D, coef_codebook, coef_commit, loss, ppl);
+  G2V_LAUNCH_CHECK("stats_finalize_kernel");
+  return G2V_OK;
+}
+
+}  // namespace g2v

@@ -1,0 +1,242 @@
+"""Drop-in replacements for the reference's hard quantizer modules.
+
+Same class names, constructor arguments, attribute names (= state_dict keys), forward
+contract ``forward(inputs) -> (loss, quantized, perplexity, encodings)`` and train/eval
+semantics as
+
+  flavour "vqvae":  scripts/model/Autoencoder_VQVAE_model.py  VQ_Payam :1088, VQ_Payam_EMA :1182,
+                    VectorQuantizerEMA :1713
+  flavour "dae":    scripts/model/DAE_model.py                VQ_Payam :277,  VQ_Payam_EMA :351
+
+but the arithmetic runs in the sm_100a CUDA library behind include/g2v_vq.h.  Inputs must be
+CUDA tensors (CPU tensors are moved to the module's device and the results moved back, which
+keeps the DataLoader-worker call site lmdb_data_loader.py:1280 working on a GPU box); there is
+no CPU implementation here.
+
+Differences from the reference that are not observable through the interface:
+  * `_ema_w` / `_embedding.weight` keep their Parameter identity; their `.data` is re-pointed
+    to a fresh tensor each EMA step (the reference re-creates the Parameters, :1276-1282);
+  * `encodings` is built by a scatter kernel from the int32 indices (also kept on the module
+    as `last_indices`), not by scatter_ into torch.zeros.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from . import functional as F
+
+
+class _HardQuantizerBase(nn.Module):
+    #: set by subclasses
+    _ema: bool = False
+
+    def _init_common(self, num_embeddings: int, embedding_dim: int, commitment_cost: float):
+        self._embedding_dim = int(embedding_dim)
+        self._num_embeddings = int(num_embeddings)
+        self._commitment_cost = float(commitment_cost)
+        # non-persistent runtime state
+        self._cb: Optional[torch.Tensor] = None          # prepared codebook aux buffer
+        self._cb_key = None                              # (data_ptr, _version, device) it was built for
+        self.search_flags: int = _lib.ALGO_AUTO
+        self.return_encodings: bool = True               # dense one-hot like the reference
+        self.last_indices: Optional[torch.Tensor] = None
+        # data-parallel EMA: callable(packed fp32 tensor) doing an in-place sum all-reduce
+        self.stats_reduce: Optional[Callable[[torch.Tensor], None]] = None
+        self.grad_scale: float = 1.0
+
+    # -- reference API -------------------------------------------------------------------------
+    def embedding_grad(self, what: bool) -> None:
+        """Autoencoder_VQVAE_model.py:1110-1113."""
+        for param in self._embedding.parameters():
+            param.requires_grad = what
+
+    # -- helpers -------------------------------------------------------------------------------
+    def _codebook(self, dev: torch.device) -> Tuple[torch.Tensor, torch.Tensor]:
+        W = self._embedding.weight
+        if W.device != dev:
+            raise RuntimeError(f"quantizer codebook is on {W.device}, inputs on {dev}")
+        E = W.detach()
+        if E.dtype != torch.float32 or not E.is_contiguous():
+            raise RuntimeError("codebook must be a contiguous fp32 tensor")
+        key = (E.data_ptr(), W._version, str(dev))
+        if self._cb is None or self._cb_key != key:
+            self._cb = F.prepare_codebook(E, self._cb)
+            self._cb_key = key
+        return W, self._cb
+
+    def invalidate_codebook_cache(self) -> None:
+        self._cb_key = None
+
+    def _search_rows(self, flat: torch.Tensor) -> Optional[torch.Tensor]:
+        """Rows the search (and the EMA sums) run on, if different from the raw rows."""
+        return None
+
+    def _run(self, inputs: torch.Tensor):
+        if inputs.numel() % self._embedding_dim:
+            raise RuntimeError(
+                f"shape '[-1, {self._embedding_dim}]' is invalid for input of size {inputs.numel()}")
+        src_dev = inputs.device
+        W0 = self._embedding.weight
+        if not inputs.is_cuda:
+            if not W0.is_cuda:
+                raise RuntimeError(
+                    "gesture2vec_b200 quantizers run on a CUDA device only: move the module to a "
+                    "B200 (`.cuda()`); there is no CPU implementation of this path")
+            inputs = inputs.to(W0.device)
+        if inputs.dtype != torch.float32:
+            inputs = inputs.float()
+        flat = inputs.contiguous().view(-1, self._embedding_dim)          # a1: inputs.view(-1, D)
+        W, cb = self._codebook(flat.device)
+        with torch.no_grad():
+            zs = self._search_rows(flat.detach())
+        training_ema = self._ema and self.training
+        want_dwr = training_ema or (not self._ema and W.requires_grad and torch.is_grad_enabled())
+        reduce_fn = self.stats_reduce if training_ema else None
+        E_arg = W if (not self._ema) else W.detach()
+        loss, out, ppl, idx, packed = F.quantize(
+            flat, E_arg, zs=zs, cb=cb, beta=self._commitment_cost,
+            coef_codebook=0.0 if self._ema else 1.0, want_dwr=want_dwr, reduce_fn=reduce_fn,
+            grad_scale=self.grad_scale, flags=self.search_flags)
+        if training_ema:
+            self._ema_step(W, packed)
+        self.last_indices = idx
+        quantized = out.view(inputs.shape)
+        enc = F.one_hot(idx, self._num_embeddings) if self.return_encodings else idx.long().unsqueeze(1)
+        if src_dev != quantized.device:
+            loss, quantized, ppl, enc = (t.to(src_dev) for t in (loss, quantized, ppl, enc))
+        return loss, quantized, ppl, enc
+
+    def _ema_step(self, W: nn.Parameter, packed: torch.Tensor) -> None:
+        with torch.no_grad():
+            E_old = W.data
+            E_new = torch.empty_like(E_old)
+            w_old = self._ema_w.data
+            if not (w_old.is_contiguous() and self._ema_cluster_size.is_contiguous()):
+                raise RuntimeError("EMA state must be contiguous")
+            w_new = w_old.clone()         # the reference also produces a fresh _ema_w tensor
+            cs = self._ema_cluster_size.clone()
+            F.ema_update(cs, w_new, E_old, E_new, packed, self._decay, self._epsilon, self._cb)
+            self._ema_cluster_size = cs   # registered buffer: assignment keeps it registered
+            self._ema_w.data = w_new
+            W.data = E_new
+            self._cb_key = (E_new.data_ptr(), W._version, str(E_new.device))
+
+    def tokenize(self, inputs: torch.Tensor) -> torch.Tensor:
+        """Bulk path: int32 code ids for the rows of `inputs`, no one-hot / gather / loss."""
+        flat = inputs.contiguous().view(-1, self._embedding_dim)
+        W, cb = self._codebook(flat.device)
+        zs = self._search_rows(flat) if flat.dtype == torch.float32 else None
+        return F.vq_search(flat if zs is None else zs, W.detach(), cb, flags=self.search_flags)
+
+    def forward(self, inputs: torch.Tensor):
+        return self._run(inputs)
+
+
+# ================================================================================================
+# flavour "dae": scripts/model/DAE_model.py
+# ================================================================================================
+class DAE_VQ_Payam(_HardQuantizerBase):
+    """DAE_model.py:277-348.  state_dict: `_embedding.weight`."""
+
+    def __init__(self, num_embeddings: int, embedding_dim: int, commitment_cost: float):
+        super().__init__()
+        self._init_common(num_embeddings, embedding_dim, commitment_cost)
+        self._embedding = nn.Embedding(self._num_embeddings, self._embedding_dim)
+        self._embedding.weight.data.uniform_(-1 / self._num_embeddings, 1 / self._num_embeddings)
+
+
+class DAE_VQ_Payam_EMA(_HardQuantizerBase):
+    """DAE_model.py:351-482.  state_dict: `pre_linear.*`, `_embedding.weight`, `_ema_w`,
+    `_ema_cluster_size`.  pre_linear exists but is unused (:419)."""
+    _ema = True
+
+    def __init__(self, num_embeddings: int, embedding_dim: int, commitment_cost: float, decay: float,
+                 epsilon: float = 1e-5):
+        super().__init__()
+        self._init_common(num_embeddings, embedding_dim, commitment_cost)
+        self.pre_linear = nn.Linear(self._embedding_dim, self._embedding_dim)
+        self._embedding = nn.Embedding(self._num_embeddings, self._embedding_dim)
+        self._embedding.weight.data.uniform_(-1 / self._num_embeddings, 1 / self._num_embeddings)
+        self.register_buffer("_ema_cluster_size", torch.zeros(num_embeddings))
+        self._ema_w = nn.Parameter(torch.Tensor(num_embeddings, self._embedding_dim))
+        self._ema_w.data.normal_()
+        self._decay = decay
+        self._epsilon = epsilon
+
+
+# ================================================================================================
+# flavour "vqvae": scripts/model/Autoencoder_VQVAE_model.py
+# ================================================================================================
+class VQVAE_VQ_Payam(_HardQuantizerBase):
+    """Autoencoder_VQVAE_model.py:1088-1174.  Owns an unused pre_linear (:1099); E ~ N(0,1) (:1104)."""
+
+    def __init__(self, num_embeddings: int, embedding_dim: int, commitment_cost: float):
+        super().__init__()
+        self._init_common(num_embeddings, embedding_dim, commitment_cost)
+        self.pre_linear = nn.Linear(self._embedding_dim, self._embedding_dim)
+        self._embedding = nn.Embedding(self._num_embeddings, self._embedding_dim)
+        self._embedding.weight.data.normal_()
+
+
+class VQVAE_VQ_Payam_EMA(_HardQuantizerBase):
+    """Autoencoder_VQVAE_model.py:1182-1296.  The search and the EMA sums run on pre_linear(z)
+    (:1230, :1275); the loss and the straight-through value use the raw inputs (:1285, :1292).
+    E ~ U(-1,1) (:1204)."""
+    _ema = True
+
+    def __init__(self, num_embeddings: int, embedding_dim: int, commitment_cost: float, decay: float,
+                 epsilon: float = 1e-5):
+        super().__init__()
+        self._init_common(num_embeddings, embedding_dim, commitment_cost)
+        self.pre_linear = nn.Linear(self._embedding_dim, self._embedding_dim)
+        self._embedding = nn.Embedding(self._num_embeddings, self._embedding_dim)
+        self._embedding.weight.data.uniform_(-1, 1)
+        self.register_buffer("_ema_cluster_size", torch.zeros(num_embeddings))
+        self._ema_w = nn.Parameter(torch.Tensor(num_embeddings, self._embedding_dim))
+        self._ema_w.data.normal_()
+        self._decay = decay
+        self._epsilon = epsilon
+
+    def _search_rows(self, flat: torch.Tensor) -> Optional[torch.Tensor]:
+        # plain library GEMM (cuBLAS through torch); no gradient reaches pre_linear
+        return torch.nn.functional.linear(flat, self.pre_linear.weight.detach(),
+                                          self.pre_linear.bias.detach()).contiguous()
+
+
+class VectorQuantizerEMA(_HardQuantizerBase):
+    """Autoencoder_VQVAE_model.py:1713-1812 (never instantiated by the reference; kept for parity).
+
+    inputs [2, B, H] -> hstack(inputs[0], inputs[1]) [B, 2H] -> pre_lin -> EMA VQ on the projected
+    rows (loss and STE DO use the projection here) -> literal reshape to (2, B, -1) (:1810)."""
+    _ema = True
+
+    def __init__(self, num_embeddings: int, embedding_dim: int, commitment_cost: float, decay: float,
+                 epsilon: float = 1e-5):
+        super().__init__()
+        self._init_common(num_embeddings, embedding_dim, commitment_cost)
+        self.pre_lin = nn.Linear(self._embedding_dim, self._embedding_dim)
+        self._embedding = nn.Embedding(self._num_embeddings, self._embedding_dim)
+        self._embedding.weight.data.normal_()
+        self.register_buffer("_ema_cluster_size", torch.zeros(num_embeddings))
+        self._ema_w = nn.Parameter(torch.Tensor(num_embeddings, self._embedding_dim))
+        self._ema_w.data.normal_()
+        self._decay = decay
+        self._epsilon = epsilon
+
+    def forward(self, inputs: torch.Tensor):
+        rows = torch.hstack((inputs[0], inputs[1]))
+        rows = self.pre_lin(rows)                       # differentiable: grads reach pre_lin here
+        loss, quantized, ppl, enc = self._run(rows)
+        quantized = torch.reshape(quantized, (2, quantized.shape[0], -1)).contiguous()
+        return loss, quantized, ppl, enc
+
+
+FLAVOURS = {
+    "dae": {"VQ_Payam": DAE_VQ_Payam, "VQ_Payam_EMA": DAE_VQ_Payam_EMA},
+    "vqvae": {"VQ_Payam": VQVAE_VQ_Payam, "VQ_Payam_EMA": VQVAE_VQ_Payam_EMA,
+              "VectorQuantizerEMA": VectorQuantizerEMA},
+}

@@ -1,0 +1,162 @@
+/* g2v_vq.h -- C ABI of the B200 (sm_100a) vector-quantizer hot path.
+ *
+ * This is the drop-in boundary for the quantizer layer of pjyazdian/Gesture2Vec.
+ * The reference has no FFI: its quantizers are eager PyTorch modules.  Each entry
+ * point below names the reference statements (file:line under
+ * /root/reference/scripts/model/) whose work it replaces; the Python modules in
+ * gesture2vec_b200/quantizers.py bind these through ctypes and keep the
+ * reference's nn.Module interface.  See INTEGRATION.md for the binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
+ *     parameter name ends in _host;
+ *   - all work is enqueued on the caller's stream (cudaStream_t passed as void*);
+ *     nothing synchronises the device except the *_host entry point;
+ *   - the library allocates no persistent device memory: scratch comes from the
+ *     caller through (ws, ws_bytes), sized by g2v_workspace_bytes();
+ *   - return value: 0 = ok, negative = error (g2v_strerror); never throws/exits;
+ *   - row-major fp32 everywhere unless a dtype code says otherwise; rows of z/x/out
+ *     are contiguous with stride D; the codebook E is [K, D].
+ */
+#ifndef G2V_VQ_H_
+#define G2V_VQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G2V_VERSION 100
+
+/* error codes */
+#define G2V_OK 0
+#define G2V_ERR_INVALID (-1)    /* null pointer / non-positive size / bad flag */
+#define G2V_ERR_ALIGN (-2)      /* pointer not aligned as required             */
+#define G2V_ERR_DTYPE (-3)      /* unsupported dtype code                      */
+#define G2V_ERR_WORKSPACE (-4)  /* workspace / codebook-aux buffer too small   */
+#define G2V_ERR_CUDA (-5)       /* a CUDA call failed (g2v_last_error_detail)  */
+#define G2V_ERR_ARCH (-6)       /* device is not sm_100                        */
+#define G2V_ERR_UNSUPPORTED (-7)/* shape outside what the selected path covers */
+
+/* dtype codes for the search rows */
+#define G2V_F32 0
+#define G2V_BF16 1
+#define G2V_F16 2
+
+/* flags for g2v_vq_search */
+#define G2V_ALGO_AUTO 0u        /* tcgen05 path when the shape allows, else SIMT */
+#define G2V_ALGO_SIMT 1u        /* fp32 CUDA-core path (any K, D)                */
+#define G2V_ALGO_TC 2u          /* tcgen05 tensor-core path, error if unsupported */
+#define G2V_ALGO_MASK 3u
+#define G2V_NO_RECHECK 4u       /* keep the fast-pass winner (bf16/fp16 "fast" variant) */
+
+/* slots of the optional int64 search_stats[8] output */
+#define G2V_STAT_ROWS 0         /* rows searched                                      */
+#define G2V_STAT_PAIR_RECHECK 1 /* rows whose top-2 were re-ranked exactly (fp64)     */
+#define G2V_STAT_FULL_RECHECK 2 /* rows whose whole distance row was recomputed (fp64) */
+#define G2V_STAT_FALLBACK_ROWS 3/* rows the tensor-core pass handed to the fp32 path   */
+
+int g2v_version(void);
+const char* g2v_strerror(int code);
+/* text of the last failure on the calling thread (CUDA error string etc.) */
+const char* g2v_last_error_detail(void);
+
+/* Codebook auxiliary data (||e||^2 in fp32 rounded from fp64, norm maxima for the
+ * error bounds, and the fp16 operand copy the tensor-core path streams by TMA).
+ * Must be re-prepared whenever E changes.  Replaces torch.sum(weight**2, dim=1)
+ * (DAE_model.py:322,425; Autoencoder_VQVAE_model.py:1134,1236). */
+size_t g2v_codebook_bytes(int K, int D);
+int g2v_codebook_prepare(const float* E, int K, int D, void* cb, size_t cb_bytes, void* stream);
+
+/* Which search path the flags select for this shape: G2V_ALGO_SIMT or G2V_ALGO_TC
+ * (negative error if G2V_ALGO_TC is forced on a shape it does not cover). */
+int g2v_search_path(int K, int D, unsigned flags);
+
+/* Scratch needed by g2v_vq_search for N rows. */
+size_t g2v_workspace_bytes(int64_t N, int K, int D, int z_dtype, unsigned flags);
+
+/* Nearest-code search: idx[n] = argmin_k ||z_n - e_k||^2, first index on exact ties.
+ * Replaces the distance matrix + argmin (DAE_model.py:320-327, 423-434;
+ * Autoencoder_VQVAE_model.py:1132-1142, 1234-1244, 1760-1767) without materialising
+ * the [N,K] distances.  Every path is a fast pass with a known error bound followed
+ * by an exact (fp64) re-rank of the rows whose top candidates are closer than that
+ * bound, so the result is the exact-arithmetic argmin.
+ *   z          [N,D] rows in z_dtype
+ *   E, cb      fp32 codebook [K,D] and its prepared aux buffer
+ *   idx        out, int32 [N]
+ *   search_stats  optional int64[8], ACCUMULATED (caller zeroes)                      */
+int g2v_vq_search(const void* z, int z_dtype, const float* E, const void* cb,
+                  int64_t N, int K, int D, int32_t* idx, int64_t* search_stats,
+                  void* ws, size_t ws_bytes, unsigned flags, void* stream);
+
+/* Gather + straight-through value + loss/EMA statistics in one pass over the rows.
+ * Replaces the one-hot GEMM gather, both mse_loss reductions, the STE add, the
+ * column sums of the one-hot and encodings^T @ flat_input
+ * (DAE_model.py:334-345, 445-464; Autoencoder_VQVAE_model.py:1151-1170, 1256-1275).
+ *   x       [N,D] fp32 rows the loss/STE are taken against (raw inputs)
+ *   zs      [N,D] fp32 rows the EMA sums are taken over (NULL -> x; differs only for
+ *           Autoencoder_VQVAE_model.VQ_Payam_EMA which searches on pre_linear(x), :1230)
+ *   out     optional [N,D]: x + (E[idx] - x)
+ *   sse     optional double[1], accumulated: sum (E[idx]-x)^2
+ *   counts  optional int32[K], accumulated: rows per code
+ *   dwr     optional fp32 [K,D], accumulated: sum_{n: idx=k} (zs_n - e_k)  (the EMA sum
+ *           encodings^T @ flat_input minus counts*E; residual form keeps grad_E accurate) */
+int g2v_vq_apply(const float* x, const float* zs, const float* E, const int32_t* idx,
+                 int64_t N, int K, int D, float* out, double* sse, int32_t* counts,
+                 float* dwr, void* stream);
+
+/* Pack the per-step statistics into ONE fp32 buffer for the data-parallel all-reduce:
+ * packed = [ dwr (K*D) | counts (K) | sse (1) | rows (1) ], K*D+K+2 floats.  dwr is
+ * expected to already live at packed[0 .. K*D) (pass that pointer to g2v_vq_apply). */
+int g2v_vq_stats_pack(const int32_t* counts, const double* sse, int64_t N, int K, int D,
+                      float* packed, void* stream);
+
+/* mse = sse/(rows*D); loss = coef_codebook*mse + coef_commit*mse; perplexity =
+ * exp(-sum p log(p+1e-10)), p = counts/rows -- from a (possibly all-reduced) packed buffer.
+ * Replaces DAE_model.py:340-347, 474-481.  (coef_codebook, coef_commit) = (1, beta) for
+ * VQ_Payam and (0, beta) for VQ_Payam_EMA.  loss / perplexity are device scalars. */
+int g2v_vq_stats_finalize(const float* packed, int K, int D, float coef_codebook, float coef_commit,
+                          float* loss, float* perplexity, void* stream);
+
+/* EMA codebook update from a packed statistics buffer; cluster_size and ema_w are updated in
+ * place, the new codebook goes to E_new (E_new == E_old is allowed; a separate buffer keeps the
+ * old codes alive for the backward pass, as the reference's re-created Parameter does).  Replaces
+ * DAE_model.py:451-471 / Autoencoder_VQVAE_model.py:1262-1282, 1777-1797:
+ *   cs <- cs*decay + (1-decay)*counts ; n = sum cs ; cs <- (cs+eps)/(n+K*eps)*n
+ *   ema_w <- ema_w*decay + (1-decay)*dw ; E <- ema_w / cs[:,None]      (dw = dwr + counts*E)
+ * If cb != NULL the aux buffer is re-prepared for E_new on the same stream. */
+int g2v_vq_ema_update(float* cluster_size, float* ema_w, const float* E_old, float* E_new,
+                      const float* packed, float decay, float eps, int K, int D, void* cb,
+                      size_t cb_bytes, void* stream);
+
+/* Backward of the layer wrt the inputs (closed form of the autograd graph the reference
+ * builds):  g_x = g_out + g_loss[0]*coef_x*(x - E[idx]),
+ * coef_x = 2*beta/(N*D).  g_out may be NULL (no gradient through `quantized`). */
+int g2v_vq_backward(const float* x, const float* E, const int32_t* idx, const float* g_out,
+                    const float* g_loss, float coef_x, int64_t N, int K, int D, float* g_x,
+                    void* stream);
+
+/* VQ_Payam only: g_E[k] = -g_loss[0]*coef_e*dwr[k], coef_e = 2/(N*D)
+ * (the gradient the reference gets through the one-hot GEMM, DAE_model.py:334-341). */
+int g2v_vq_grad_codebook(const float* packed_dwr, const float* g_loss, float coef_e,
+                         int K, int D, float* g_E, void* stream);
+
+/* encodings = one_hot(idx) as a dense fp32 [N,K] (DAE_model.py:328-331); the reference
+ * returns it and callers argmax it (Clustering.py:156, lmdb_data_loader.py:1281). */
+int g2v_onehot(const int32_t* idx, int64_t N, int K, float* enc, void* stream);
+
+/* End-to-end tokenisation with HOST buffers (the batched form of Clustering.py:102-166):
+ * copies z_host -> device in chunks, searches, copies idx back; copies and kernels overlap
+ * on internal streams; returns after everything completed.  z_host/idx_host should be
+ * pinned for full PCIe rate.  ws must hold g2v_tokenize_host_bytes(). */
+size_t g2v_tokenize_host_bytes(int64_t chunk_rows, int K, int D, int z_dtype, unsigned flags);
+int g2v_tokenize_host(const void* z_host, int z_dtype, int64_t N, const float* E, const void* cb,
+                      int K, int D, int32_t* idx_host, int64_t chunk_rows, int64_t* search_stats_host,
+                      void* ws, size_t ws_bytes, unsigned flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G2V_VQ_H_ */
