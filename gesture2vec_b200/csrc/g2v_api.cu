@@ -94,7 +94,7 @@ size_t g2v_codebook_bytes(int K, int D) {
 int g2v_codebook_prepare(const float* E, int K, int D, void* cb, size_t cb_bytes, void* stream) {
   if (!E || !cb || K <= 0 || D <= 0) return G2V_ERR_INVALID;
   if (cb_bytes < cb_total_bytes(K, D)) return G2V_ERR_WORKSPACE;
-  if (reinterpret_cast<uintptr_t>(cb) & 1023) return G2V_ERR_ALIGN;
+  if (reinterpret_cast<uintptr_t>(cb) & 255) return G2V_ERR_ALIGN;
   int rc = check_arch();
   if (rc) return rc;
   return launch_codebook_prepare(E, K, D, cb, (cudaStream_t)stream);

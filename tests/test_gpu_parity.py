@@ -305,8 +305,11 @@ def test_large_n_properties():
     # (5) residual sums: dwr[k] + counts[k]*E[k] == sum of the rows assigned to k
     dwr = packed[:K * D].view(K, D)
     dw = torch.zeros(K, D, device=_dev(), dtype=torch.float64).index_add_(0, idx.long(), z.double())
-    np.testing.assert_allclose((dwr.double() + counts.double()[:, None] * E.double()).cpu().numpy(),
-                               dw.cpu().numpy(), rtol=1e-4, atol=1e-2)
+    #     (fp32 atomics: with iid latents a few low-norm codes attract >1e5 rows, so the
+    #      tolerance is relative to each code's largest sum, not elementwise)
+    got = (dwr.double() + counts.double()[:, None] * E.double())
+    err = (got - dw).abs().amax(dim=1)
+    assert bool((err <= 2e-4 * dw.abs().amax(dim=1) + 1e-3).all()), float((err / dw.abs().amax(dim=1)).max())
     assert mse.item() > 0
 
 
