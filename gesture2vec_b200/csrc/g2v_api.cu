@@ -56,12 +56,6 @@ static inline bool bad_shape(int64_t N, int K, int D) { return N < 0 || K <= 0 |
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int elem_size(int dtype) { return dtype == G2V_F32 ? 4 : 2; }
 
-// workspace of g2v_vq_search:  [stats 64 B][fp32 copy of z when the SIMT path gets 16-bit rows]
-//                              [tensor-core scratch]
-static size_t simt_convert_bytes(int64_t N, int D, int z_dtype) {
-  return z_dtype == G2V_F32 ? 0 : align_up((size_t)N * D * 4, 256);
-}
-
 }  // namespace g2v
 
 using namespace g2v;
@@ -114,7 +108,6 @@ size_t g2v_workspace_bytes(int64_t N, int K, int D, int z_dtype, unsigned flags)
   unsigned algo = flags & G2V_ALGO_MASK;
   bool tc = (algo == G2V_ALGO_TC) || (algo == G2V_ALGO_AUTO && tc_supported(K, D));
   if (tc) b += align_up(tc_workspace_bytes(N, K, D, z_dtype), 256);
-  b += simt_convert_bytes(N, D, z_dtype);  // used by the SIMT path and by the TC path's fp32 second stage
   return b;
 }
 
@@ -138,20 +131,8 @@ int g2v_vq_search(const void* z, int z_dtype, const float* E, const void* cb, in
     return G2V_ERR_UNSUPPORTED;
   }
   bool tc = (algo == G2V_ALGO_TC) || (algo == G2V_ALGO_AUTO && tc_supported(K, D));
-  if (tc) {
-    size_t tcb = align_up(tc_workspace_bytes(N, K, D, z_dtype), 256);
-    (void)tcb;
-    rc = launch_search_tc(z, z_dtype, E, cb, N, K, D, idx, stats, p, ws_bytes - 256, flags, st);
-    return rc;
-  }
-  const float* z32 = reinterpret_cast<const float*>(z);
-  if (z_dtype != G2V_F32) {
-    float* tmp = reinterpret_cast<float*>(p);
-    rc = launch_convert_rows_f32(z, z_dtype, N * D, tmp, st);
-    if (rc) return rc;
-    z32 = tmp;
-  }
-  return launch_search_simt(z32, E, cb, N, K, D, nullptr, nullptr, idx, stats, st);
+  if (tc) return launch_search_tc(z, z_dtype, E, cb, N, K, D, idx, stats, p, ws_bytes - 256, flags, st);
+  return launch_search_simt(z, z_dtype, E, cb, N, K, D, nullptr, nullptr, idx, stats, st);
 }
 
 int g2v_vq_apply(const float* x, const float* zs, const float* E, const int32_t* idx, int64_t N, int K, int D,

@@ -21,10 +21,11 @@ struct CbHeader {
   float e2max;      // max_k ||e_k||^2
   float q4max;      // max_k (sum_j e_kj^4)^(1/2)    (variance bound of the fp16 rounding error)
   float amax;       // max |e_kj|
-  float scale_e;    // power of two the fp16 copy was multiplied by (1 unless amax is huge/tiny)
+  float scale_e;    // power of two the fp16 copy was multiplied by (brings amax into [256,512))
   int K, D, Kp, Dp;
   int magic;
-  int pad[55];
+  float smax;       // max_k || e_k - fp16(e_k*scale_e)/scale_e ||_2   (rounding residual of the fp16 copy)
+  int pad[54];
 };
 static_assert(sizeof(CbHeader) == 256, "CbHeader must be 256 bytes");
 constexpr int kCbMagic = 0x67327631;  // "g2v1"
@@ -58,7 +59,7 @@ int num_sms();
 int launch_codebook_prepare(const float* E, int K, int D, void* cb, cudaStream_t st);
 // fp32 CUDA-core search over all rows (row_list == nullptr) or over the rows listed in
 // row_list[0 .. *row_count).
-int launch_search_simt(const float* z, const float* E, const void* cb, int64_t N, int K, int D,
+int launch_search_simt(const void* z, int z_dtype, const float* E, const void* cb, int64_t N, int K, int D,
                        const int32_t* row_list, const int32_t* row_count, int32_t* idx,
                        unsigned long long* stats, cudaStream_t st);
 int launch_apply(const float* x, const float* zs, const float* E, const int32_t* idx, int64_t N, int K,
@@ -75,7 +76,6 @@ int launch_backward(const float* x, const float* E, const int32_t* idx, const fl
 int launch_grad_codebook(const float* dwr, const float* g_loss, float coef_e, int K, int D, float* g_E,
                          cudaStream_t st);
 int launch_onehot(const int32_t* idx, int64_t N, int K, float* enc, cudaStream_t st);
-int launch_convert_rows_f32(const void* src, int dtype, int64_t n_elems, float* dst, cudaStream_t st);
 
 // ---- tensor-core path, implemented in g2v_tc.cu ---------------------------------------------
 bool tc_supported(int K, int D);

@@ -87,15 +87,24 @@ __global__ void cb_header_kernel(CbHeader* hdr, int K, int D, int Kp, int Dp) {
   hdr->magic = kCbMagic;
 }
 
-__global__ void cb_fp16_kernel(const float* __restrict__ E, int K, int D, int Kp, int Dp,
-                               const CbHeader* __restrict__ hdr, __half* __restrict__ E16) {
-  float sc = hdr->scale_e;
-  size_t total = (size_t)Kp * Dp;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int k = (int)(i / Dp), j = (int)(i % Dp);
-    float v = (k < K && j < D) ? E[(size_t)k * D + j] * sc : 0.f;
-    E16[i] = __float2half_rn(v);
+// fp16 operand copy of the codebook (one warp per code) + the norm of its rounding residual
+__global__ void cb_fp16_kernel(const float* __restrict__ E, int K, int D, int Kp, int Dp, CbHeader* hdr,
+                               __half* __restrict__ E16) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= Kp) return;
+  const float sc = hdr->scale_e, inv = 1.f / sc;   // power of two: exact
+  __half* o = E16 + (size_t)warp * Dp;
+  float s2 = 0.f;
+  for (int j = lane; j < Dp; j += 32) {
+    float v = (warp < K && j < D) ? E[(size_t)warp * D + j] : 0.f;
+    __half h = __float2half_rn(v * sc);
+    float r = v - __half2float(h) * inv;
+    s2 = fmaf(r, r, s2);
+    o[j] = h;
   }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+  if (lane == 0 && warp < K) atomicMax(reinterpret_cast<int*>(&hdr->smax), __float_as_int(sqrtf(s2) * 1.0001f));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -115,28 +124,40 @@ struct SearchSmem {
   int red_i[NT / 32];
 };
 
-template <bool VEC>
-__device__ __forceinline__ void load8(const float* __restrict__ base, long long row, int D, int col,
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// 8 consecutive elements of a row (fp32 / fp16 / bf16 storage) as fp32; zero beyond D or for row < 0
+template <bool VEC, typename T>
+__device__ __forceinline__ void load8(const T* __restrict__ base, long long row, int D, int col,
                                       float (&v)[8]) {
   if (row < 0) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = 0.f;
     return;
   }
-  const float* p = base + (size_t)row * D + col;
+  const T* p = base + (size_t)row * D + col;
   if (VEC && col + 8 <= D) {
-    float4 a = ldg4(p), b = ldg4(p + 4);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    if constexpr (sizeof(T) == 4) {
+      float4 a = ldg4(reinterpret_cast<const float*>(p)), b = ldg4(reinterpret_cast<const float*>(p) + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+      v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+      uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
+      const T* h = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = to_f32(h[i]);
+    }
   } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = (col + i < D) ? __ldg(p + i) : 0.f;
+    for (int i = 0; i < 8; ++i) v[i] = (col + i < D) ? to_f32(p[i]) : 0.f;
   }
 }
 
-template <bool VEC>
+template <bool VEC, typename ZT>
 __global__ void __launch_bounds__(NT) search_simt_kernel(
-    const float* __restrict__ z, const float* __restrict__ E, const float* __restrict__ e2,
+    const ZT* __restrict__ z, const float* __restrict__ E, const float* __restrict__ e2,
     const CbHeader* __restrict__ hdr, long long N, int K, int D, const int* __restrict__ row_list,
     const int* __restrict__ row_count, int* __restrict__ idx_out, unsigned long long* stats) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -280,14 +301,14 @@ __global__ void __launch_bounds__(NT) search_simt_kernel(
     const int nflag = S.nflag;
     for (int f = 0; f < nflag; ++f) {
       const int g = S.rows[S.flagged[f]];
-      const float* zr = z + (size_t)g * D;
+      const ZT* zr = z + (size_t)g * D;
       double best = INFINITY;
       int besti = 0x7fffffff;
       for (int k = t; k < K; k += NT) {
         const float* er = E + (size_t)k * D;
         double s = 0.0;
         for (int j = 0; j < D; ++j) {
-          double df = (double)__ldg(zr + j) - (double)__ldg(er + j);
+          double df = (double)to_f32(zr[j]) - (double)__ldg(er + j);
           s = fma(df, df, s);
         }
         if (s < best) { best = s; besti = k; }
@@ -528,12 +549,6 @@ __global__ void __launch_bounds__(256) onehot_kernel(const int* __restrict__ idx
   }
 }
 
-template <typename T>
-__global__ void convert_f32_kernel(const T* __restrict__ src, size_t n, float* __restrict__ dst) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    dst[i] = (float)src[i];
-}
-
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 inline int grid_for(long long work_items, int per_block, int cap_mult) {
   long long g = (work_items + per_block - 1) / per_block;
@@ -558,30 +573,43 @@ int launch_codebook_prepare(const float* E, int K, int D, void* cb, cudaStream_t
   G2V_LAUNCH_CHECK("cb_rows_kernel");
   cb_header_kernel<<<1, 1, 0, st>>>(hdr, K, D, Kp, Dp);
   G2V_LAUNCH_CHECK("cb_header_kernel");
-  cb_fp16_kernel<<<grid_for((long long)Kp * Dp, 256, 8), 256, 0, st>>>(E, K, D, Kp, Dp, hdr, e16);
+  cb_fp16_kernel<<<(Kp * 32 + 255) / 256, 256, 0, st>>>(E, K, D, Kp, Dp, hdr, e16);
   G2V_LAUNCH_CHECK("cb_fp16_kernel");
   return G2V_OK;
 }
 
-int launch_search_simt(const float* z, const float* E, const void* cb, int64_t N, int K, int D,
-                       const int32_t* row_list, const int32_t* row_count, int32_t* idx,
-                       unsigned long long* stats, cudaStream_t st) {
+template <typename ZT>
+static int launch_search_simt_t(const ZT* z, const float* E, const void* cb, int64_t N, int K, int D,
+                                const int32_t* row_list, const int32_t* row_count, int32_t* idx,
+                                unsigned long long* stats, cudaStream_t st) {
   const auto* hdr = reinterpret_cast<const CbHeader*>(cb);
   const float* e2 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_e2_offset());
-  const bool vec = (D % 4 == 0) && aligned16(z) && aligned16(E);
+  // vector path: 8 elements per load must stay 16-byte aligned in every row
+  const bool vec = ((size_t)D * sizeof(ZT) % 16 == 0) && (D % 4 == 0) && aligned16(z) && aligned16(E);
   const size_t smem = sizeof(SearchSmem);
-  // persistent grid: a few CTAs per SM, each walks row tiles
+  // persistent grid: two CTAs per SM, each walks row tiles
   long long tiles = (N + BM - 1) / BM;
   int grid = (int)((tiles < (long long)num_sms() * 2) ? (tiles > 0 ? tiles : 1) : (long long)num_sms() * 2);
   if (vec) {
-    G2V_CUDA_CHECK(cudaFuncSetAttribute(search_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    search_simt_kernel<true><<<grid, NT, smem, st>>>(z, E, e2, hdr, N, K, D, row_list, row_count, idx, stats);
+    G2V_CUDA_CHECK(cudaFuncSetAttribute(search_simt_kernel<true, ZT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    search_simt_kernel<true, ZT><<<grid, NT, smem, st>>>(z, E, e2, hdr, N, K, D, row_list, row_count, idx, stats);
   } else {
-    G2V_CUDA_CHECK(cudaFuncSetAttribute(search_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    search_simt_kernel<false><<<grid, NT, smem, st>>>(z, E, e2, hdr, N, K, D, row_list, row_count, idx, stats);
+    G2V_CUDA_CHECK(cudaFuncSetAttribute(search_simt_kernel<false, ZT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    search_simt_kernel<false, ZT><<<grid, NT, smem, st>>>(z, E, e2, hdr, N, K, D, row_list, row_count, idx, stats);
   }
   G2V_LAUNCH_CHECK("search_simt_kernel");
   return G2V_OK;
+}
+
+int launch_search_simt(const void* z, int z_dtype, const float* E, const void* cb, int64_t N, int K, int D,
+                       const int32_t* row_list, const int32_t* row_count, int32_t* idx,
+                       unsigned long long* stats, cudaStream_t st) {
+  switch (z_dtype) {
+    case G2V_F32: return launch_search_simt_t(reinterpret_cast<const float*>(z), E, cb, N, K, D, row_list, row_count, idx, stats, st);
+    case G2V_F16: return launch_search_simt_t(reinterpret_cast<const __half*>(z), E, cb, N, K, D, row_list, row_count, idx, stats, st);
+    case G2V_BF16: return launch_search_simt_t(reinterpret_cast<const __nv_bfloat16*>(z), E, cb, N, K, D, row_list, row_count, idx, stats, st);
+    default: return G2V_ERR_DTYPE;
+  }
 }
 
 int launch_apply(const float* x, const float* zs, const float* E, const int32_t* idx, int64_t N, int K, int D,
@@ -641,18 +669,6 @@ int launch_onehot(const int32_t* idx, int64_t N, int K, float* enc, cudaStream_t
   if (vec) onehot_kernel<true><<<grid, 256, 0, st>>>(idx, N, K, enc);
   else onehot_kernel<false><<<grid, 256, 0, st>>>(idx, N, K, enc);
   G2V_LAUNCH_CHECK("onehot_kernel");
-  return G2V_OK;
-}
-
-int launch_convert_rows_f32(const void* src, int dtype, int64_t n, float* dst, cudaStream_t st) {
-  const int grid = grid_for(n, 256 * 4, 16);
-  if (dtype == G2V_BF16)
-    convert_f32_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), (size_t)n, dst);
-  else if (dtype == G2V_F16)
-    convert_f32_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(src), (size_t)n, dst);
-  else
-    return G2V_ERR_DTYPE;
-  G2V_LAUNCH_CHECK("convert_f32_kernel");
   return G2V_OK;
 }
 

@@ -1,11 +1,666 @@
-// placeholder: tensor-core search (filled in next)
+// Tensor-core nearest-code search for sm_100a: tcgen05.mma (fp16 operands, fp32 accumulators in
+// TMEM) fed by TMA, fused with an argmin epilogue, so the [N,K] distance matrix never exists.
+//
+// Pipeline of one search (all on the caller's stream):
+//   1. row_prep_kernel   z (fp32/bf16/fp16) -> z16 [N,Dp] fp16, each row scaled by a power of two,
+//                        plus per-row constants (fixed-point scale, rigorous error bound tau).
+//   2. tc_search_kernel  persistent, one CTA per SM, 128-row tiles.  Warp roles:
+//                          w0  TMA producer of codebook (B) K-panels, 3-stage mbarrier ring
+//                          w1  tcgen05.mma issuer (one lane); 2 x 256-column accumulators in TMEM
+//                          w2  TMA producer of the row tile (A), per-K-panel barriers so the next
+//                              tile streams in while the last code tile is still being multiplied
+//                          w4-7 epilogue: tcgen05.ld -> d = e2 - 2 z.e as a 23-bit fixed-point key
+//                              (2 FFMA + 1 IMAD) -> 32 independent running top-2 chains (3 VIMNMX)
+//                        Rows whose best two codes are closer than tau go to a pair list (exact
+//                        fp64 re-rank of two candidates) or, if a third code may be involved, to
+//                        a fallback list (fp32 SIMT search + fp64 full-row re-rank, g2v_simt.cu).
+//   3. pair_recheck_kernel / search_simt_kernel(list)
+//
+// Operand layouts: K-major, SWIZZLE_128B panels of 64 fp16 (TMA box 64 x rows) and, for the
+// D % 64 remainder, SWIZZLE_32B panels of 16 fp16 (one UMMA_K step each).
 #include "g2v_common.cuh"
+
+#include <cuda.h>
+#include <math.h>
+
 namespace g2v {
-bool tc_supported(int, int) { return false; }
-size_t tc_workspace_bytes(int64_t, int, int, int) { return 0; }
-int launch_search_tc(const void*, int, const float*, const void*, int64_t, int, int, int32_t*,
-                     unsigned long long*, void*, size_t, unsigned, cudaStream_t) {
-  set_error_detail("tensor-core search not built");
-  return G2V_ERR_UNSUPPORTED;
+namespace {
+
+constexpr int TM = 128;                 // rows per tile (UMMA M)
+constexpr int TN = 256;                 // codes per accumulator stage (max UMMA N)
+constexpr int KC = 64;                  // fp16 per full K panel (128 bytes)
+constexpr int KT = 16;                  // fp16 per tail K panel (32 bytes) == UMMA K
+constexpr int NSTAGE = 3;
+constexpr int A_PANEL = TM * KC * 2;    // 16384
+constexpr int A_TAIL = TM * KT * 2;     // 4096
+constexpr int B_PANEL = TN * KC * 2;    // 32768
+constexpr int B_TAIL = TN * KT * 2;     // 8192
+constexpr int MAX_CHUNKS = 12;
+constexpr int NTHREADS = 256;
+constexpr int EPI_WARP0 = 4;
+constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23: float bits = 0x4B400000 + round(v)
+constexpr int kMaxDp = 496;
+constexpr int kMaxK = 16384;            // 9-bit column-group field of the key
+
+struct RowInfo {       // 16 bytes per row, written by row_prep_kernel
+  float cS;            // -2 / (scale_z * scale_e) * S
+  float S;             // fixed-point scale (power of two)
+  float tauI;          // certification threshold in fixed-point units
+  float pad;
+};
+
+struct TcParams {
+  long long N;
+  int K, D, Dp;
+  int n_full, n_tail, n_chunks;
+  int n_ntiles, n_last_mma;     // code tiles; UMMA N of the last one (multiple of 16)
+  int n_row_tiles;
+  const RowInfo* rowinfo;
+  const float* e2;
+  int* idx;
+  int* pair_list;               // 3 ints per entry: row, code a, code b
+  int* full_list;               // 1 int per entry: row
+  int* counters;                // [0] pairs, [1] fallback rows
+  unsigned flags;
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor, K-major.  layout: 2 = SWIZZLE_128B, 6 = SWIZZLE_32B.
+// sbo = byte distance between consecutive 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                      // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;       // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                      // descriptor version 1 (sm_100)
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+// instruction descriptor: fp16 x fp16 -> fp32, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t umma_idesc(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------
+// shared memory plan
+// ------------------------------------------------------------------------------------------
+struct SmemPlan {
+  uint32_t a_off, b_off, e2_off, bar_off, tmem_off, total;
+};
+__host__ __device__ inline SmemPlan smem_plan(int n_full, int n_tail) {
+  SmemPlan p;
+  p.a_off = 0;
+  uint32_t a_bytes = (uint32_t)n_full * A_PANEL + (uint32_t)n_tail * A_TAIL;
+  p.b_off = (a_bytes + 1023u) & ~1023u;
+  p.e2_off = p.b_off + NSTAGE * B_PANEL;
+  p.bar_off = p.e2_off + 2 * TN * 4;
+  p.tmem_off = p.bar_off + 8 * (2 * NSTAGE + 2 * MAX_CHUNKS + 4);
+  p.total = p.tmem_off + 16;
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------
+// epilogue helpers
+// ------------------------------------------------------------------------------------------
+// one 32-column chunk: key = fixed-point(e2 - 2 z.e) << 9 | column group; chain j = column % 32
+template <bool PARTIAL>
+__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* __restrict__ e2c, float cS, float S,
+                                          uint32_t group, int nvalid, uint32_t (&m1)[32], uint32_t (&m2)[32]) {
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 e = *reinterpret_cast<const float4*>(e2c + 4 * j4);
+    const float ee[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = 4 * j4 + u;
+      float x = fmaf(__uint_as_float(v[j]), cS, fmaf(ee[u], S, kMagic));
+      uint32_t key = __float_as_uint(x) * 512u + group;
+      if (PARTIAL && j >= nvalid) key = 0xFFFFFFFFu;
+      m2[j] = max(m1[j], min(m2[j], key));
+      m1[j] = min(m1[j], key);
+    }
+  }
+}
+
+struct Cand {
+  uint32_t key;
+  uint32_t key2;   // second-best key of the same chain
+  int j;
+};
+
+// ------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAt,
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBt,
+                 const TcParams P) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t raw = smem_u32(smem_dyn);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  unsigned char* gbase = smem_dyn + (base - raw);
+  const SmemPlan sp = smem_plan(P.n_full, P.n_tail);
+
+  const uint32_t sA = base + sp.a_off, sB = base + sp.b_off;
+  float* e2s = reinterpret_cast<float*>(gbase + sp.e2_off);
+  const uint32_t bars = base + sp.bar_off;
+  // barrier map
+  auto bar_full = [&](int s) { return bars + 8u * s; };
+  auto bar_empty = [&](int s) { return bars + 8u * (NSTAGE + s); };
+  auto bar_afull = [&](int c) { return bars + 8u * (2 * NSTAGE + c); };
+  auto bar_aempty = [&](int c) { return bars + 8u * (2 * NSTAGE + MAX_CHUNKS + c); };
+  auto bar_accfull = [&](int a) { return bars + 8u * (2 * NSTAGE + 2 * MAX_CHUNKS + a); };
+  auto bar_accempty = [&](int a) { return bars + 8u * (2 * NSTAGE + 2 * MAX_CHUNKS + 2 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + sp.tmem_off);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_chunks = P.n_chunks, n_full = P.n_full;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int c = 0; c < MAX_CHUNKS; ++c) { mbar_init(bar_afull(c), 1); mbar_init(bar_aempty(c), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_accfull(a), 1); mbar_init(bar_accempty(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // chunk geometry: chunk c < n_full is a 64-wide SW128 panel, otherwise a 16-wide SW32 tail
+  auto a_chunk_addr = [&](int c) { return c < n_full ? sA + (uint32_t)c * A_PANEL : sA + (uint32_t)n_full * A_PANEL + (uint32_t)(c - n_full) * A_TAIL; };
+  auto chunk_col = [&](int c) { return c < n_full ? c * KC : n_full * KC + (c - n_full) * KT; };
+
+  if (warp == 0) {
+    // =========================== B producer ===========================
+    if (lane == 0) {
+      uint32_t g = 0;  // global chunk counter
+      for (int tile = blockIdx.x; tile < P.n_row_tiles; tile += gridDim.x) {
+        for (int nt = 0; nt < P.n_ntiles; ++nt) {
+          for (int c = 0; c < n_chunks; ++c, ++g) {
+            const int s = g % NSTAGE;
+            const uint32_t round = g / NSTAGE;
+            mbar_wait(bar_empty(s), (round & 1u) ^ 1u);
+            const bool full = c < n_full;
+            mbar_expect_tx(bar_full(s), full ? B_PANEL : B_TAIL);
+            tma_load_2d(sB + (uint32_t)s * B_PANEL, full ? &tmB : &tmBt, chunk_col(c), nt * TN, bar_full(s));
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // =========================== A producer ===========================
+    if (lane == 0) {
+      uint32_t ti = 0;
+      for (int tile = blockIdx.x; tile < P.n_row_tiles; tile += gridDim.x, ++ti) {
+        for (int c = 0; c < n_chunks; ++c) {
+          mbar_wait(bar_aempty(c), (ti & 1u) ^ 1u);
+          const bool full = c < n_full;
+          mbar_expect_tx(bar_afull(c), full ? A_PANEL : A_TAIL);
+          tma_load_2d(a_chunk_addr(c), full ? &tmA : &tmAt, chunk_col(c), tile * TM, bar_afull(c));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      uint32_t g = 0, it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < P.n_row_tiles; tile += gridDim.x, ++ti) {
+        for (int nt = 0; nt < P.n_ntiles; ++nt, ++it) {
+          const uint32_t as = it & 1u, around = it >> 1;
+          const bool last_nt = (nt == P.n_ntiles - 1);
+          const uint32_t idesc = umma_idesc(last_nt ? P.n_last_mma : TN);
+          mbar_wait(bar_accempty(as), (around & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + as * TN;
+          for (int c = 0; c < n_chunks; ++c, ++g) {
+            const int s = g % NSTAGE;
+            const uint32_t round = g / NSTAGE;
+            if (nt == 0) mbar_wait(bar_afull(c), ti & 1u);
+            mbar_wait(bar_full(s), round & 1u);
+            tc_fence_after();
+            const uint32_t a_addr = a_chunk_addr(c), b_addr = sB + (uint32_t)s * B_PANEL;
+            if (c < n_full) {
+#pragma unroll
+              for (int k = 0; k < KC / KT; ++k) {
+                const uint64_t ad = umma_desc(a_addr + k * 32, 1024, 2);
+                const uint64_t bd = umma_desc(b_addr + k * 32, 1024, 2);
+                tc_mma_f16(d_tmem, ad, bd, idesc, (c | k) != 0);
+              }
+            } else {
+              const uint64_t ad = umma_desc(a_addr, 256, 6);
+              const uint64_t bd = umma_desc(b_addr, 256, 6);
+              tc_mma_f16(d_tmem, ad, bd, idesc, c != 0);
+            }
+            tc_commit(bar_empty(s));                 // B stage free once these MMAs retire
+            if (last_nt) tc_commit(bar_aempty(c));   // A panel free after its last use in this row tile
+          }
+          tc_commit(bar_accfull(as));
+        }
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // =========================== epilogue ===========================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;            // row within the tile == TMEM lane
+    const int et = threadIdx.x - EPI_WARP0 * 32;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < P.n_row_tiles; tile += gridDim.x) {
+      const long long row = (long long)tile * TM + r;
+      const bool valid = row < P.N;
+      RowInfo ri = valid ? P.rowinfo[row] : RowInfo{0.f, 0.f, 0.f, 0.f};
+      uint32_t m1[32], m2[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { m1[j] = 0xFFFFFFFFu; m2[j] = 0xFFFFFFFFu; }
+
+      for (int nt = 0; nt < P.n_ntiles; ++nt, ++it) {
+        const uint32_t as = it & 1u, around = it >> 1;
+        float* e2c = e2s + as * TN;
+        // stage this code tile's ||e||^2 (two per thread)
+        {
+          const int k0 = nt * TN + et, k1 = k0 + 128;
+          e2c[et] = (k0 < P.K) ? __ldg(P.e2 + k0) : 0.f;
+          e2c[et + 128] = (k1 < P.K) ? __ldg(P.e2 + k1) : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        mbar_wait(bar_accfull(as), around & 1u);
+        tc_fence_after();
+        const int ncols = min(TN, P.K - nt * TN);
+        const int nch = (ncols + 31) >> 5;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * TN;
+        uint32_t va[32], vb[32];
+        tc_ld32(taddr, va);
+        for (int ch = 0; ch < nch; ch += 2) {
+          tc_wait_ld();
+          if (ch + 1 < nch) tc_ld32(taddr + (ch + 1) * 32, vb);
+          {
+            const int nv = ncols - ch * 32;
+            if (nv >= 32) epi_chunk<false>(va, e2c + ch * 32, ri.cS, ri.S, (uint32_t)(nt * 8 + ch), 32, m1, m2);
+            else epi_chunk<true>(va, e2c + ch * 32, ri.cS, ri.S, (uint32_t)(nt * 8 + ch), nv, m1, m2);
+          }
+          if (ch + 1 < nch) {
+            tc_wait_ld();
+            if (ch + 2 < nch) tc_ld32(taddr + (ch + 2) * 32, va);
+            const int nv = ncols - (ch + 1) * 32;
+            if (nv >= 32) epi_chunk<false>(vb, e2c + (ch + 1) * 32, ri.cS, ri.S, (uint32_t)(nt * 8 + ch + 1), 32, m1, m2);
+            else epi_chunk<true>(vb, e2c + (ch + 1) * 32, ri.cS, ri.S, (uint32_t)(nt * 8 + ch + 1), nv, m1, m2);
+          }
+        }
+        // all TMEM reads of this stage are complete (last wait::ld above): hand it back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_accempty(as));
+      }
+
+      // ---- per-row decision: best three keys over the 32 chains ----
+      Cand c1{0xFFFFFFFFu, 0xFFFFFFFFu, 0}, c2{0xFFFFFFFFu, 0xFFFFFFFFu, 0};
+      uint32_t k3 = 0xFFFFFFFFu;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const uint32_t k = m1[j];
+        if (k < c1.key) {
+          k3 = c2.key; c2 = c1; c1 = Cand{k, m2[j], j};
+        } else if (k < c2.key) {
+          k3 = c2.key; c2 = Cand{k, m2[j], j};
+        } else {
+          k3 = min(k3, k);
+        }
+      }
+      // candidates ordered over all codes: t1 <= t2 <= t3
+      const uint32_t t1 = c1.key;
+      const int code1 = (int)(t1 & 511u) * 32 + c1.j;
+      uint32_t t2, t3;
+      int code2;
+      bool same_chain;
+      if (c1.key2 < c2.key) {            // runner-up sits in the winner's own chain: its third is unknown
+        t2 = c1.key2; code2 = (int)(t2 & 511u) * 32 + c1.j; same_chain = true; t3 = c2.key;
+      } else {
+        t2 = c2.key; code2 = (int)(t2 & 511u) * 32 + c2.j; same_chain = false;
+        t3 = min(min(c1.key2, c2.key2), k3);
+      }
+      if (valid) {
+        const uint32_t tau = (uint32_t)fminf(ri.tauI, 4194304.f);
+        const uint32_t v1 = t1 >> 9, v2 = t2 >> 9, v3 = t3 >> 9;
+        int result = code1;
+        if (!(P.flags & G2V_NO_RECHECK) && (v2 - v1 <= tau)) {
+          if (!same_chain && (v3 - v1 > tau) && code2 < P.K) {
+            const int slot = atomicAdd(P.counters + 0, 1);
+            P.pair_list[3 * slot + 0] = (int)row;
+            P.pair_list[3 * slot + 1] = code1;
+            P.pair_list[3 * slot + 2] = code2;
+          } else {
+            const int slot = atomicAdd(P.counters + 1, 1);
+            P.full_list[slot] = (int)row;
+          }
+        }
+        P.idx[row] = min(result, P.K - 1);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// row preparation: fp16 operand rows + per-row constants
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ld_f32(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_f32(const __half* p) { return __half2float(*p); }
+__device__ __forceinline__ float ld_f32(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename ZT>
+__global__ void __launch_bounds__(256) row_prep_kernel(const ZT* __restrict__ z, long long N, int D, int Dp,
+                                                       const CbHeader* __restrict__ hdr, __half* __restrict__ z16,
+                                                       RowInfo* __restrict__ rowinfo, int* counters, int n_ksteps) {
+  if (blockIdx.x == 0 && threadIdx.x < 4) counters[threadIdx.x] = 0;
+  const int lane = threadIdx.x & 31;
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= N) return;
+  const ZT* zr = z + (size_t)row * D;
+  float am = 0.f, s2 = 0.f;
+  for (int j = lane; j < D; j += 32) {
+    float v = ld_f32(zr + j);
+    am = fmaxf(am, fabsf(v));
+    s2 = fmaf(v, v, s2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  float sc = 1.f;
+  if (am > 0.f && isfinite(am)) {
+    int e;
+    frexpf(am, &e);
+    sc = ldexpf(1.f, max(min(9 - e, 100), -100));      // row max lands in [256, 512)
+  }
+  const float inv = 1.f / sc;
+  float r2 = 0.f;
+  __half* o = z16 + (size_t)row * Dp;
+  for (int j = lane; j < Dp; j += 32) {
+    float v = (j < D) ? ld_f32(zr + j) : 0.f;
+    __half h = __float2half_rn(v * sc);
+    float r = v - __half2float(h) * inv;
+    r2 = fmaf(r, r, r2);
+    o[j] = h;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, off);
+  if (lane == 0) {
+    const float znorm = sqrtf(s2) * 1.0001f, rnorm = sqrtf(r2) * 1.0001f;
+    const float enorm = sqrtf(hdr->e2max) * 1.0001f, snorm = hdr->smax;
+    // |dot_hat - dot| <= |r||e| + |z||s| + |r||s|  (operand rounding, Cauchy-Schwarz on the actual
+    // residuals) + tensor-core accumulation (2^-19 alignment + one fp32 rounding per K step)
+    const float acc = (1.9073486e-6f + (float)(n_ksteps + 2) * 1.1920929e-7f) * znorm * enorm;
+    const float err_dot = rnorm * enorm + znorm * snorm + rnorm * snorm + acc;
+    // distance = e2 - 2 dot; a gap of two codes can be off by twice the per-code error
+    float tau = 4.f * err_dot + 4.f * 5.9604645e-8f * hdr->e2max;
+    const float R = hdr->e2max + 2.f * znorm * enorm;
+    float S = 1.f;
+    if (R > 0.f && isfinite(R)) {
+      int e;
+      frexpf(R, &e);                                    // R < 2^e
+      S = ldexpf(1.f, max(min(21 - e, 100), -100));     // |d| * S < 2^21
+    }
+    RowInfo ri;
+    ri.S = S;
+    ri.cS = (-2.f * inv / hdr->scale_e) * S;
+    ri.tauI = fminf(tau * S + 4.f, 4194304.f);          // + fixed-point rounding of both keys
+    ri.pad = 0.f;
+    rowinfo[row] = ri;
+  }
+}
+
+// exact re-rank of two candidate codes per listed row (one warp per entry, fp64)
+template <typename ZT>
+__global__ void __launch_bounds__(256) pair_recheck_kernel(const ZT* __restrict__ z, const float* __restrict__ E,
+                                                           int D, const int* __restrict__ pair_list,
+                                                           const int* __restrict__ counters, int* __restrict__ idx,
+                                                           unsigned long long* stats) {
+  const int lane = threadIdx.x & 31;
+  const int n = counters[0];
+  const int wstride = (gridDim.x * blockDim.x) >> 5;
+  for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n; e += wstride) {
+    const int row = pair_list[3 * e], a = pair_list[3 * e + 1], b = pair_list[3 * e + 2];
+    const ZT* zr = z + (size_t)row * D;
+    const float* ea = E + (size_t)a * D;
+    const float* eb = E + (size_t)b * D;
+    double da = 0.0, db = 0.0;
+    for (int j = lane; j < D; j += 32) {
+      const double zv = (double)ld_f32(zr + j);
+      const double xa = zv - (double)__ldg(ea + j), xb = zv - (double)__ldg(eb + j);
+      da = fma(xa, xa, da);
+      db = fma(xb, xb, db);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      da += __shfl_xor_sync(0xffffffffu, da, o);
+      db += __shfl_xor_sync(0xffffffffu, db, o);
+    }
+    if (lane == 0) idx[row] = (db < da || (db == da && b < a)) ? b : a;
+  }
+  if (stats && blockIdx.x == 0 && threadIdx.x == 0) {
+    atomicAdd(stats + G2V_STAT_PAIR_RECHECK, (unsigned long long)n);
+    atomicAdd(stats + G2V_STAT_FALLBACK_ROWS, (unsigned long long)counters[1]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int make_map(CUtensorMap* tm, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows,
+             CUtensorMapSwizzle sw) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error_detail("cuTensorMapEncodeTiled entry point not available");
+    return G2V_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {cols * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(gptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error_detail("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu box=%ux%u)", (int)r,
+                     (unsigned long long)rows, (unsigned long long)cols, box_cols, box_rows);
+    return G2V_ERR_CUDA;
+  }
+  return G2V_OK;
+}
+
+inline size_t al256(size_t v) { return (v + 255) / 256 * 256; }
+
+struct TcWs {
+  size_t z16, rowinfo, pairs, fulls, counters, total;
+};
+TcWs tc_ws(int64_t N, int D) {
+  const int Dp = round_up(D, 16);
+  TcWs w;
+  w.z16 = 0;
+  w.rowinfo = al256((size_t)N * Dp * 2);
+  w.pairs = w.rowinfo + al256((size_t)N * sizeof(RowInfo));
+  w.fulls = w.pairs + al256((size_t)N * 12);
+  w.counters = w.fulls + al256((size_t)N * 4);
+  w.total = w.counters + 256;
+  return w;
+}
+
+template <typename ZT>
+int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, int K, int D, int32_t* idx,
+           unsigned long long* stats, void* ws, unsigned flags, cudaStream_t st) {
+  const int Dp = round_up(D, 16), Kp = round_up(K, 256);
+  const TcWs w = tc_ws(N, D);
+  char* base = reinterpret_cast<char*>(ws);
+  __half* z16 = reinterpret_cast<__half*>(base + w.z16);
+  RowInfo* rowinfo = reinterpret_cast<RowInfo*>(base + w.rowinfo);
+  int* pairs = reinterpret_cast<int*>(base + w.pairs);
+  int* fulls = reinterpret_cast<int*>(base + w.fulls);
+  int* counters = reinterpret_cast<int*>(base + w.counters);
+  const auto* hdr = reinterpret_cast<const CbHeader*>(cb);
+  const float* e2 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_e2_offset());
+  const __half* e16 = reinterpret_cast<const __half*>(reinterpret_cast<const char*>(cb) + cb_e16_offset(K));
+
+  TcParams P;
+  P.N = N; P.K = K; P.D = D; P.Dp = Dp;
+  P.n_full = Dp / KC;
+  P.n_tail = (Dp % KC) / KT;
+  P.n_chunks = P.n_full + P.n_tail;
+  P.n_ntiles = (K + TN - 1) / TN;
+  P.n_last_mma = round_up(K - (P.n_ntiles - 1) * TN, 16);
+  P.n_row_tiles = (int)((N + TM - 1) / TM);
+  P.rowinfo = rowinfo; P.e2 = e2; P.idx = idx;
+  P.pair_list = pairs; P.full_list = fulls; P.counters = counters; P.flags = flags;
+
+  const int n_ksteps = P.n_full * (KC / KT) + P.n_tail;
+  {
+    const long long threads = N * 32;
+    const int grid = (int)((threads + 255) / 256);
+    row_prep_kernel<ZT><<<grid, 256, 0, st>>>(z, N, D, Dp, hdr, z16, rowinfo, counters, n_ksteps);
+    G2V_LAUNCH_CHECK("row_prep_kernel");
+  }
+
+  alignas(64) CUtensorMap tmA, tmAt, tmB, tmBt;
+  int rc;
+  // main maps need a 64-wide box; if D < 64 there are no full panels and the main maps are unused
+  const uint32_t main_box = (Dp >= KC) ? KC : KT;
+  const CUtensorMapSwizzle main_sw = (Dp >= KC) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
+  if ((rc = make_map(&tmA, z16, (uint64_t)N, (uint64_t)Dp, main_box, TM, main_sw))) return rc;
+  if ((rc = make_map(&tmAt, z16, (uint64_t)N, (uint64_t)Dp, KT, TM, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  if ((rc = make_map(&tmB, e16, (uint64_t)Kp, (uint64_t)Dp, main_box, TN, main_sw))) return rc;
+  if ((rc = make_map(&tmBt, e16, (uint64_t)Kp, (uint64_t)Dp, KT, TN, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+
+  const SmemPlan sp = smem_plan(P.n_full, P.n_tail);
+  const size_t smem = sp.total + 1024;
+  G2V_CUDA_CHECK(cudaFuncSetAttribute(tc_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = P.n_row_tiles < num_sms() ? P.n_row_tiles : num_sms();
+  tc_search_kernel<<<grid, NTHREADS, smem, st>>>(tmA, tmAt, tmB, tmBt, P);
+  G2V_LAUNCH_CHECK("tc_search_kernel");
+
+  if (!(flags & G2V_NO_RECHECK)) {
+    const int pgrid = num_sms() * 2;
+    pair_recheck_kernel<ZT><<<pgrid, 256, 0, st>>>(z, E, D, pairs, counters, idx, stats);
+    G2V_LAUNCH_CHECK("pair_recheck_kernel");
+    rc = launch_search_simt(z, z_dtype, E, cb, N, K, D, fulls, counters + 1, idx, stats, st);
+    if (rc) return rc;
+  }
+  return G2V_OK;
+}
+
+}  // namespace
+
+bool tc_supported(int K, int D) {
+  const int Dp = round_up(D, 16);
+  if (Dp > kMaxDp || K > kMaxK) return false;
+  if ((long long)K * D < 16384) return false;       // tiny problems: the fp32 path is already bandwidth-bound
+  const SmemPlan sp = smem_plan(Dp / KC, (Dp % KC) / KT);
+  return sp.total + 1024 <= 227 * 1024;
+}
+
+size_t tc_workspace_bytes(int64_t N, int K, int D, int z_dtype) {
+  (void)K; (void)z_dtype;
+  return tc_ws(N, D).total;
+}
+
+int launch_search_tc(const void* z, int z_dtype, const float* E, const void* cb, int64_t N, int K, int D,
+                     int32_t* idx, unsigned long long* stats, void* ws, size_t ws_bytes, unsigned flags,
+                     cudaStream_t st) {
+  if (!tc_supported(K, D)) return G2V_ERR_UNSUPPORTED;
+  if (ws_bytes < tc_ws(N, D).total) return G2V_ERR_WORKSPACE;
+  switch (z_dtype) {
+    case G2V_F32: return run_tc(reinterpret_cast<const float*>(z), z_dtype, E, cb, N, K, D, idx, stats, ws, flags, st);
+    case G2V_F16: return run_tc(reinterpret_cast<const __half*>(z), z_dtype, E, cb, N, K, D, idx, stats, ws, flags, st);
+    case G2V_BF16: return run_tc(reinterpret_cast<const __nv_bfloat16*>(z), z_dtype, E, cb, N, K, D, idx, stats, ws, flags, st);
+    default: return G2V_ERR_DTYPE;
+  }
+}
+
 }  // namespace g2v
