@@ -108,6 +108,7 @@ size_t g2v_workspace_bytes(int64_t N, int K, int D, int z_dtype, unsigned flags)
   unsigned algo = flags & G2V_ALGO_MASK;
   bool tc = (algo == G2V_ALGO_TC) || (algo == G2V_ALGO_AUTO && tc_supported(K, D));
   if (tc) b += align_up(tc_workspace_bytes(N, K, D, z_dtype), 256);
+  else b += align_up((size_t)N * 4, 256);   // list of rows for the fp64 re-rank
   return b;
 }
 
@@ -132,7 +133,8 @@ int g2v_vq_search(const void* z, int z_dtype, const float* E, const void* cb, in
   }
   bool tc = (algo == G2V_ALGO_TC) || (algo == G2V_ALGO_AUTO && tc_supported(K, D));
   if (tc) return launch_search_tc(z, z_dtype, E, cb, N, K, D, idx, stats, p, ws_bytes - 256, flags, st);
-  return launch_search_simt(z, z_dtype, E, cb, N, K, D, nullptr, nullptr, idx, stats, st);
+  return launch_search_simt(z, z_dtype, E, cb, N, K, D, reinterpret_cast<int32_t*>(p),
+                            reinterpret_cast<int32_t*>(ws), idx, stats, st);
 }
 
 int g2v_vq_apply(const float* x, const float* zs, const float* E, const int32_t* idx, int64_t N, int K, int D,

@@ -57,11 +57,15 @@ int num_sms();
 
 // ---- launchers implemented in g2v_simt.cu ----------------------------------------------------
 int launch_codebook_prepare(const float* E, int K, int D, void* cb, cudaStream_t st);
-// fp32 CUDA-core search over all rows (row_list == nullptr) or over the rows listed in
-// row_list[0 .. *row_count).
+// fp32 CUDA-core search over all rows + fp64 re-rank of the rows it cannot certify;
+// full_list (N ints) / full_count (1 int) are device scratch.
 int launch_search_simt(const void* z, int z_dtype, const float* E, const void* cb, int64_t N, int K, int D,
-                       const int32_t* row_list, const int32_t* row_count, int32_t* idx,
+                       int32_t* full_list, int32_t* full_count, int32_t* idx,
                        unsigned long long* stats, cudaStream_t st);
+// exact fp64 argmin of the rows in list[0 .. *count) (count <= max_rows)
+int launch_full_recheck(const void* z, int z_dtype, const float* E, const void* cb, int K, int D, const int32_t* list,
+                        const int32_t* count, int64_t max_rows, int32_t* idx, unsigned long long* stats,
+                        cudaStream_t st);
 int launch_apply(const float* x, const float* zs, const float* E, const int32_t* idx, int64_t N, int K,
                  int D, float* out, double* sse, int32_t* counts, float* dwr, cudaStream_t st);
 int launch_stats_pack(const int32_t* counts, const double* sse, int64_t N, int K, int D, float* packed,

@@ -118,10 +118,6 @@ struct SearchSmem {
   float e2s[BN];
   float z2p[2][BM];
   int rows[BM];
-  int flagged[BM];
-  int nflag;
-  double red_v[NT / 32];
-  int red_i[NT / 32];
 };
 
 __device__ __forceinline__ float to_f32(float v) { return v; }
@@ -158,13 +154,13 @@ __device__ __forceinline__ void load8(const T* __restrict__ base, long long row,
 template <bool VEC, typename ZT>
 __global__ void __launch_bounds__(NT) search_simt_kernel(
     const ZT* __restrict__ z, const float* __restrict__ E, const float* __restrict__ e2,
-    const CbHeader* __restrict__ hdr, long long N, int K, int D, const int* __restrict__ row_list,
-    const int* __restrict__ row_count, int* __restrict__ idx_out, unsigned long long* stats) {
+    const CbHeader* __restrict__ hdr, long long N, int K, int D, int* __restrict__ full_list,
+    int* __restrict__ full_count, int* __restrict__ idx_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SearchSmem& S = *reinterpret_cast<SearchSmem*>(smem_raw);
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
   const int lrow = t & (BM - 1), lhalf = t >> 7;  // loader mapping: row, which 8 of the 16 columns
-  const long long n_rows = row_list ? (long long)*row_count : N;
+  const long long n_rows = N;
   const int nk = (D + BK - 1) / BK;
   const int n_ctile = (K + BN - 1) / BN;
   const float e2max = hdr->e2max;
@@ -173,9 +169,8 @@ __global__ void __launch_bounds__(NT) search_simt_kernel(
     __syncthreads();  // previous tile fully done with smem
     if (t < BM) {
       long long r = tile * BM + t;
-      S.rows[t] = (r < n_rows) ? (row_list ? row_list[r] : (int)r) : -1;
+      S.rows[t] = (r < n_rows) ? (int)r : -1;
     }
-    if (t == 0) S.nflag = 0;
     __syncthreads();
     const long long grow = S.rows[lrow];
 
@@ -289,49 +284,143 @@ __global__ void __launch_bounds__(NT) search_simt_kernel(
         // off by twice that.
         float z2 = S.z2p[0][r] + S.z2p[1][r];
         float tau = 4.f * (float)D * kU32 * sqrtf(z2 * e2max) + 4.f * kU32 * (e2max + fabsf(m1[i]));
-        if (!(m2[i] - m1[i] > tau)) {
-          int slot = atomicAdd(&S.nflag, 1);
-          S.flagged[slot] = r;
-        }
+        // uncertified rows get their whole distance row recomputed in fp64 (full_recheck_kernel)
+        if (!(m2[i] - m1[i] > tau)) full_list[atomicAdd(full_count, 1)] = g;
       }
-    }
-    __syncthreads();
-
-    // exact re-rank of the uncertified rows: whole distance row in fp64, first index on ties
-    const int nflag = S.nflag;
-    for (int f = 0; f < nflag; ++f) {
-      const int g = S.rows[S.flagged[f]];
-      const ZT* zr = z + (size_t)g * D;
-      double best = INFINITY;
-      int besti = 0x7fffffff;
-      for (int k = t; k < K; k += NT) {
-        const float* er = E + (size_t)k * D;
-        double s = 0.0;
-        for (int j = 0; j < D; ++j) {
-          double df = (double)to_f32(zr[j]) - (double)__ldg(er + j);
-          s = fma(df, df, s);
-        }
-        if (s < best) { best = s; besti = k; }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        double ov = __shfl_xor_sync(0xffffffffu, best, o);
-        int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-        if (ov < best || (ov == best && oi < besti)) { best = ov; besti = oi; }
-      }
-      if ((t & 31) == 0) { S.red_v[t >> 5] = best; S.red_i[t >> 5] = besti; }
-      __syncthreads();
-      if (t == 0) {
-        for (int w = 1; w < NT / 32; ++w)
-          if (S.red_v[w] < best || (S.red_v[w] == best && S.red_i[w] < besti)) { best = S.red_v[w]; besti = S.red_i[w]; }
-        idx_out[g] = besti;
-      }
-      __syncthreads();
-    }
-    if (t == 0 && stats) {
-      if (nflag) atomicAdd(stats + G2V_STAT_FULL_RECHECK, (unsigned long long)nflag);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// exact re-rank of the listed rows over the whole codebook, first index on exact ties.
+// One CTA takes FR_ROWS rows at a time so each codebook row read from L2 serves all of them;
+// warps split the codes, lanes split the dimensions (coalesced), fixed reduction order.
+// Phase A evaluates every distance in fp32 (tight bound: ~20 roundings per dot) and certifies the
+// rows whose top-2 gap exceeds that bound; phase B redoes the remaining rows in fp64.
+// ------------------------------------------------------------------------------------------
+constexpr int FR_ROWS = 8, FR_WARPS = 8;
+
+template <typename ZT>
+__global__ void __launch_bounds__(FR_WARPS * 32) full_recheck_kernel(
+    const ZT* __restrict__ z, const float* __restrict__ E, const float* __restrict__ e2,
+    const CbHeader* __restrict__ hdr, int K, int D, const int* __restrict__ list,
+    const int* __restrict__ count, int* __restrict__ idx_out, unsigned long long* stats) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* zs = reinterpret_cast<float*>(smem_raw);                 // [FR_ROWS][D]
+  __shared__ double bv[FR_WARPS][FR_ROWS];
+  __shared__ float b1[FR_WARPS][FR_ROWS], b2[FR_WARPS][FR_ROWS];
+  __shared__ int bi[FR_WARPS][FR_ROWS];
+  __shared__ int rows[FR_ROWS];
+  __shared__ int need64[FR_ROWS];
+  __shared__ float z2s[FR_ROWS];
+  __shared__ int n64;
+  const int n = *count;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float e2max = hdr->e2max;
+  if (threadIdx.x == 0) n64 = 0;
+  for (int b0 = blockIdx.x * FR_ROWS; b0 < n; b0 += gridDim.x * FR_ROWS) {
+    __syncthreads();
+    if (threadIdx.x < FR_ROWS) rows[threadIdx.x] = (b0 + threadIdx.x < n) ? list[b0 + threadIdx.x] : -1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < FR_ROWS * D; i += blockDim.x) {
+      const int r = i / D, j = i - r * D;
+      zs[i] = rows[r] >= 0 ? to_f32(z[(size_t)rows[r] * D + j]) : 0.f;
+    }
+    __syncthreads();
+    if (warp < FR_ROWS) {                                  // row norms for the fp32 error bound
+      float s = 0.f;
+      for (int j = lane; j < D; j += 32) s = fmaf(zs[warp * D + j], zs[warp * D + j], s);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) z2s[warp] = s;
+    }
+    // ---- phase A: fp32 distances, running top-2 per row ----
+    float m1[FR_ROWS], m2[FR_ROWS];
+    int i1[FR_ROWS];
+#pragma unroll
+    for (int r = 0; r < FR_ROWS; ++r) { m1[r] = INFINITY; m2[r] = INFINITY; i1[r] = 0x7fffffff; }
+    for (int k = warp; k < K; k += FR_WARPS) {
+      const float* er = E + (size_t)k * D;
+      float part[FR_ROWS];
+#pragma unroll
+      for (int r = 0; r < FR_ROWS; ++r) part[r] = 0.f;
+      for (int j = lane; j < D; j += 32) {
+        const float e = __ldg(er + j);
+#pragma unroll
+        for (int r = 0; r < FR_ROWS; ++r) part[r] = fmaf(zs[r * D + j], e, part[r]);
+      }
+      const float ek = __ldg(e2 + k);
+#pragma unroll
+      for (int r = 0; r < FR_ROWS; ++r) {
+        float s = part[r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float d = fmaf(-2.f, s, ek);
+        const bool lt = d < m1[r];                          // ascending k inside a warp: first wins
+        m2[r] = fminf(m2[r], fmaxf(d, m1[r]));
+        i1[r] = lt ? k : i1[r];
+        m1[r] = fminf(m1[r], d);
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < FR_ROWS; ++r) { b1[warp][r] = m1[r]; b2[warp][r] = m2[r]; bi[warp][r] = i1[r]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < FR_ROWS) {
+      const int r = threadIdx.x;
+      float v1 = b1[0][r], v2 = b2[0][r];
+      int id = bi[0][r];
+      for (int w = 1; w < FR_WARPS; ++w) {
+        const float o1 = b1[w][r], o2 = b2[w][r];
+        const int oi = bi[w][r];
+        const bool take = (o1 < v1) || (o1 == v1 && oi < id);
+        const float nv2 = take ? fminf(v1, o2) : fminf(v2, o1);
+        v1 = take ? o1 : v1;
+        id = take ? oi : id;
+        v2 = nv2;
+      }
+      // per-code error of this fp32 evaluation: (ceil(D/32) + 7) roundings on the dot, one on e2, one on d
+      const float nsteps = (float)((D + 31) / 32 + 7);
+      const float tau = 4.f * nsteps * kU32 * sqrtf(z2s[r] * e2max) + 4.f * kU32 * (e2max + fabsf(v1));
+      int need = 0;
+      if (rows[r] >= 0) {
+        idx_out[rows[r]] = id;
+        need = !(v2 - v1 > tau);
+      }
+      need64[r] = need;
+      if (need) atomicAdd(&n64, 1);
+    }
+    __syncthreads();
+    // ---- phase B (rare): fp64 for the rows fp32 could not certify ----
+    for (int r = 0; r < FR_ROWS; ++r) {
+      if (!need64[r]) continue;                            // block-uniform
+      double best = INFINITY;
+      int besti = 0x7fffffff;
+      for (int k = warp; k < K; k += FR_WARPS) {
+        const float* er = E + (size_t)k * D;
+        double part = 0.0;
+        for (int j = lane; j < D; j += 32) {
+          const double df = (double)zs[r * D + j] - (double)__ldg(er + j);
+          part = fma(df, df, part);
+        }
+        part = warp_sum(part);
+        if (part < best) { best = part; besti = k; }
+      }
+      if (lane == 0) { bv[warp][0] = best; bi[warp][0] = besti; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double v = bv[0][0];
+        int id = bi[0][0];
+        for (int w = 1; w < FR_WARPS; ++w)
+          if (bv[w][0] < v || (bv[w][0] == v && bi[w][0] < id)) { v = bv[w][0]; id = bi[w][0]; }
+        idx_out[rows[r]] = id;
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  if (stats && threadIdx.x == 0 && n64) atomicAdd(stats + G2V_STAT_FULL_RECHECK, (unsigned long long)n64);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -579,35 +668,65 @@ int launch_codebook_prepare(const float* E, int K, int D, void* cb, cudaStream_t
 }
 
 template <typename ZT>
-static int launch_search_simt_t(const ZT* z, const float* E, const void* cb, int64_t N, int K, int D,
-                                const int32_t* row_list, const int32_t* row_count, int32_t* idx,
+static int launch_full_recheck_t(const ZT* z, const float* E, const void* cb, int K, int D, const int32_t* list,
+                                 const int32_t* count, int64_t max_rows, int32_t* idx,
+                                 unsigned long long* stats, cudaStream_t st) {
+  const size_t smem = (size_t)FR_ROWS * D * sizeof(float);
+  if (smem > 48 * 1024)
+    G2V_CUDA_CHECK(cudaFuncSetAttribute(full_recheck_kernel<ZT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long batches = (max_rows + FR_ROWS - 1) / FR_ROWS;
+  long long cap = (long long)num_sms() * 4;
+  const int grid = (int)(batches < 1 ? 1 : (batches < cap ? batches : cap));
+  const auto* hdr = reinterpret_cast<const CbHeader*>(cb);
+  const float* e2 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_e2_offset());
+  full_recheck_kernel<ZT><<<grid, FR_WARPS * 32, smem, st>>>(z, E, e2, hdr, K, D, list, count, idx, stats);
+  G2V_LAUNCH_CHECK("full_recheck_kernel");
+  return G2V_OK;
+}
+
+int launch_full_recheck(const void* z, int z_dtype, const float* E, const void* cb, int K, int D, const int32_t* list,
+                        const int32_t* count, int64_t max_rows, int32_t* idx, unsigned long long* stats,
+                        cudaStream_t st) {
+  switch (z_dtype) {
+    case G2V_F32: return launch_full_recheck_t(reinterpret_cast<const float*>(z), E, cb, K, D, list, count, max_rows, idx, stats, st);
+    case G2V_F16: return launch_full_recheck_t(reinterpret_cast<const __half*>(z), E, cb, K, D, list, count, max_rows, idx, stats, st);
+    case G2V_BF16: return launch_full_recheck_t(reinterpret_cast<const __nv_bfloat16*>(z), E, cb, K, D, list, count, max_rows, idx, stats, st);
+    default: return G2V_ERR_DTYPE;
+  }
+}
+
+template <typename ZT>
+static int launch_search_simt_t(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, int K, int D,
+                                int32_t* full_list, int32_t* full_count, int32_t* idx,
                                 unsigned long long* stats, cudaStream_t st) {
   const auto* hdr = reinterpret_cast<const CbHeader*>(cb);
   const float* e2 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_e2_offset());
   // vector path: 8 elements per load must stay 16-byte aligned in every row
   const bool vec = ((size_t)D * sizeof(ZT) % 16 == 0) && (D % 4 == 0) && aligned16(z) && aligned16(E);
   const size_t smem = sizeof(SearchSmem);
+  G2V_CUDA_CHECK(cudaMemsetAsync(full_count, 0, sizeof(int32_t), st));
   // persistent grid: two CTAs per SM, each walks row tiles
   long long tiles = (N + BM - 1) / BM;
   int grid = (int)((tiles < (long long)num_sms() * 2) ? (tiles > 0 ? tiles : 1) : (long long)num_sms() * 2);
   if (vec) {
     G2V_CUDA_CHECK(cudaFuncSetAttribute(search_simt_kernel<true, ZT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    search_simt_kernel<true, ZT><<<grid, NT, smem, st>>>(z, E, e2, hdr, N, K, D, row_list, row_count, idx, stats);
+    search_simt_kernel<true, ZT><<<grid, NT, smem, st>>>(z, E, e2, hdr, N, K, D, full_list, full_count, idx);
   } else {
     G2V_CUDA_CHECK(cudaFuncSetAttribute(search_simt_kernel<false, ZT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    search_simt_kernel<false, ZT><<<grid, NT, smem, st>>>(z, E, e2, hdr, N, K, D, row_list, row_count, idx, stats);
+    search_simt_kernel<false, ZT><<<grid, NT, smem, st>>>(z, E, e2, hdr, N, K, D, full_list, full_count, idx);
   }
   G2V_LAUNCH_CHECK("search_simt_kernel");
-  return G2V_OK;
+  return launch_full_recheck_t(z, E, cb, K, D, full_list, full_count, N, idx, stats, st);
 }
 
+// fp32 search of all rows; `full_list` (N ints) and `full_count` (1 int) are scratch
 int launch_search_simt(const void* z, int z_dtype, const float* E, const void* cb, int64_t N, int K, int D,
-                       const int32_t* row_list, const int32_t* row_count, int32_t* idx,
+                       int32_t* full_list, int32_t* full_count, int32_t* idx,
                        unsigned long long* stats, cudaStream_t st) {
   switch (z_dtype) {
-    case G2V_F32: return launch_search_simt_t(reinterpret_cast<const float*>(z), E, cb, N, K, D, row_list, row_count, idx, stats, st);
-    case G2V_F16: return launch_search_simt_t(reinterpret_cast<const __half*>(z), E, cb, N, K, D, row_list, row_count, idx, stats, st);
-    case G2V_BF16: return launch_search_simt_t(reinterpret_cast<const __nv_bfloat16*>(z), E, cb, N, K, D, row_list, row_count, idx, stats, st);
+    case G2V_F32: return launch_search_simt_t(reinterpret_cast<const float*>(z), z_dtype, E, cb, N, K, D, full_list, full_count, idx, stats, st);
+    case G2V_F16: return launch_search_simt_t(reinterpret_cast<const __half*>(z), z_dtype, E, cb, N, K, D, full_list, full_count, idx, stats, st);
+    case G2V_BF16: return launch_search_simt_t(reinterpret_cast<const __nv_bfloat16*>(z), z_dtype, E, cb, N, K, D, full_list, full_count, idx, stats, st);
     default: return G2V_ERR_DTYPE;
   }
 }

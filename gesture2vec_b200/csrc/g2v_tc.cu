@@ -13,8 +13,8 @@
 //                              (2 FFMA + 1 IMAD) -> 32 independent running top-2 chains (3 VIMNMX)
 //                        Rows whose best two codes are closer than tau go to a pair list (exact
 //                        fp64 re-rank of two candidates) or, if a third code may be involved, to
-//                        a fallback list (fp32 SIMT search + fp64 full-row re-rank, g2v_simt.cu).
-//   3. pair_recheck_kernel / search_simt_kernel(list)
+//                        a fallback list (whole row re-ranked: fp32, then fp64 where needed).
+//   3. pair_recheck_kernel, full_recheck_kernel (g2v_simt.cu)
 //
 // Operand layouts: K-major, SWIZZLE_128B panels of 64 fp16 (TMA box 64 x rows) and, for the
 // D % 64 remainder, SWIZZLE_32B panels of 16 fp16 (one UMMA_K step each).
@@ -195,6 +195,7 @@ struct Cand {
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAt,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBt,
+                 const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmBlt,
                  const TcParams P) {
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t raw = smem_u32(smem_dyn);
@@ -249,8 +250,12 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t round = g / NSTAGE;
             mbar_wait(bar_empty(s), (round & 1u) ^ 1u);
             const bool full = c < n_full;
-            mbar_expect_tx(bar_full(s), full ? B_PANEL : B_TAIL);
-            tma_load_2d(sB + (uint32_t)s * B_PANEL, full ? &tmB : &tmBt, chunk_col(c), nt * TN, bar_full(s));
+            // the last code tile only fetches the rows its MMA reads (n_last_mma <= 256)
+            const bool last = (nt == P.n_ntiles - 1);
+            const uint32_t rows = last ? (uint32_t)P.n_last_mma : (uint32_t)TN;
+            mbar_expect_tx(bar_full(s), rows * (full ? KC : KT) * 2u);
+            const CUtensorMap* tm = last ? (full ? &tmBl : &tmBlt) : (full ? &tmB : &tmBt);
+            tma_load_2d(sB + (uint32_t)s * B_PANEL, tm, chunk_col(c), nt * TN, bar_full(s));
           }
         }
       }
@@ -482,7 +487,8 @@ __global__ void __launch_bounds__(256) row_prep_kernel(const ZT* __restrict__ z,
   }
 }
 
-// exact re-rank of two candidate codes per listed row (one warp per entry, fp64)
+// exact re-rank of two candidate codes per listed row (one warp per entry, fp64); all loads of an
+// entry are issued before the first use
 template <typename ZT>
 __global__ void __launch_bounds__(256) pair_recheck_kernel(const ZT* __restrict__ z, const float* __restrict__ E,
                                                            int D, const int* __restrict__ pair_list,
@@ -491,17 +497,49 @@ __global__ void __launch_bounds__(256) pair_recheck_kernel(const ZT* __restrict_
   const int lane = threadIdx.x & 31;
   const int n = counters[0];
   const int wstride = (gridDim.x * blockDim.x) >> 5;
+  constexpr int U = 4;                                   // 4 x 128 columns per pass
+  const bool vec = (D % 4 == 0) && sizeof(ZT) == 4;
   for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n; e += wstride) {
     const int row = pair_list[3 * e], a = pair_list[3 * e + 1], b = pair_list[3 * e + 2];
     const ZT* zr = z + (size_t)row * D;
     const float* ea = E + (size_t)a * D;
     const float* eb = E + (size_t)b * D;
     double da = 0.0, db = 0.0;
-    for (int j = lane; j < D; j += 32) {
-      const double zv = (double)ld_f32(zr + j);
-      const double xa = zv - (double)__ldg(ea + j), xb = zv - (double)__ldg(eb + j);
-      da = fma(xa, xa, da);
-      db = fma(xb, xb, db);
+    if (vec) {
+      const float* zf = reinterpret_cast<const float*>(zr);
+      for (int j0 = lane * 4; j0 < D; j0 += 128 * U) {
+        float4 zv[U], av[U], bv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + 128 * u;
+          if (j < D) {
+            zv[u] = __ldg(reinterpret_cast<const float4*>(zf + j));
+            av[u] = __ldg(reinterpret_cast<const float4*>(ea + j));
+            bv[u] = __ldg(reinterpret_cast<const float4*>(eb + j));
+          } else {
+            zv[u] = av[u] = bv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float zz[4] = {zv[u].x, zv[u].y, zv[u].z, zv[u].w};
+          const float aa[4] = {av[u].x, av[u].y, av[u].z, av[u].w};
+          const float bb[4] = {bv[u].x, bv[u].y, bv[u].z, bv[u].w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const double xa = (double)zz[c] - (double)aa[c], xb = (double)zz[c] - (double)bb[c];
+            da = fma(xa, xa, da);
+            db = fma(xb, xb, db);
+          }
+        }
+      }
+    } else {
+      for (int j = lane; j < D; j += 32) {
+        const double zv = (double)ld_f32(zr + j);
+        const double xa = zv - (double)__ldg(ea + j), xb = zv - (double)__ldg(eb + j);
+        da = fma(xa, xa, da);
+        db = fma(xb, xb, db);
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -608,7 +646,7 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
     G2V_LAUNCH_CHECK("row_prep_kernel");
   }
 
-  alignas(64) CUtensorMap tmA, tmAt, tmB, tmBt;
+  alignas(64) CUtensorMap tmA, tmAt, tmB, tmBt, tmBl, tmBlt;
   int rc;
   // main maps need a 64-wide box; if D < 64 there are no full panels and the main maps are unused
   const uint32_t main_box = (Dp >= KC) ? KC : KT;
@@ -617,19 +655,21 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
   if ((rc = make_map(&tmAt, z16, (uint64_t)N, (uint64_t)Dp, KT, TM, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
   if ((rc = make_map(&tmB, e16, (uint64_t)Kp, (uint64_t)Dp, main_box, TN, main_sw))) return rc;
   if ((rc = make_map(&tmBt, e16, (uint64_t)Kp, (uint64_t)Dp, KT, TN, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  if ((rc = make_map(&tmBl, e16, (uint64_t)Kp, (uint64_t)Dp, main_box, (uint32_t)P.n_last_mma, main_sw))) return rc;
+  if ((rc = make_map(&tmBlt, e16, (uint64_t)Kp, (uint64_t)Dp, KT, (uint32_t)P.n_last_mma, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
 
   const SmemPlan sp = smem_plan(P.n_full, P.n_tail);
   const size_t smem = sp.total + 1024;
   G2V_CUDA_CHECK(cudaFuncSetAttribute(tc_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = P.n_row_tiles < num_sms() ? P.n_row_tiles : num_sms();
-  tc_search_kernel<<<grid, NTHREADS, smem, st>>>(tmA, tmAt, tmB, tmBt, P);
+  tc_search_kernel<<<grid, NTHREADS, smem, st>>>(tmA, tmAt, tmB, tmBt, tmBl, tmBlt, P);
   G2V_LAUNCH_CHECK("tc_search_kernel");
 
   if (!(flags & G2V_NO_RECHECK)) {
     const int pgrid = num_sms() * 2;
     pair_recheck_kernel<ZT><<<pgrid, 256, 0, st>>>(z, E, D, pairs, counters, idx, stats);
     G2V_LAUNCH_CHECK("pair_recheck_kernel");
-    rc = launch_search_simt(z, z_dtype, E, cb, N, K, D, fulls, counters + 1, idx, stats, st);
+    rc = launch_full_recheck(z, z_dtype, E, cb, K, D, fulls, counters + 1, N, idx, stats, st);
     if (rc) return rc;
   }
   return G2V_OK;
