@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(NT) search_simt_kernel(
 // Phase A evaluates every distance in fp32 (tight bound: ~20 roundings per dot) and certifies the
 // rows whose top-2 gap exceeds that bound; phase B redoes the remaining rows in fp64.
 // ------------------------------------------------------------------------------------------
-constexpr int FR_ROWS = 8, FR_WARPS = 8;
+constexpr int FR_ROWS = 16, FR_WARPS = 8, FR_NJ = 4, FR_KC = 4;   // rows/batch, warps, column steps and codes per pass
 
 template <typename ZT>
 __global__ void __launch_bounds__(FR_WARPS * 32) full_recheck_kernel(
@@ -306,13 +306,14 @@ __global__ void __launch_bounds__(FR_WARPS * 32) full_recheck_kernel(
     const CbHeader* __restrict__ hdr, int K, int D, const int* __restrict__ list,
     const int* __restrict__ count, int* __restrict__ idx_out, unsigned long long* stats) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* zs = reinterpret_cast<float*>(smem_raw);                 // [FR_ROWS][D]
+  float* zs = reinterpret_cast<float*>(smem_raw);                 // [FR_ROWS][Dp], Dp = D rounded up to 32
+  const int Dp = (D + 31) & ~31;
   __shared__ double bv[FR_WARPS][FR_ROWS];
   __shared__ float b1[FR_WARPS][FR_ROWS], b2[FR_WARPS][FR_ROWS];
   __shared__ int bi[FR_WARPS][FR_ROWS];
   __shared__ int rows[FR_ROWS];
   __shared__ int need64[FR_ROWS];
-  __shared__ float z2s[FR_ROWS];
+  __shared__ float z2s[FR_ROWS], v1s[FR_ROWS], taus[FR_ROWS];
   __shared__ int n64;
   const int n = *count;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -322,44 +323,68 @@ __global__ void __launch_bounds__(FR_WARPS * 32) full_recheck_kernel(
     __syncthreads();
     if (threadIdx.x < FR_ROWS) rows[threadIdx.x] = (b0 + threadIdx.x < n) ? list[b0 + threadIdx.x] : -1;
     __syncthreads();
-    for (int i = threadIdx.x; i < FR_ROWS * D; i += blockDim.x) {
-      const int r = i / D, j = i - r * D;
-      zs[i] = rows[r] >= 0 ? to_f32(z[(size_t)rows[r] * D + j]) : 0.f;
+    for (int i = threadIdx.x; i < FR_ROWS * Dp; i += blockDim.x) {
+      const int r = i / Dp, j = i - r * Dp;
+      zs[i] = (rows[r] >= 0 && j < D) ? to_f32(z[(size_t)rows[r] * D + j]) : 0.f;
     }
     __syncthreads();
-    if (warp < FR_ROWS) {                                  // row norms for the fp32 error bound
+    for (int r = warp; r < FR_ROWS; r += FR_WARPS) {       // row norms for the fp32 error bound
       float s = 0.f;
-      for (int j = lane; j < D; j += 32) s = fmaf(zs[warp * D + j], zs[warp * D + j], s);
+      for (int j = lane; j < Dp; j += 32) s = fmaf(zs[r * Dp + j], zs[r * Dp + j], s);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) z2s[warp] = s;
+      if (lane == 0) z2s[r] = s;
     }
     // ---- phase A: fp32 distances, running top-2 per row ----
     float m1[FR_ROWS], m2[FR_ROWS];
     int i1[FR_ROWS];
 #pragma unroll
     for (int r = 0; r < FR_ROWS; ++r) { m1[r] = INFINITY; m2[r] = INFINITY; i1[r] = 0x7fffffff; }
-    for (int k = warp; k < K; k += FR_WARPS) {
-      const float* er = E + (size_t)k * D;
-      float part[FR_ROWS];
+    // each warp takes FR_KC codes at a time: one shared-memory read of a latent value feeds FR_KC FMAs
+    for (int kb = warp * FR_KC; kb < K; kb += FR_WARPS * FR_KC) {
+      float part[FR_KC][FR_ROWS];
 #pragma unroll
-      for (int r = 0; r < FR_ROWS; ++r) part[r] = 0.f;
-      for (int j = lane; j < D; j += 32) {
-        const float e = __ldg(er + j);
+      for (int c = 0; c < FR_KC; ++c)
 #pragma unroll
-        for (int r = 0; r < FR_ROWS; ++r) part[r] = fmaf(zs[r * D + j], e, part[r]);
+        for (int r = 0; r < FR_ROWS; ++r) part[c][r] = 0.f;
+      for (int j0 = lane; j0 < Dp; j0 += 32 * FR_NJ) {      // FR_KC*FR_NJ loads in flight, then the FMAs
+        float e[FR_KC][FR_NJ];
+#pragma unroll
+        for (int c = 0; c < FR_KC; ++c) {
+          const float* er = E + (size_t)min(kb + c, K - 1) * D;
+#pragma unroll
+          for (int u = 0; u < FR_NJ; ++u) e[c][u] = (j0 + 32 * u < D) ? __ldg(er + j0 + 32 * u) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < FR_NJ; ++u) {
+          const int j = j0 + 32 * u;
+          if (j < Dp) {
+#pragma unroll
+            for (int r = 0; r < FR_ROWS; ++r) {
+              const float zv = zs[r * Dp + j];
+#pragma unroll
+              for (int c = 0; c < FR_KC; ++c) part[c][r] = fmaf(zv, e[c][u], part[c][r]);
+            }
+          }
+        }
       }
-      const float ek = __ldg(e2 + k);
 #pragma unroll
-      for (int r = 0; r < FR_ROWS; ++r) {
-        float s = part[r];
+      for (int c = 0; c < FR_KC; ++c) {
+        const int k = kb + c;
+        if (k < K) {                                        // warp-uniform
+          const float ek = __ldg(e2 + k);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        const float d = fmaf(-2.f, s, ek);
-        const bool lt = d < m1[r];                          // ascending k inside a warp: first wins
-        m2[r] = fminf(m2[r], fmaxf(d, m1[r]));
-        i1[r] = lt ? k : i1[r];
-        m1[r] = fminf(m1[r], d);
+          for (int r = 0; r < FR_ROWS; ++r) {
+            float s = part[c][r];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float d = fmaf(-2.f, s, ek);
+            const bool lt = d < m1[r];                      // ascending k inside a warp: first wins
+            m2[r] = fminf(m2[r], fmaxf(d, m1[r]));
+            i1[r] = lt ? k : i1[r];
+            m1[r] = fminf(m1[r], d);
+          }
+        }
       }
     }
     if (lane == 0) {
@@ -380,7 +405,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32) full_recheck_kernel(
         id = take ? oi : id;
         v2 = nv2;
       }
-      // per-code error of this fp32 evaluation: (ceil(D/32) + 7) roundings on the dot, one on e2, one on d
+      // per-code error of this fp32 evaluation: (ceil(D/32) + 7) roundings cover the dot, e2 and d
       const float nsteps = (float)((D + 31) / 32 + 7);
       const float tau = 4.f * nsteps * kU32 * sqrtf(z2s[r] * e2max) + 4.f * kU32 * (e2max + fabsf(v1));
       int need = 0;
@@ -389,23 +414,67 @@ __global__ void __launch_bounds__(FR_WARPS * 32) full_recheck_kernel(
         need = !(v2 - v1 > tau);
       }
       need64[r] = need;
+      v1s[r] = v1;
+      taus[r] = tau;
       if (need) atomicAdd(&n64, 1);
     }
     __syncthreads();
-    // ---- phase B (rare): fp64 for the rows fp32 could not certify ----
+    // ---- phase B (rare): rows fp32 could not certify.  Re-scan the row in fp32 (same arithmetic,
+    // so the same values) and evaluate in fp64 only the codes within tau of its fp32 minimum ----
     for (int r = 0; r < FR_ROWS; ++r) {
       if (!need64[r]) continue;                            // block-uniform
+      const float lim = v1s[r] + taus[r];
       double best = INFINITY;
       int besti = 0x7fffffff;
-      for (int k = warp; k < K; k += FR_WARPS) {
-        const float* er = E + (size_t)k * D;
-        double part = 0.0;
-        for (int j = lane; j < D; j += 32) {
-          const double df = (double)zs[r * D + j] - (double)__ldg(er + j);
-          part = fma(df, df, part);
+      for (int kb = warp * FR_KC; kb < K; kb += FR_WARPS * FR_KC) {
+        float part[FR_KC];
+#pragma unroll
+        for (int c = 0; c < FR_KC; ++c) part[c] = 0.f;
+        for (int j0 = lane; j0 < Dp; j0 += 32 * FR_NJ) {
+          float e[FR_KC][FR_NJ];
+#pragma unroll
+          for (int c = 0; c < FR_KC; ++c) {
+            const float* er = E + (size_t)min(kb + c, K - 1) * D;
+#pragma unroll
+            for (int u = 0; u < FR_NJ; ++u) e[c][u] = (j0 + 32 * u < D) ? __ldg(er + j0 + 32 * u) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < FR_NJ; ++u) {
+            const int j = j0 + 32 * u;
+            if (j < Dp) {
+              const float zv = zs[r * Dp + j];
+#pragma unroll
+              for (int c = 0; c < FR_KC; ++c) part[c] = fmaf(zv, e[c][u], part[c]);
+            }
+          }
         }
-        part = warp_sum(part);
-        if (part < best) { best = part; besti = k; }
+#pragma unroll
+        for (int c = 0; c < FR_KC; ++c) {
+          const int k = kb + c;
+          if (k >= K) continue;                             // warp-uniform
+          float sdot = part[c];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
+          const float d = fmaf(-2.f, sdot, __ldg(e2 + k));
+          if (!(d <= lim)) continue;                        // warp-uniform: d is identical in all lanes
+          const float* er = E + (size_t)k * D;
+          double acc = 0.0;
+          for (int j0 = lane; j0 < D; j0 += 32 * 8) {
+            float ev[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) ev[u] = (j0 + 32 * u < D) ? __ldg(er + j0 + 32 * u) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int j = j0 + 32 * u;
+              if (j < D) {
+                const double df = (double)zs[r * Dp + j] - (double)ev[u];
+                acc = fma(df, df, acc);
+              }
+            }
+          }
+          acc = warp_sum(acc);
+          if (acc < best) { best = acc; besti = k; }        // ascending k inside a warp: first wins
+        }
       }
       if (lane == 0) { bv[warp][0] = best; bi[warp][0] = besti; }
       __syncthreads();
@@ -414,7 +483,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32) full_recheck_kernel(
         int id = bi[0][0];
         for (int w = 1; w < FR_WARPS; ++w)
           if (bv[w][0] < v || (bv[w][0] == v && bi[w][0] < id)) { v = bv[w][0]; id = bi[w][0]; }
-        idx_out[rows[r]] = id;
+        if (id != 0x7fffffff) idx_out[rows[r]] = id;
       }
       __syncthreads();
     }
@@ -671,8 +740,8 @@ template <typename ZT>
 static int launch_full_recheck_t(const ZT* z, const float* E, const void* cb, int K, int D, const int32_t* list,
                                  const int32_t* count, int64_t max_rows, int32_t* idx,
                                  unsigned long long* stats, cudaStream_t st) {
-  const size_t smem = (size_t)FR_ROWS * D * sizeof(float);
-  if (smem > 48 * 1024)
+  const size_t smem = (size_t)FR_ROWS * ((D + 31) / 32 * 32) * sizeof(float);
+  if (smem > 40 * 1024)
     G2V_CUDA_CHECK(cudaFuncSetAttribute(full_recheck_kernel<ZT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long batches = (max_rows + FR_ROWS - 1) / FR_ROWS;
   long long cap = (long long)num_sms() * 4;

@@ -22,6 +22,7 @@
 
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace g2v {
 namespace {
@@ -90,27 +91,71 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar), "r"(parity)
       : "memory");
 }
+// TMA tile load.  CG == 2: the .cta_group::2 form, whose completion bytes are credited to the
+// mbarrier at the same offset in the LEADER CTA (peer bit of the shared::cluster address cleared).
+template <int CG>
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(tm), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
+  if constexpr (CG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(tm), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+  }
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// arrive on `bar` once every tcgen05 op issued so far by this thread has retired; CG == 2 signals
+// the barrier at that offset in BOTH CTAs of the pair
+template <int CG>
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  } else {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+  }
 }
+template <int CG>
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if constexpr (CG == 1) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -137,23 +182,26 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes
   d |= (uint64_t)layout << 61;
   return d;
 }
-// instruction descriptor: fp16 x fp16 -> fp32, both K-major, M = 128, N = n
-__device__ __forceinline__ uint32_t umma_idesc(int n) {
-  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+// instruction descriptor: fp16 x fp16 -> fp32, both K-major, M = m (128, or 256 for a CTA pair), N = n
+__device__ __forceinline__ uint32_t umma_idesc(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------
 // shared memory plan
 // ------------------------------------------------------------------------------------------
 struct SmemPlan {
-  uint32_t a_off, b_off, e2_off, bar_off, tmem_off, total;
+  uint32_t a_off, b_off, b_stage, e2_off, bar_off, tmem_off, total;
 };
-__host__ __device__ inline SmemPlan smem_plan(int n_full, int n_tail) {
+// cg = CTAs cooperating on one MMA (cta_group): each holds its own 128-row A tile and 1/cg of every
+// codebook stage
+__host__ __device__ inline SmemPlan smem_plan(int n_full, int n_tail, int cg) {
   SmemPlan p;
   p.a_off = 0;
   uint32_t a_bytes = (uint32_t)n_full * A_PANEL + (uint32_t)n_tail * A_TAIL;
   p.b_off = (a_bytes + 1023u) & ~1023u;
-  p.e2_off = p.b_off + NSTAGE * B_PANEL;
+  p.b_stage = B_PANEL / cg;
+  p.e2_off = p.b_off + NSTAGE * p.b_stage;
   p.bar_off = p.e2_off + 2 * TN * 4;
   p.tmem_off = p.bar_off + 8 * (2 * NSTAGE + 2 * MAX_CHUNKS + 4);
   p.total = p.tmem_off + 16;
@@ -192,6 +240,7 @@ struct Cand {
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
+template <int CG>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAt,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBt,
@@ -201,7 +250,10 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t raw = smem_u32(smem_dyn);
   const uint32_t base = (raw + 1023u) & ~1023u;
   unsigned char* gbase = smem_dyn + (base - raw);
-  const SmemPlan sp = smem_plan(P.n_full, P.n_tail);
+  const SmemPlan sp = smem_plan(P.n_full, P.n_tail, CG);
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int n_groups = gridDim.x / CG, group = blockIdx.x / CG;   // CTA groups walk the row tiles
 
   const uint32_t sA = base + sp.a_off, sB = base + sp.b_off;
   float* e2s = reinterpret_cast<float*>(gbase + sp.e2_off);
@@ -221,17 +273,25 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
     for (int c = 0; c < MAX_CHUNKS; ++c) { mbar_init(bar_afull(c), 1); mbar_init(bar_aempty(c), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_accfull(a), 1); mbar_init(bar_accempty(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_accfull(a), 1); mbar_init(bar_accempty(a), 4 * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
-                 "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                   "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                   "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 1) __syncthreads();
+  else cluster_sync_all();       // the peer's barriers must be initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -243,19 +303,21 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // =========================== B producer ===========================
     if (lane == 0) {
       uint32_t g = 0;  // global chunk counter
-      for (int tile = blockIdx.x; tile < P.n_row_tiles; tile += gridDim.x) {
+      for (int tile = group; tile < P.n_row_tiles; tile += n_groups) {
         for (int nt = 0; nt < P.n_ntiles; ++nt) {
           for (int c = 0; c < n_chunks; ++c, ++g) {
             const int s = g % NSTAGE;
             const uint32_t round = g / NSTAGE;
             mbar_wait(bar_empty(s), (round & 1u) ^ 1u);
             const bool full = c < n_full;
-            // the last code tile only fetches the rows its MMA reads (n_last_mma <= 256)
+            // the last code tile only fetches the rows its MMA reads (n_last_mma <= 256); each CTA
+            // of a pair fetches its 1/CG slice of the code rows
             const bool last = (nt == P.n_ntiles - 1);
             const uint32_t rows = last ? (uint32_t)P.n_last_mma : (uint32_t)TN;
-            mbar_expect_tx(bar_full(s), rows * (full ? KC : KT) * 2u);
+            if (leader) mbar_expect_tx(bar_full(s), rows * (full ? KC : KT) * 2u);   // bytes of all CTAs
             const CUtensorMap* tm = last ? (full ? &tmBl : &tmBlt) : (full ? &tmB : &tmBt);
-            tma_load_2d(sB + (uint32_t)s * B_PANEL, tm, chunk_col(c), nt * TN, bar_full(s));
+            tma_load_2d<CG>(sB + (uint32_t)s * sp.b_stage, tm, chunk_col(c), nt * TN + (int)(cta_rank * (rows / CG)),
+                            bar_full(s));
           }
         }
       }
@@ -264,24 +326,25 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // =========================== A producer ===========================
     if (lane == 0) {
       uint32_t ti = 0;
-      for (int tile = blockIdx.x; tile < P.n_row_tiles; tile += gridDim.x, ++ti) {
+      for (int tile = group; tile < P.n_row_tiles; tile += n_groups, ++ti) {
         for (int c = 0; c < n_chunks; ++c) {
           mbar_wait(bar_aempty(c), (ti & 1u) ^ 1u);
           const bool full = c < n_full;
-          mbar_expect_tx(bar_afull(c), full ? A_PANEL : A_TAIL);
-          tma_load_2d(a_chunk_addr(c), full ? &tmA : &tmAt, chunk_col(c), tile * TM, bar_afull(c));
+          if (leader) mbar_expect_tx(bar_afull(c), (uint32_t)CG * (full ? A_PANEL : A_TAIL));
+          tma_load_2d<CG>(a_chunk_addr(c), full ? &tmA : &tmAt, chunk_col(c), (tile * CG + (int)cta_rank) * TM,
+                          bar_afull(c));
         }
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    if (lane == 0 && leader) {                  // one thread of the leader CTA issues for the whole group
       uint32_t g = 0, it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < P.n_row_tiles; tile += gridDim.x, ++ti) {
+      for (int tile = group; tile < P.n_row_tiles; tile += n_groups, ++ti) {
         for (int nt = 0; nt < P.n_ntiles; ++nt, ++it) {
           const uint32_t as = it & 1u, around = it >> 1;
           const bool last_nt = (nt == P.n_ntiles - 1);
-          const uint32_t idesc = umma_idesc(last_nt ? P.n_last_mma : TN);
+          const uint32_t idesc = umma_idesc(TM * CG, last_nt ? P.n_last_mma : TN);
           mbar_wait(bar_accempty(as), (around & 1u) ^ 1u);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + as * TN;
@@ -291,23 +354,23 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (nt == 0) mbar_wait(bar_afull(c), ti & 1u);
             mbar_wait(bar_full(s), round & 1u);
             tc_fence_after();
-            const uint32_t a_addr = a_chunk_addr(c), b_addr = sB + (uint32_t)s * B_PANEL;
+            const uint32_t a_addr = a_chunk_addr(c), b_addr = sB + (uint32_t)s * sp.b_stage;
             if (c < n_full) {
 #pragma unroll
               for (int k = 0; k < KC / KT; ++k) {
                 const uint64_t ad = umma_desc(a_addr + k * 32, 1024, 2);
                 const uint64_t bd = umma_desc(b_addr + k * 32, 1024, 2);
-                tc_mma_f16(d_tmem, ad, bd, idesc, (c | k) != 0);
+                tc_mma_f16<CG>(d_tmem, ad, bd, idesc, (c | k) != 0);
               }
             } else {
               const uint64_t ad = umma_desc(a_addr, 256, 6);
               const uint64_t bd = umma_desc(b_addr, 256, 6);
-              tc_mma_f16(d_tmem, ad, bd, idesc, c != 0);
+              tc_mma_f16<CG>(d_tmem, ad, bd, idesc, c != 0);
             }
-            tc_commit(bar_empty(s));                 // B stage free once these MMAs retire
-            if (last_nt) tc_commit(bar_aempty(c));   // A panel free after its last use in this row tile
+            tc_commit<CG>(bar_empty(s));                 // B stage free once these MMAs retire
+            if (last_nt) tc_commit<CG>(bar_aempty(c));   // A panel free after its last use in this row tile
           }
-          tc_commit(bar_accfull(as));
+          tc_commit<CG>(bar_accfull(as));
         }
       }
     }
@@ -317,8 +380,8 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int r = q * 32 + lane;            // row within the tile == TMEM lane
     const int et = threadIdx.x - EPI_WARP0 * 32;
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < P.n_row_tiles; tile += gridDim.x) {
-      const long long row = (long long)tile * TM + r;
+    for (int tile = group; tile < P.n_row_tiles; tile += n_groups) {
+      const long long row = ((long long)tile * CG + cta_rank) * TM + r;
       const bool valid = row < P.N;
       RowInfo ri = valid ? P.rowinfo[row] : RowInfo{0.f, 0.f, 0.f, 0.f};
       uint32_t m1[32], m2[32];
@@ -361,7 +424,10 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // all TMEM reads of this stage are complete (last wait::ld above): hand it back
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_accempty(as));
+        if (lane == 0) {
+          if (CG == 1 || leader) mbar_arrive(bar_accempty(as));
+          else mbar_arrive_cluster(bar_accempty(as), 0);      // the leader's MMA thread waits for both CTAs
+        }
       }
 
       // ---- per-row decision: best three keys over the 32 chains ----
@@ -411,9 +477,13 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 1) __syncthreads();
+  else cluster_sync_all();       // neither CTA may leave while the other still reads its smem / TMEM
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if constexpr (CG == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -632,9 +702,13 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
   P.n_full = Dp / KC;
   P.n_tail = (Dp % KC) / KT;
   P.n_chunks = P.n_full + P.n_tail;
+  // CTA pairs (cta_group::2: M = 256 per MMA, each CTA streams half of every codebook stage) as soon
+  // as there are two row tiles; G2V_TC_CG=1 forces the single-CTA kernel
+  int cg = (N > TM) ? 2 : 1;
+  if (const char* env = getenv("G2V_TC_CG")) cg = (atoi(env) == 1) ? 1 : cg;
   P.n_ntiles = (K + TN - 1) / TN;
-  P.n_last_mma = round_up(K - (P.n_ntiles - 1) * TN, 16);
-  P.n_row_tiles = (int)((N + TM - 1) / TM);
+  P.n_last_mma = round_up(K - (P.n_ntiles - 1) * TN, 16 * cg);
+  P.n_row_tiles = (int)((N + (long long)TM * cg - 1) / ((long long)TM * cg));   // tiles of 128*cg rows
   P.rowinfo = rowinfo; P.e2 = e2; P.idx = idx;
   P.pair_list = pairs; P.full_list = fulls; P.counters = counters; P.flags = flags;
 
@@ -653,16 +727,35 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
   const CUtensorMapSwizzle main_sw = (Dp >= KC) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
   if ((rc = make_map(&tmA, z16, (uint64_t)N, (uint64_t)Dp, main_box, TM, main_sw))) return rc;
   if ((rc = make_map(&tmAt, z16, (uint64_t)N, (uint64_t)Dp, KT, TM, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
-  if ((rc = make_map(&tmB, e16, (uint64_t)Kp, (uint64_t)Dp, main_box, TN, main_sw))) return rc;
-  if ((rc = make_map(&tmBt, e16, (uint64_t)Kp, (uint64_t)Dp, KT, TN, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
-  if ((rc = make_map(&tmBl, e16, (uint64_t)Kp, (uint64_t)Dp, main_box, (uint32_t)P.n_last_mma, main_sw))) return rc;
-  if ((rc = make_map(&tmBlt, e16, (uint64_t)Kp, (uint64_t)Dp, KT, (uint32_t)P.n_last_mma, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  const uint32_t brow = TN / cg, blast = (uint32_t)P.n_last_mma / cg;     // code rows each CTA fetches per stage
+  if ((rc = make_map(&tmB, e16, (uint64_t)Kp, (uint64_t)Dp, main_box, brow, main_sw))) return rc;
+  if ((rc = make_map(&tmBt, e16, (uint64_t)Kp, (uint64_t)Dp, KT, brow, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  if ((rc = make_map(&tmBl, e16, (uint64_t)Kp, (uint64_t)Dp, main_box, blast, main_sw))) return rc;
+  if ((rc = make_map(&tmBlt, e16, (uint64_t)Kp, (uint64_t)Dp, KT, blast, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
 
-  const SmemPlan sp = smem_plan(P.n_full, P.n_tail);
+  const SmemPlan sp = smem_plan(P.n_full, P.n_tail, cg);
   const size_t smem = sp.total + 1024;
-  G2V_CUDA_CHECK(cudaFuncSetAttribute(tc_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = P.n_row_tiles < num_sms() ? P.n_row_tiles : num_sms();
-  tc_search_kernel<<<grid, NTHREADS, smem, st>>>(tmA, tmAt, tmB, tmBt, tmBl, tmBlt, P);
+  const int max_groups = num_sms() / cg;
+  const int groups = P.n_row_tiles < max_groups ? P.n_row_tiles : max_groups;
+  if (cg == 1) {
+    G2V_CUDA_CHECK(cudaFuncSetAttribute(tc_search_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_search_kernel<1><<<groups, NTHREADS, smem, st>>>(tmA, tmAt, tmB, tmBt, tmBl, tmBlt, P);
+  } else {
+    G2V_CUDA_CHECK(cudaFuncSetAttribute(tc_search_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(groups * 2);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    G2V_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_search_kernel<2>, tmA, tmAt, tmB, tmBt, tmBl, tmBlt, P));
+  }
   G2V_LAUNCH_CHECK("tc_search_kernel");
 
   if (!(flags & G2V_NO_RECHECK)) {
@@ -681,7 +774,7 @@ bool tc_supported(int K, int D) {
   const int Dp = round_up(D, 16);
   if (Dp > kMaxDp || K > kMaxK) return false;
   if ((long long)K * D < 16384) return false;       // tiny problems: the fp32 path is already bandwidth-bound
-  const SmemPlan sp = smem_plan(Dp / KC, (Dp % KC) / KT);
+  const SmemPlan sp = smem_plan(Dp / KC, (Dp % KC) / KT, 1);
   return sp.total + 1024 <= 227 * 1024;
 }
 
