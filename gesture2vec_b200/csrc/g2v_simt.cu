@@ -293,24 +293,55 @@ __global__ void __launch_bounds__(NT) search_simt_kernel(
 
 // ------------------------------------------------------------------------------------------
 // exact re-rank of the listed rows over the whole codebook, first index on exact ties.
-// One CTA takes FR_ROWS rows at a time so each codebook row read from L2 serves all of them;
-// warps split the codes, lanes split the dimensions (coalesced), fixed reduction order.
-// Phase A evaluates every distance in fp32 (tight bound: ~20 roundings per dot) and certifies the
-// rows whose top-2 gap exceeds that bound; phase B redoes the remaining rows in fp64.
+// One CTA takes FR_ROWS rows at a time (held in shared memory) so each codebook row fetched from
+// L2 serves all of them.  Thread = code: a thread walks its code's D values once (128-bit loads)
+// and the latent values arrive as shared-memory broadcasts, so there is no cross-lane reduction
+// in the inner loop.  Phase A evaluates every distance in fp32 and certifies the rows whose top-2
+// gap exceeds the fp32 error bound; phase B re-scans an uncertified row with the same arithmetic
+// and evaluates in fp64 only the codes within the bound of its minimum.
 // ------------------------------------------------------------------------------------------
-constexpr int FR_ROWS = 16, FR_WARPS = 8, FR_NJ = 4, FR_KC = 4;   // rows/batch, warps, column steps and codes per pass
+constexpr int FR_ROWS = 16, FR_THREADS = 256;
 
-template <typename ZT>
-__global__ void __launch_bounds__(FR_WARPS * 32) full_recheck_kernel(
+// fp32 dot products of one code row with R latent rows (sequential over D: same order everywhere)
+template <int R, bool VEC>
+__device__ __forceinline__ void fr_dots(const float* __restrict__ er, const float* __restrict__ zs, int Dp4, int D,
+                                        float (&acc)[R]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.f;
+  if (VEC) {
+#pragma unroll 2
+    for (int j = 0; j < D; j += 4) {
+      const float4 e = ldg4(er + j);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float4 zv = *reinterpret_cast<const float4*>(zs + r * Dp4 + j);
+        acc[r] = fmaf(zv.x, e.x, acc[r]);
+        acc[r] = fmaf(zv.y, e.y, acc[r]);
+        acc[r] = fmaf(zv.z, e.z, acc[r]);
+        acc[r] = fmaf(zv.w, e.w, acc[r]);
+      }
+    }
+  } else {
+    for (int j = 0; j < D; ++j) {
+      const float e = __ldg(er + j);
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = fmaf(zs[r * Dp4 + j], e, acc[r]);
+    }
+  }
+}
+
+template <typename ZT, bool VEC>
+__global__ void __launch_bounds__(FR_THREADS) full_recheck_kernel(
     const ZT* __restrict__ z, const float* __restrict__ E, const float* __restrict__ e2,
     const CbHeader* __restrict__ hdr, int K, int D, const int* __restrict__ list,
     const int* __restrict__ count, int* __restrict__ idx_out, unsigned long long* stats) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* zs = reinterpret_cast<float*>(smem_raw);                 // [FR_ROWS][Dp], Dp = D rounded up to 32
-  const int Dp = (D + 31) & ~31;
-  __shared__ double bv[FR_WARPS][FR_ROWS];
-  __shared__ float b1[FR_WARPS][FR_ROWS], b2[FR_WARPS][FR_ROWS];
-  __shared__ int bi[FR_WARPS][FR_ROWS];
+  float* zs = reinterpret_cast<float*>(smem_raw);                 // [FR_ROWS][Dp4]
+  const int Dp4 = (D + 3) & ~3;
+  constexpr int NW = FR_THREADS / 32;
+  __shared__ double bv[NW];
+  __shared__ float b1[NW][FR_ROWS], b2[NW][FR_ROWS];
+  __shared__ int bi[NW][FR_ROWS];
   __shared__ int rows[FR_ROWS];
   __shared__ int need64[FR_ROWS];
   __shared__ float z2s[FR_ROWS], v1s[FR_ROWS], taus[FR_ROWS];
@@ -323,68 +354,47 @@ __global__ void __launch_bounds__(FR_WARPS * 32) full_recheck_kernel(
     __syncthreads();
     if (threadIdx.x < FR_ROWS) rows[threadIdx.x] = (b0 + threadIdx.x < n) ? list[b0 + threadIdx.x] : -1;
     __syncthreads();
-    for (int i = threadIdx.x; i < FR_ROWS * Dp; i += blockDim.x) {
-      const int r = i / Dp, j = i - r * Dp;
+    for (int i = threadIdx.x; i < FR_ROWS * Dp4; i += blockDim.x) {
+      const int r = i / Dp4, j = i - r * Dp4;
       zs[i] = (rows[r] >= 0 && j < D) ? to_f32(z[(size_t)rows[r] * D + j]) : 0.f;
     }
     __syncthreads();
-    for (int r = warp; r < FR_ROWS; r += FR_WARPS) {       // row norms for the fp32 error bound
+    for (int r = warp; r < FR_ROWS; r += NW) {              // row norms for the fp32 error bound
       float s = 0.f;
-      for (int j = lane; j < Dp; j += 32) s = fmaf(zs[r * Dp + j], zs[r * Dp + j], s);
+      for (int j = lane; j < Dp4; j += 32) s = fmaf(zs[r * Dp4 + j], zs[r * Dp4 + j], s);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if (lane == 0) z2s[r] = s;
     }
-    // ---- phase A: fp32 distances, running top-2 per row ----
+    // ---- phase A: fp32 distances, running top-2 per row (codes ascend inside a thread) ----
     float m1[FR_ROWS], m2[FR_ROWS];
     int i1[FR_ROWS];
 #pragma unroll
     for (int r = 0; r < FR_ROWS; ++r) { m1[r] = INFINITY; m2[r] = INFINITY; i1[r] = 0x7fffffff; }
-    // each warp takes FR_KC codes at a time: one shared-memory read of a latent value feeds FR_KC FMAs
-    for (int kb = warp * FR_KC; kb < K; kb += FR_WARPS * FR_KC) {
-      float part[FR_KC][FR_ROWS];
+    for (int k = threadIdx.x; k < K; k += FR_THREADS) {
+      float acc[FR_ROWS];
+      fr_dots<FR_ROWS, VEC>(E + (size_t)k * D, zs, Dp4, D, acc);
+      const float ek = __ldg(e2 + k);
 #pragma unroll
-      for (int c = 0; c < FR_KC; ++c)
-#pragma unroll
-        for (int r = 0; r < FR_ROWS; ++r) part[c][r] = 0.f;
-      for (int j0 = lane; j0 < Dp; j0 += 32 * FR_NJ) {      // FR_KC*FR_NJ loads in flight, then the FMAs
-        float e[FR_KC][FR_NJ];
-#pragma unroll
-        for (int c = 0; c < FR_KC; ++c) {
-          const float* er = E + (size_t)min(kb + c, K - 1) * D;
-#pragma unroll
-          for (int u = 0; u < FR_NJ; ++u) e[c][u] = (j0 + 32 * u < D) ? __ldg(er + j0 + 32 * u) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < FR_NJ; ++u) {
-          const int j = j0 + 32 * u;
-          if (j < Dp) {
-#pragma unroll
-            for (int r = 0; r < FR_ROWS; ++r) {
-              const float zv = zs[r * Dp + j];
-#pragma unroll
-              for (int c = 0; c < FR_KC; ++c) part[c][r] = fmaf(zv, e[c][u], part[c][r]);
-            }
-          }
-        }
+      for (int r = 0; r < FR_ROWS; ++r) {
+        const float d = fmaf(-2.f, acc[r], ek);
+        const bool lt = d < m1[r];
+        m2[r] = fminf(m2[r], fmaxf(d, m1[r]));
+        i1[r] = lt ? k : i1[r];
+        m1[r] = fminf(m1[r], d);
       }
+    }
 #pragma unroll
-      for (int c = 0; c < FR_KC; ++c) {
-        const int k = kb + c;
-        if (k < K) {                                        // warp-uniform
-          const float ek = __ldg(e2 + k);
+    for (int r = 0; r < FR_ROWS; ++r) {                     // warp merge (value, then lower index)
 #pragma unroll
-          for (int r = 0; r < FR_ROWS; ++r) {
-            float s = part[c][r];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            const float d = fmaf(-2.f, s, ek);
-            const bool lt = d < m1[r];                      // ascending k inside a warp: first wins
-            m2[r] = fminf(m2[r], fmaxf(d, m1[r]));
-            i1[r] = lt ? k : i1[r];
-            m1[r] = fminf(m1[r], d);
-          }
-        }
+      for (int o = 16; o > 0; o >>= 1) {
+        const float o1 = __shfl_xor_sync(0xffffffffu, m1[r], o), o2 = __shfl_xor_sync(0xffffffffu, m2[r], o);
+        const int oi = __shfl_xor_sync(0xffffffffu, i1[r], o);
+        const bool take = (o1 < m1[r]) || (o1 == m1[r] && oi < i1[r]);
+        const float nv2 = take ? fminf(m1[r], o2) : fminf(m2[r], o1);
+        m1[r] = take ? o1 : m1[r];
+        i1[r] = take ? oi : i1[r];
+        m2[r] = nv2;
       }
     }
     if (lane == 0) {
@@ -396,7 +406,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32) full_recheck_kernel(
       const int r = threadIdx.x;
       float v1 = b1[0][r], v2 = b2[0][r];
       int id = bi[0][r];
-      for (int w = 1; w < FR_WARPS; ++w) {
+      for (int w = 1; w < NW; ++w) {
         const float o1 = b1[w][r], o2 = b2[w][r];
         const int oi = bi[w][r];
         const bool take = (o1 < v1) || (o1 == v1 && oi < id);
@@ -405,9 +415,8 @@ __global__ void __launch_bounds__(FR_WARPS * 32) full_recheck_kernel(
         id = take ? oi : id;
         v2 = nv2;
       }
-      // per-code error of this fp32 evaluation: (ceil(D/32) + 7) roundings cover the dot, e2 and d
-      const float nsteps = (float)((D + 31) / 32 + 7);
-      const float tau = 4.f * nsteps * kU32 * sqrtf(z2s[r] * e2max) + 4.f * kU32 * (e2max + fabsf(v1));
+      // per-code error: D sequential FMA roundings on the dot, one on e2, one on d; a gap can be off by twice that
+      const float tau = 4.f * (float)(D + 2) * kU32 * sqrtf(z2s[r] * e2max) + 4.f * kU32 * (e2max + fabsf(v1));
       int need = 0;
       if (rows[r] >= 0) {
         idx_out[rows[r]] = id;
@@ -419,70 +428,39 @@ __global__ void __launch_bounds__(FR_WARPS * 32) full_recheck_kernel(
       if (need) atomicAdd(&n64, 1);
     }
     __syncthreads();
-    // ---- phase B (rare): rows fp32 could not certify.  Re-scan the row in fp32 (same arithmetic,
-    // so the same values) and evaluate in fp64 only the codes within tau of its fp32 minimum ----
+    // ---- phase B (rare): same fp32 scan of the one row, fp64 for the codes within tau of its minimum ----
     for (int r = 0; r < FR_ROWS; ++r) {
       if (!need64[r]) continue;                            // block-uniform
       const float lim = v1s[r] + taus[r];
       double best = INFINITY;
       int besti = 0x7fffffff;
-      for (int kb = warp * FR_KC; kb < K; kb += FR_WARPS * FR_KC) {
-        float part[FR_KC];
-#pragma unroll
-        for (int c = 0; c < FR_KC; ++c) part[c] = 0.f;
-        for (int j0 = lane; j0 < Dp; j0 += 32 * FR_NJ) {
-          float e[FR_KC][FR_NJ];
-#pragma unroll
-          for (int c = 0; c < FR_KC; ++c) {
-            const float* er = E + (size_t)min(kb + c, K - 1) * D;
-#pragma unroll
-            for (int u = 0; u < FR_NJ; ++u) e[c][u] = (j0 + 32 * u < D) ? __ldg(er + j0 + 32 * u) : 0.f;
-          }
-#pragma unroll
-          for (int u = 0; u < FR_NJ; ++u) {
-            const int j = j0 + 32 * u;
-            if (j < Dp) {
-              const float zv = zs[r * Dp + j];
-#pragma unroll
-              for (int c = 0; c < FR_KC; ++c) part[c] = fmaf(zv, e[c][u], part[c]);
-            }
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < FR_KC; ++c) {
-          const int k = kb + c;
-          if (k >= K) continue;                             // warp-uniform
-          float sdot = part[c];
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
-          const float d = fmaf(-2.f, sdot, __ldg(e2 + k));
-          if (!(d <= lim)) continue;                        // warp-uniform: d is identical in all lanes
+      for (int k = threadIdx.x; k < K; k += FR_THREADS) {
+        float acc[1];
+        fr_dots<1, VEC>(E + (size_t)k * D, zs + r * Dp4, Dp4, D, acc);
+        const float d = fmaf(-2.f, acc[0], __ldg(e2 + k));
+        if (d <= lim) {
           const float* er = E + (size_t)k * D;
-          double acc = 0.0;
-          for (int j0 = lane; j0 < D; j0 += 32 * 8) {
-            float ev[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) ev[u] = (j0 + 32 * u < D) ? __ldg(er + j0 + 32 * u) : 0.f;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int j = j0 + 32 * u;
-              if (j < D) {
-                const double df = (double)zs[r * Dp + j] - (double)ev[u];
-                acc = fma(df, df, acc);
-              }
-            }
+          double s = 0.0;
+          for (int j = 0; j < D; ++j) {
+            const double df = (double)zs[r * Dp4 + j] - (double)__ldg(er + j);
+            s = fma(df, df, s);
           }
-          acc = warp_sum(acc);
-          if (acc < best) { best = acc; besti = k; }        // ascending k inside a warp: first wins
+          if (s < best) { best = s; besti = k; }            // ascending k inside a thread: first wins
         }
       }
-      if (lane == 0) { bv[warp][0] = best; bi[warp][0] = besti; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (ov < best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+      }
+      if (lane == 0) { bv[warp] = best; bi[warp][0] = besti; }
       __syncthreads();
       if (threadIdx.x == 0) {
-        double v = bv[0][0];
+        double v = bv[0];
         int id = bi[0][0];
-        for (int w = 1; w < FR_WARPS; ++w)
-          if (bv[w][0] < v || (bv[w][0] == v && bi[w][0] < id)) { v = bv[w][0]; id = bi[w][0]; }
+        for (int w = 1; w < NW; ++w)
+          if (bv[w] < v || (bv[w] == v && bi[w][0] < id)) { v = bv[w]; id = bi[w][0]; }
         if (id != 0x7fffffff) idx_out[rows[r]] = id;
       }
       __syncthreads();
@@ -740,15 +718,22 @@ template <typename ZT>
 static int launch_full_recheck_t(const ZT* z, const float* E, const void* cb, int K, int D, const int32_t* list,
                                  const int32_t* count, int64_t max_rows, int32_t* idx,
                                  unsigned long long* stats, cudaStream_t st) {
-  const size_t smem = (size_t)FR_ROWS * ((D + 31) / 32 * 32) * sizeof(float);
-  if (smem > 40 * 1024)
-    G2V_CUDA_CHECK(cudaFuncSetAttribute(full_recheck_kernel<ZT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = (size_t)FR_ROWS * ((D + 3) / 4 * 4) * sizeof(float);
+  const bool vec = (D % 4 == 0) && aligned16(E);
   long long batches = (max_rows + FR_ROWS - 1) / FR_ROWS;
-  long long cap = (long long)num_sms() * 4;
+  long long cap = (long long)num_sms() * 2;
   const int grid = (int)(batches < 1 ? 1 : (batches < cap ? batches : cap));
   const auto* hdr = reinterpret_cast<const CbHeader*>(cb);
   const float* e2 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_e2_offset());
-  full_recheck_kernel<ZT><<<grid, FR_WARPS * 32, smem, st>>>(z, E, e2, hdr, K, D, list, count, idx, stats);
+  if (vec) {
+    if (smem > 40 * 1024)
+      G2V_CUDA_CHECK(cudaFuncSetAttribute(full_recheck_kernel<ZT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    full_recheck_kernel<ZT, true><<<grid, FR_THREADS, smem, st>>>(z, E, e2, hdr, K, D, list, count, idx, stats);
+  } else {
+    if (smem > 40 * 1024)
+      G2V_CUDA_CHECK(cudaFuncSetAttribute(full_recheck_kernel<ZT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    full_recheck_kernel<ZT, false><<<grid, FR_THREADS, smem, st>>>(z, E, e2, hdr, K, D, list, count, idx, stats);
+  }
   G2V_LAUNCH_CHECK("full_recheck_kernel");
   return G2V_OK;
 }

@@ -31,17 +31,18 @@ constexpr int TM = 128;                 // rows per tile (UMMA M)
 constexpr int TN = 256;                 // codes per accumulator stage (max UMMA N)
 constexpr int KC = 64;                  // fp16 per full K panel (128 bytes)
 constexpr int KT = 16;                  // fp16 per tail K panel (32 bytes) == UMMA K
-constexpr int NSTAGE = 3;
+constexpr int MAX_STAGES = 8;            // barrier slots; the ring depth itself is chosen per launch
 constexpr int A_PANEL = TM * KC * 2;    // 16384
 constexpr int A_TAIL = TM * KT * 2;     // 4096
 constexpr int B_PANEL = TN * KC * 2;    // 32768
 constexpr int B_TAIL = TN * KT * 2;     // 8192
 constexpr int MAX_CHUNKS = 12;
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 384;           // 4 producer/MMA warps + 8 epilogue warps
 constexpr int EPI_WARP0 = 4;
 constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23: float bits = 0x4B400000 + round(v)
 constexpr int kMaxDp = 496;
 constexpr int kMaxK = 16384;            // 9-bit column-group field of the key
+constexpr unsigned kDbgSkipMma = 0x100u, kDbgSkipEpi = 0x200u;   // G2V_TC_DEBUG bring-up switches (timing only)
 
 struct RowInfo {       // 16 bytes per row, written by row_prep_kernel
   float cS;            // -2 / (scale_z * scale_e) * S
@@ -56,6 +57,7 @@ struct TcParams {
   int n_full, n_tail, n_chunks;
   int n_ntiles, n_last_mma;     // code tiles; UMMA N of the last one (multiple of 16)
   int n_row_tiles;
+  int nstage;                   // depth of the codebook-stage ring
   const RowInfo* rowinfo;
   const float* e2;
   int* idx;
@@ -107,6 +109,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
         : "memory");
   }
 }
+// one lane of a converged warp; everything around it stays warp-uniform, so descriptors and
+// addresses live in uniform registers (UTCHMMA / UTMALDG take uniform operands)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -157,15 +172,12 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
         : "memory");
   }
 }
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
 }
@@ -191,19 +203,20 @@ __device__ __forceinline__ uint32_t umma_idesc(int m, int n) {
 // shared memory plan
 // ------------------------------------------------------------------------------------------
 struct SmemPlan {
-  uint32_t a_off, b_off, b_stage, e2_off, bar_off, tmem_off, total;
+  uint32_t a_off, b_off, b_stage, e2_off, xch_off, bar_off, tmem_off, total;
 };
 // cg = CTAs cooperating on one MMA (cta_group): each holds its own 128-row A tile and 1/cg of every
 // codebook stage
-__host__ __device__ inline SmemPlan smem_plan(int n_full, int n_tail, int cg) {
+__host__ __device__ inline SmemPlan smem_plan(int n_full, int n_tail, int cg, int nstage) {
   SmemPlan p;
   p.a_off = 0;
   uint32_t a_bytes = (uint32_t)n_full * A_PANEL + (uint32_t)n_tail * A_TAIL;
   p.b_off = (a_bytes + 1023u) & ~1023u;
   p.b_stage = B_PANEL / cg;
-  p.e2_off = p.b_off + NSTAGE * p.b_stage;
-  p.bar_off = p.e2_off + 2 * TN * 4;
-  p.tmem_off = p.bar_off + 8 * (2 * NSTAGE + 2 * MAX_CHUNKS + 4);
+  p.e2_off = p.b_off + (uint32_t)nstage * p.b_stage;
+  p.xch_off = p.e2_off + 2 * TN * 4;          // 128 rows x 8 words: epilogue half 1 -> half 0
+  p.bar_off = p.xch_off + TM * 8 * 4;
+  p.tmem_off = p.bar_off + 8 * (2 * MAX_STAGES + 2 * MAX_CHUNKS + 4);
   p.total = p.tmem_off + 16;
   return p;
 }
@@ -211,12 +224,13 @@ __host__ __device__ inline SmemPlan smem_plan(int n_full, int n_tail, int cg) {
 // ------------------------------------------------------------------------------------------
 // epilogue helpers
 // ------------------------------------------------------------------------------------------
-// one 32-column chunk: key = fixed-point(e2 - 2 z.e) << 9 | column group; chain j = column % 32
+// 16 columns of a chunk: key = fixed-point(e2 - 2 z.e) << 9 | column group; one running top-2 chain
+// per column position
 template <bool PARTIAL>
-__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* __restrict__ e2c, float cS, float S,
-                                          uint32_t group, int nvalid, uint32_t (&m1)[32], uint32_t (&m2)[32]) {
+__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[16], const float* __restrict__ e2c, float cS, float S,
+                                          uint32_t group, int nvalid, uint32_t (&m1)[16], uint32_t (&m2)[16]) {
 #pragma unroll
-  for (int j4 = 0; j4 < 8; ++j4) {
+  for (int j4 = 0; j4 < 4; ++j4) {
     const float4 e = *reinterpret_cast<const float4*>(e2c + 4 * j4);
     const float ee[4] = {e.x, e.y, e.z, e.w};
 #pragma unroll
@@ -232,10 +246,20 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* 
 }
 
 struct Cand {
-  uint32_t key;
+  uint32_t key;    // best key of a chain
   uint32_t key2;   // second-best key of the same chain
-  int j;
+  int j;           // chain id = column % 32
 };
+// keep the two smallest chain minima (c1 <= c2) and the third smallest key (k3)
+__device__ __forceinline__ void cand_insert(Cand& c1, Cand& c2, uint32_t& k3, const Cand n) {
+  if (n.key < c1.key) {
+    k3 = c2.key; c2 = c1; c1 = n;
+  } else if (n.key < c2.key) {
+    k3 = c2.key; c2 = n;
+  } else {
+    k3 = min(k3, n.key);
+  }
+}
 
 // ------------------------------------------------------------------------------------------
 // the kernel
@@ -250,30 +274,32 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t raw = smem_u32(smem_dyn);
   const uint32_t base = (raw + 1023u) & ~1023u;
   unsigned char* gbase = smem_dyn + (base - raw);
-  const SmemPlan sp = smem_plan(P.n_full, P.n_tail, CG);
+  const SmemPlan sp = smem_plan(P.n_full, P.n_tail, CG, P.nstage);
+  const uint32_t NST = (uint32_t)P.nstage;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   const int n_groups = gridDim.x / CG, group = blockIdx.x / CG;   // CTA groups walk the row tiles
 
   const uint32_t sA = base + sp.a_off, sB = base + sp.b_off;
   float* e2s = reinterpret_cast<float*>(gbase + sp.e2_off);
+  uint32_t* xch = reinterpret_cast<uint32_t*>(gbase + sp.xch_off);
   const uint32_t bars = base + sp.bar_off;
   // barrier map
   auto bar_full = [&](int s) { return bars + 8u * s; };
-  auto bar_empty = [&](int s) { return bars + 8u * (NSTAGE + s); };
-  auto bar_afull = [&](int c) { return bars + 8u * (2 * NSTAGE + c); };
-  auto bar_aempty = [&](int c) { return bars + 8u * (2 * NSTAGE + MAX_CHUNKS + c); };
-  auto bar_accfull = [&](int a) { return bars + 8u * (2 * NSTAGE + 2 * MAX_CHUNKS + a); };
-  auto bar_accempty = [&](int a) { return bars + 8u * (2 * NSTAGE + 2 * MAX_CHUNKS + 2 + a); };
+  auto bar_empty = [&](int s) { return bars + 8u * (MAX_STAGES + s); };
+  auto bar_afull = [&](int c) { return bars + 8u * (2 * MAX_STAGES + c); };
+  auto bar_aempty = [&](int c) { return bars + 8u * (2 * MAX_STAGES + MAX_CHUNKS + c); };
+  auto bar_accfull = [&](int a) { return bars + 8u * (2 * MAX_STAGES + 2 * MAX_CHUNKS + a); };
+  auto bar_accempty = [&](int a) { return bars + 8u * (2 * MAX_STAGES + 2 * MAX_CHUNKS + 2 + a); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + sp.tmem_off);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_chunks = P.n_chunks, n_full = P.n_full;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
     for (int c = 0; c < MAX_CHUNKS; ++c) { mbar_init(bar_afull(c), 1); mbar_init(bar_aempty(c), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_accfull(a), 1); mbar_init(bar_accempty(a), 4 * CG); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_accfull(a), 1); mbar_init(bar_accempty(a), 8 * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -301,44 +327,50 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // =========================== B producer ===========================
-    if (lane == 0) {
+    {   // whole warp walks the schedule (uniform control flow); one elected lane issues
       uint32_t g = 0;  // global chunk counter
       for (int tile = group; tile < P.n_row_tiles; tile += n_groups) {
         for (int nt = 0; nt < P.n_ntiles; ++nt) {
           for (int c = 0; c < n_chunks; ++c, ++g) {
-            const int s = g % NSTAGE;
-            const uint32_t round = g / NSTAGE;
+            const int s = g % NST;
+            const uint32_t round = g / NST;
             mbar_wait(bar_empty(s), (round & 1u) ^ 1u);
             const bool full = c < n_full;
             // the last code tile only fetches the rows its MMA reads (n_last_mma <= 256); each CTA
             // of a pair fetches its 1/CG slice of the code rows
             const bool last = (nt == P.n_ntiles - 1);
             const uint32_t rows = last ? (uint32_t)P.n_last_mma : (uint32_t)TN;
-            if (leader) mbar_expect_tx(bar_full(s), rows * (full ? KC : KT) * 2u);   // bytes of all CTAs
             const CUtensorMap* tm = last ? (full ? &tmBl : &tmBlt) : (full ? &tmB : &tmBt);
-            tma_load_2d<CG>(sB + (uint32_t)s * sp.b_stage, tm, chunk_col(c), nt * TN + (int)(cta_rank * (rows / CG)),
-                            bar_full(s));
+            if (elect_one()) {
+              if (leader) mbar_expect_tx(bar_full(s), rows * (full ? KC : KT) * 2u);   // bytes of all CTAs
+              tma_load_2d<CG>(sB + (uint32_t)s * sp.b_stage, tm, chunk_col(c), nt * TN + (int)(cta_rank * (rows / CG)),
+                              bar_full(s));
+            }
+            __syncwarp();
           }
         }
       }
     }
   } else if (warp == 2) {
     // =========================== A producer ===========================
-    if (lane == 0) {
+    {
       uint32_t ti = 0;
       for (int tile = group; tile < P.n_row_tiles; tile += n_groups, ++ti) {
         for (int c = 0; c < n_chunks; ++c) {
           mbar_wait(bar_aempty(c), (ti & 1u) ^ 1u);
           const bool full = c < n_full;
-          if (leader) mbar_expect_tx(bar_afull(c), (uint32_t)CG * (full ? A_PANEL : A_TAIL));
-          tma_load_2d<CG>(a_chunk_addr(c), full ? &tmA : &tmAt, chunk_col(c), (tile * CG + (int)cta_rank) * TM,
-                          bar_afull(c));
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(bar_afull(c), (uint32_t)CG * (full ? A_PANEL : A_TAIL));
+            tma_load_2d<CG>(a_chunk_addr(c), full ? &tmA : &tmAt, chunk_col(c), (tile * CG + (int)cta_rank) * TM,
+                            bar_afull(c));
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0 && leader) {                  // one thread of the leader CTA issues for the whole group
+    if (leader) {                  // the leader CTA issues for the whole group; one elected lane per step
       uint32_t g = 0, it = 0, ti = 0;
       for (int tile = group; tile < P.n_row_tiles; tile += n_groups, ++ti) {
         for (int nt = 0; nt < P.n_ntiles; ++nt, ++it) {
@@ -349,76 +381,81 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + as * TN;
           for (int c = 0; c < n_chunks; ++c, ++g) {
-            const int s = g % NSTAGE;
-            const uint32_t round = g / NSTAGE;
+            const int s = g % NST;
+            const uint32_t round = g / NST;
             if (nt == 0) mbar_wait(bar_afull(c), ti & 1u);
             mbar_wait(bar_full(s), round & 1u);
             tc_fence_after();
             const uint32_t a_addr = a_chunk_addr(c), b_addr = sB + (uint32_t)s * sp.b_stage;
-            if (c < n_full) {
+            const bool fullp = c < n_full;
+            const uint64_t ad0 = fullp ? umma_desc(a_addr, 1024, 2) : umma_desc(a_addr, 256, 6);
+            const uint64_t bd0 = fullp ? umma_desc(b_addr, 1024, 2) : umma_desc(b_addr, 256, 6);
+            if (elect_one()) {
+              if (P.flags & kDbgSkipMma) {
+                // bring-up aid: measure everything but the tensor work
+              } else if (fullp) {
 #pragma unroll
-              for (int k = 0; k < KC / KT; ++k) {
-                const uint64_t ad = umma_desc(a_addr + k * 32, 1024, 2);
-                const uint64_t bd = umma_desc(b_addr + k * 32, 1024, 2);
-                tc_mma_f16<CG>(d_tmem, ad, bd, idesc, (c | k) != 0);
+                for (int k = 0; k < KC / KT; ++k)        // +32 bytes per K step = +2 in the address field
+                  tc_mma_f16<CG>(d_tmem, ad0 + 2u * k, bd0 + 2u * k, idesc, (c | k) != 0);
+              } else {
+                tc_mma_f16<CG>(d_tmem, ad0, bd0, idesc, c != 0);
               }
-            } else {
-              const uint64_t ad = umma_desc(a_addr, 256, 6);
-              const uint64_t bd = umma_desc(b_addr, 256, 6);
-              tc_mma_f16<CG>(d_tmem, ad, bd, idesc, c != 0);
+              tc_commit<CG>(bar_empty(s));                 // B stage free once these MMAs retire
+              if (last_nt) tc_commit<CG>(bar_aempty(c));   // A panel free after its last use in this row tile
+              if (c == n_chunks - 1) tc_commit<CG>(bar_accfull(as));
             }
-            tc_commit<CG>(bar_empty(s));                 // B stage free once these MMAs retire
-            if (last_nt) tc_commit<CG>(bar_aempty(c));   // A panel free after its last use in this row tile
+            __syncwarp();
           }
-          tc_commit<CG>(bar_accfull(as));
         }
       }
     }
   } else if (warp >= EPI_WARP0) {
     // =========================== epilogue ===========================
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;            // row within the tile == TMEM lane
-    const int et = threadIdx.x - EPI_WARP0 * 32;
+    // 8 warps: two per TMEM lane quarter, each taking 16 of every 32 columns (so every scheduler
+    // has two epilogue warps to interleave).  Thread = one row; 16 running top-2 chains per thread.
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    const int eh = (warp - EPI_WARP0) >> 2;          // which 16-column half of each 32-column chunk
+    const int r = q * 32 + lane;                     // row within the tile == TMEM lane
+    const int et = threadIdx.x - EPI_WARP0 * 32;     // 0..255
+    uint32_t* xrow = xch + (size_t)r * 8;            // hand-off slot of this row (half 1 -> half 0)
     uint32_t it = 0;
     for (int tile = group; tile < P.n_row_tiles; tile += n_groups) {
       const long long row = ((long long)tile * CG + cta_rank) * TM + r;
       const bool valid = row < P.N;
       RowInfo ri = valid ? P.rowinfo[row] : RowInfo{0.f, 0.f, 0.f, 0.f};
-      uint32_t m1[32], m2[32];
+      uint32_t m1[16], m2[16];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) { m1[j] = 0xFFFFFFFFu; m2[j] = 0xFFFFFFFFu; }
+      for (int j = 0; j < 16; ++j) { m1[j] = 0xFFFFFFFFu; m2[j] = 0xFFFFFFFFu; }
 
       for (int nt = 0; nt < P.n_ntiles; ++nt, ++it) {
         const uint32_t as = it & 1u, around = it >> 1;
         float* e2c = e2s + as * TN;
-        // stage this code tile's ||e||^2 (two per thread)
-        {
-          const int k0 = nt * TN + et, k1 = k0 + 128;
+        {  // stage this code tile's ||e||^2 (one per thread)
+          const int k0 = nt * TN + et;
           e2c[et] = (k0 < P.K) ? __ldg(P.e2 + k0) : 0.f;
-          e2c[et + 128] = (k1 < P.K) ? __ldg(P.e2 + k1) : 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         mbar_wait(bar_accfull(as), around & 1u);
         tc_fence_after();
         const int ncols = min(TN, P.K - nt * TN);
         const int nch = (ncols + 31) >> 5;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * TN;
-        uint32_t va[32], vb[32];
-        tc_ld32(taddr, va);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * TN + eh * 16;
+        uint32_t va[16], vb[16];
+        tc_ld16(taddr, va);
         for (int ch = 0; ch < nch; ch += 2) {
           tc_wait_ld();
-          if (ch + 1 < nch) tc_ld32(taddr + (ch + 1) * 32, vb);
-          {
-            const int nv = ncols - ch * 32;
-            if (nv >= 32) epi_chunk<false>(va, e2c + ch * 32, ri.cS, ri.S, (uint32_t)(nt * 8 + ch), 32, m1, m2);
-            else epi_chunk<true>(va, e2c + ch * 32, ri.cS, ri.S, (uint32_t)(nt * 8 + ch), nv, m1, m2);
+          if (ch + 1 < nch) tc_ld16(taddr + (ch + 1) * 32, vb);
+          if (!(P.flags & kDbgSkipEpi)) {
+            const int nv = ncols - ch * 32 - eh * 16;
+            if (nv >= 16) epi_chunk<false>(va, e2c + ch * 32 + eh * 16, ri.cS, ri.S, (uint32_t)(nt * 8 + ch), 16, m1, m2);
+            else epi_chunk<true>(va, e2c + ch * 32 + eh * 16, ri.cS, ri.S, (uint32_t)(nt * 8 + ch), nv, m1, m2);
           }
           if (ch + 1 < nch) {
             tc_wait_ld();
-            if (ch + 2 < nch) tc_ld32(taddr + (ch + 2) * 32, va);
-            const int nv = ncols - (ch + 1) * 32;
-            if (nv >= 32) epi_chunk<false>(vb, e2c + (ch + 1) * 32, ri.cS, ri.S, (uint32_t)(nt * 8 + ch + 1), 32, m1, m2);
-            else epi_chunk<true>(vb, e2c + (ch + 1) * 32, ri.cS, ri.S, (uint32_t)(nt * 8 + ch + 1), nv, m1, m2);
+            if (ch + 2 < nch) tc_ld16(taddr + (ch + 2) * 32, va);
+            const int nv = (P.flags & kDbgSkipEpi) ? -1000 : ncols - (ch + 1) * 32 - eh * 16;
+            if (nv >= 16) epi_chunk<false>(vb, e2c + (ch + 1) * 32 + eh * 16, ri.cS, ri.S, (uint32_t)(nt * 8 + ch + 1), 16, m1, m2);
+            else epi_chunk<true>(vb, e2c + (ch + 1) * 32 + eh * 16, ri.cS, ri.S, (uint32_t)(nt * 8 + ch + 1), nv, m1, m2);
           }
         }
         // all TMEM reads of this stage are complete (last wait::ld above): hand it back
@@ -430,49 +467,55 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
 
-      // ---- per-row decision: best three keys over the 32 chains ----
+      // ---- per-row decision ----
+      // best two chain minima (with the runner-up of their own chain) and the third chain minimum,
+      // first over this thread's 16 chains, then merged with the other half's
       Cand c1{0xFFFFFFFFu, 0xFFFFFFFFu, 0}, c2{0xFFFFFFFFu, 0xFFFFFFFFu, 0};
       uint32_t k3 = 0xFFFFFFFFu;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const uint32_t k = m1[j];
-        if (k < c1.key) {
-          k3 = c2.key; c2 = c1; c1 = Cand{k, m2[j], j};
-        } else if (k < c2.key) {
-          k3 = c2.key; c2 = Cand{k, m2[j], j};
+      for (int j = 0; j < 16; ++j) cand_insert(c1, c2, k3, Cand{m1[j], m2[j], eh * 16 + j});
+      if (eh == 1) {
+        xrow[0] = c1.key; xrow[1] = c1.key2; xrow[2] = (uint32_t)c1.j;
+        xrow[3] = c2.key; xrow[4] = c2.key2; xrow[5] = (uint32_t)c2.j;
+        xrow[6] = k3;
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");     // the two warps of this lane quarter
+      if (eh == 0) {
+        const Cand o1{xrow[0], xrow[1], (int)xrow[2]}, o2{xrow[3], xrow[4], (int)xrow[5]};
+        const uint32_t ok3 = xrow[6];
+        cand_insert(c1, c2, k3, o1);
+        cand_insert(c1, c2, k3, o2);
+        k3 = min(k3, ok3);
+        // candidates ordered over all codes: t1 <= t2 <= t3
+        const uint32_t t1 = c1.key;
+        const int code1 = (int)(t1 & 511u) * 32 + c1.j;
+        uint32_t t2, t3;
+        int code2;
+        bool same_chain;
+        if (c1.key2 < c2.key) {            // runner-up sits in the winner's own chain: its third is unknown
+          t2 = c1.key2; code2 = (int)(t2 & 511u) * 32 + c1.j; same_chain = true; t3 = c2.key;
         } else {
-          k3 = min(k3, k);
+          t2 = c2.key; code2 = (int)(t2 & 511u) * 32 + c2.j; same_chain = false;
+          t3 = min(min(c1.key2, c2.key2), k3);
         }
-      }
-      // candidates ordered over all codes: t1 <= t2 <= t3
-      const uint32_t t1 = c1.key;
-      const int code1 = (int)(t1 & 511u) * 32 + c1.j;
-      uint32_t t2, t3;
-      int code2;
-      bool same_chain;
-      if (c1.key2 < c2.key) {            // runner-up sits in the winner's own chain: its third is unknown
-        t2 = c1.key2; code2 = (int)(t2 & 511u) * 32 + c1.j; same_chain = true; t3 = c2.key;
-      } else {
-        t2 = c2.key; code2 = (int)(t2 & 511u) * 32 + c2.j; same_chain = false;
-        t3 = min(min(c1.key2, c2.key2), k3);
-      }
-      if (valid) {
-        const uint32_t tau = (uint32_t)fminf(ri.tauI, 4194304.f);
-        const uint32_t v1 = t1 >> 9, v2 = t2 >> 9, v3 = t3 >> 9;
-        int result = code1;
-        if (!(P.flags & G2V_NO_RECHECK) && (v2 - v1 <= tau)) {
-          if (!same_chain && (v3 - v1 > tau) && code2 < P.K) {
-            const int slot = atomicAdd(P.counters + 0, 1);
-            P.pair_list[3 * slot + 0] = (int)row;
-            P.pair_list[3 * slot + 1] = code1;
-            P.pair_list[3 * slot + 2] = code2;
-          } else {
-            const int slot = atomicAdd(P.counters + 1, 1);
-            P.full_list[slot] = (int)row;
+        if (valid) {
+          const uint32_t tau = (uint32_t)fminf(ri.tauI, 4194304.f);
+          const uint32_t v1 = t1 >> 9, v2 = t2 >> 9, v3 = t3 >> 9;
+          if (!(P.flags & G2V_NO_RECHECK) && (v2 - v1 <= tau)) {
+            if (!same_chain && (v3 - v1 > tau) && code2 < P.K) {
+              const int slot = atomicAdd(P.counters + 0, 1);
+              P.pair_list[3 * slot + 0] = (int)row;
+              P.pair_list[3 * slot + 1] = code1;
+              P.pair_list[3 * slot + 2] = code2;
+            } else {
+              const int slot = atomicAdd(P.counters + 1, 1);
+              P.full_list[slot] = (int)row;
+            }
           }
+          P.idx[row] = min(code1, P.K - 1);
         }
-        P.idx[row] = min(result, P.K - 1);
       }
+      asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");     // slot may be rewritten by the next tile
     }
   }
 
@@ -711,6 +754,7 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
   P.n_row_tiles = (int)((N + (long long)TM * cg - 1) / ((long long)TM * cg));   // tiles of 128*cg rows
   P.rowinfo = rowinfo; P.e2 = e2; P.idx = idx;
   P.pair_list = pairs; P.full_list = fulls; P.counters = counters; P.flags = flags;
+  if (const char* env = getenv("G2V_TC_DEBUG")) P.flags |= ((unsigned)atoi(env) & 3u) << 8;   // results are wrong with these
 
   const int n_ksteps = P.n_full * (KC / KT) + P.n_tail;
   {
@@ -733,7 +777,12 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
   if ((rc = make_map(&tmBl, e16, (uint64_t)Kp, (uint64_t)Dp, main_box, blast, main_sw))) return rc;
   if ((rc = make_map(&tmBlt, e16, (uint64_t)Kp, (uint64_t)Dp, KT, blast, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
 
-  const SmemPlan sp = smem_plan(P.n_full, P.n_tail, cg);
+  // ring depth: whatever shared memory is left after the resident row tile, capped at MAX_STAGES
+  // (the ring has to cover the TMA round trip, ~2.5k cycles, at 512 MMA cycles per full panel)
+  int nstage = MAX_STAGES;
+  while (nstage > 2 && smem_plan(P.n_full, P.n_tail, cg, nstage).total + 1024 > 227 * 1024) --nstage;
+  P.nstage = nstage;
+  const SmemPlan sp = smem_plan(P.n_full, P.n_tail, cg, nstage);
   const size_t smem = sp.total + 1024;
   const int max_groups = num_sms() / cg;
   const int groups = P.n_row_tiles < max_groups ? P.n_row_tiles : max_groups;
@@ -774,7 +823,7 @@ bool tc_supported(int K, int D) {
   const int Dp = round_up(D, 16);
   if (Dp > kMaxDp || K > kMaxK) return false;
   if ((long long)K * D < 16384) return false;       // tiny problems: the fp32 path is already bandwidth-bound
-  const SmemPlan sp = smem_plan(Dp / KC, (Dp % KC) / KT, 1);
+  const SmemPlan sp = smem_plan(Dp / KC, (Dp % KC) / KT, 1, 2);
   return sp.total + 1024 <= 227 * 1024;
 }
 
