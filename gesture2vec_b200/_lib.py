@@ -26,6 +26,7 @@ SIGNATURES = {
     "g2v_last_error_detail": (C.c_char_p, []),
     "g2v_codebook_bytes": (_sz, [_i, _i]),
     "g2v_codebook_prepare": (_i, [_p, _i, _i, _p, _sz, _p]),
+    "g2v_profile_next_search": (_i, [_p, _p]),
     "g2v_search_path": (_i, [_i, _i, _u]),
     "g2v_workspace_bytes": (_sz, [_i64, _i, _i, _i, _u]),
     "g2v_vq_search": (_i, [_p, _i, _p, _p, _i64, _i, _i, _p, _p, _p, _sz, _u, _p]),

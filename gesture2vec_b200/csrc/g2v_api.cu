@@ -35,6 +35,13 @@ int num_sms() {
   return cached;
 }
 
+static thread_local cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
+void profile_take(cudaEvent_t* start, cudaEvent_t* stop) {
+  *start = g_prof_start;
+  *stop = g_prof_stop;
+  g_prof_start = g_prof_stop = nullptr;
+}
+
 static int check_arch() {
   static thread_local int cached_dev = -1, ok = 0;
   int dev = 0;
@@ -92,6 +99,12 @@ int g2v_codebook_prepare(const float* E, int K, int D, void* cb, size_t cb_bytes
   int rc = check_arch();
   if (rc) return rc;
   return launch_codebook_prepare(E, K, D, cb, (cudaStream_t)stream);
+}
+
+int g2v_profile_next_search(void* ev_start, void* ev_stop) {
+  g_prof_start = (cudaEvent_t)ev_start;
+  g_prof_stop = (cudaEvent_t)ev_stop;
+  return G2V_OK;
 }
 
 int g2v_search_path(int K, int D, unsigned flags) {

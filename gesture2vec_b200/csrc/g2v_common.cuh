@@ -11,31 +11,55 @@
 namespace g2v {
 
 // ---------------------------------------------------------------------------------------------
-// Codebook aux buffer ("cb"): header + ||e||^2 + fp16 operand copy.  Layout in bytes:
+// Codebook aux buffer ("cb"): header + norm table + ||e||^2 + fp16 operand copy.  Layout in bytes:
 //   [0, 256)                       CbHeader
-//   [256, 256 + 4*Kp)              e2[Kp] fp32 (fp64-accumulated, rounded once; +inf for k >= K)
+//   [256, 768)                     ntab[128] fp32: ntab[b] = largest ||e_k|| among codes whose norm falls in
+//                                  quarter-octave bucket <= b (see norm_bucket) -- "reachable norm" lookup
+//   [768, 768 + 4*Kp)              e2[Kp] fp32 (fp64-accumulated, rounded once; +inf for k >= K)
 //   [off16, off16 + 2*Kp*Dp)       E16[Kp][Dp] fp16, zero padded, scaled by header.scale_e
 // Kp = K rounded up to 256, Dp = D rounded up to 16.
+//
+// Why the table: every error bound is linear in the norm of the codes that could still win a row.
+// A code can only win if ||e_k|| <= ||z|| + sqrt(d_min), so bounds use the largest norm below that
+// reach instead of the global maximum -- EMA codebooks carry dead codes with norms ~1e5 that would
+// otherwise make every row look uncertain.
 // ---------------------------------------------------------------------------------------------
 struct CbHeader {
   float e2max;      // max_k ||e_k||^2
-  float q4max;      // max_k (sum_j e_kj^4)^(1/2)    (variance bound of the fp16 rounding error)
+  float e2min;      // min_k ||e_k||^2
   float amax;       // max |e_kj|
   float scale_e;    // power of two the fp16 copy was multiplied by (brings amax into [256,512))
   int K, D, Kp, Dp;
   int magic;
-  float smax;       // max_k || e_k - fp16(e_k*scale_e)/scale_e ||_2   (rounding residual of the fp16 copy)
+  float sfrac;      // max_k ||e_k - fp16(e_k*scale_e)/scale_e|| / ||e_k||: measured residual of the fp16 copy
   int pad[54];
 };
 static_assert(sizeof(CbHeader) == 256, "CbHeader must be 256 bytes");
-constexpr int kCbMagic = 0x67327631;  // "g2v1"
+constexpr int kCbMagic = 0x67327632;  // "g2v2"
+constexpr int kNormBuckets = 128;
 
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
-inline size_t cb_e2_offset() { return 256; }
-inline size_t cb_e16_offset(int K) { return 256 + (size_t)round_up(K, 256) * 4; }  // multiple of 1024
+inline size_t cb_tab_offset() { return 256; }
+inline size_t cb_e2_offset() { return 768; }
+inline size_t cb_e16_offset(int K) { return 768 + (size_t)round_up(K, 256) * 4; }  // 256-byte aligned
 inline size_t cb_total_bytes(int K, int D) {
   return cb_e16_offset(K) + (size_t)round_up(K, 256) * round_up(D, 16) * 2;
 }
+
+#ifdef __CUDACC__
+// quarter-octave bucket of a norm: 2^-16 .. 2^16 -> 0 .. 127 (clamped)
+__device__ __forceinline__ int norm_bucket(float c) {
+  int b = (__float_as_int(c) >> 21) - ((127 - 16) << 2);
+  return b < 0 ? 0 : (b > kNormBuckets - 1 ? kNormBuckets - 1 : b);
+}
+// largest code norm that a row with norm `znorm` and (approximate) best squared distance `d1` can
+// still be won by: ||e_k|| <= ||z|| + sqrt(d_k) and d_k <= d_min.  The factor 2 on the sqrt and the 1 %
+// on ||z|| absorb the error of d1 itself.
+__device__ __forceinline__ float reachable_norm(const float* __restrict__ ntab, float znorm, float d1) {
+  const float cstar = 1.01f * znorm + 2.f * sqrtf(fmaxf(d1, 0.f)) + 1e-30f;
+  return ntab[norm_bucket(cstar)];
+}
+#endif
 
 // error recording (thread local), defined in g2v_api.cu
 void set_error_detail(const char* fmt, ...);
@@ -54,6 +78,8 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 int num_sms();
+// one-shot profiling events (thread local), see g2v_profile_next_search
+void profile_take(cudaEvent_t* start, cudaEvent_t* stop);
 
 // ---- launchers implemented in g2v_simt.cu ----------------------------------------------------
 int launch_codebook_prepare(const float* E, int K, int D, void* cb, cudaStream_t st);

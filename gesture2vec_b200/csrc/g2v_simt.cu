@@ -44,7 +44,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // codebook preparation
 // ------------------------------------------------------------------------------------------
 __global__ void cb_rows_kernel(const float* __restrict__ E, int K, int D, int Kp, CbHeader* hdr,
-                               float* __restrict__ e2) {
+                               float* __restrict__ ntab, float* __restrict__ e2) {
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= Kp) return;
   if (warp >= K) {
@@ -69,12 +69,19 @@ __global__ void cb_rows_kernel(const float* __restrict__ E, int K, int D, int Kp
     e2[warp] = f2;
     // non-negative floats order like their bit patterns
     atomicMax(reinterpret_cast<int*>(&hdr->e2max), __float_as_int(f2));
-    atomicMax(reinterpret_cast<int*>(&hdr->q4max), __float_as_int((float)sqrt(s4)));
+    atomicMin(reinterpret_cast<int*>(&hdr->e2min), __float_as_int(f2));
     atomicMax(reinterpret_cast<int*>(&hdr->amax), __float_as_int(am));
+    const float nrm = sqrtf(f2) * 1.0001f;
+    atomicMax(reinterpret_cast<int*>(&ntab[norm_bucket(nrm)]), __float_as_int(nrm));
   }
 }
 
-__global__ void cb_header_kernel(CbHeader* hdr, int K, int D, int Kp, int Dp) {
+__global__ void cb_header_kernel(CbHeader* hdr, float* ntab, int K, int D, int Kp, int Dp) {
+  float run = 0.f;                                   // prefix maximum over the norm buckets
+  for (int b = 0; b < kNormBuckets; ++b) {
+    run = fmaxf(run, ntab[b]);
+    ntab[b] = run;
+  }
   float am = hdr->amax;
   float sc = 1.f;
   if (am > 0.f && isfinite(am)) {
@@ -94,17 +101,23 @@ __global__ void cb_fp16_kernel(const float* __restrict__ E, int K, int D, int Kp
   if (warp >= Kp) return;
   const float sc = hdr->scale_e, inv = 1.f / sc;   // power of two: exact
   __half* o = E16 + (size_t)warp * Dp;
-  float s2 = 0.f;
+  float s2 = 0.f, n2 = 0.f;
   for (int j = lane; j < Dp; j += 32) {
     float v = (warp < K && j < D) ? E[(size_t)warp * D + j] : 0.f;
     __half h = __float2half_rn(v * sc);
     float r = v - __half2float(h) * inv;
     s2 = fmaf(r, r, s2);
+    n2 = fmaf(v, v, n2);
     o[j] = h;
   }
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, off);
-  if (lane == 0 && warp < K) atomicMax(reinterpret_cast<int*>(&hdr->smax), __float_as_int(sqrtf(s2) * 1.0001f));
+  for (int off = 16; off > 0; off >>= 1) {
+    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+    n2 += __shfl_xor_sync(0xffffffffu, n2, off);
+  }
+  // residual relative to the code's own norm, so one scalar bounds every code: ||r_e,k|| <= sfrac ||e_k||
+  if (lane == 0 && warp < K && n2 > 0.f)
+    atomicMax(reinterpret_cast<int*>(&hdr->sfrac), __float_as_int(sqrtf(s2 / n2) * 1.001f));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -154,7 +167,7 @@ __device__ __forceinline__ void load8(const T* __restrict__ base, long long row,
 template <bool VEC, typename ZT>
 __global__ void __launch_bounds__(NT) search_simt_kernel(
     const ZT* __restrict__ z, const float* __restrict__ E, const float* __restrict__ e2,
-    const CbHeader* __restrict__ hdr, long long N, int K, int D, int* __restrict__ full_list,
+    const float* __restrict__ ntab, long long N, int K, int D, int* __restrict__ full_list,
     int* __restrict__ full_count, int* __restrict__ idx_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SearchSmem& S = *reinterpret_cast<SearchSmem*>(smem_raw);
@@ -163,7 +176,6 @@ __global__ void __launch_bounds__(NT) search_simt_kernel(
   const long long n_rows = N;
   const int nk = (D + BK - 1) / BK;
   const int n_ctile = (K + BN - 1) / BN;
-  const float e2max = hdr->e2max;
 
   for (long long tile = blockIdx.x; tile * BM < n_rows; tile += gridDim.x) {
     __syncthreads();  // previous tile fully done with smem
@@ -282,8 +294,10 @@ __global__ void __launch_bounds__(NT) search_simt_kernel(
         idx_out[g] = i1[i];
         // |d_hat - d| <= 2*D*u*|z||e| + u*e2 + u*|d_hat| per code; the gap of two codes can be
         // off by twice that.
-        float z2 = S.z2p[0][r] + S.z2p[1][r];
-        float tau = 4.f * (float)D * kU32 * sqrtf(z2 * e2max) + 4.f * kU32 * (e2max + fabsf(m1[i]));
+        // (|e| bounded by the largest code norm that can still win this row, see reachable_norm)
+        const float z2 = S.z2p[0][r] + S.z2p[1][r], zn = sqrtf(z2) * 1.0001f;
+        const float cu = reachable_norm(ntab, zn, z2 + m1[i]);
+        const float tau = 4.f * (float)(D + 2) * kU32 * zn * cu + 4.f * kU32 * (cu * cu + fabsf(m1[i]));
         // uncertified rows get their whole distance row recomputed in fp64 (full_recheck_kernel)
         if (!(m2[i] - m1[i] > tau)) full_list[atomicAdd(full_count, 1)] = g;
       }
@@ -333,7 +347,7 @@ __device__ __forceinline__ void fr_dots(const float* __restrict__ er, const floa
 template <typename ZT, bool VEC>
 __global__ void __launch_bounds__(FR_THREADS) full_recheck_kernel(
     const ZT* __restrict__ z, const float* __restrict__ E, const float* __restrict__ e2,
-    const CbHeader* __restrict__ hdr, int K, int D, const int* __restrict__ list,
+    const float* __restrict__ ntab, int K, int D, const int* __restrict__ list,
     const int* __restrict__ count, int* __restrict__ idx_out, unsigned long long* stats) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* zs = reinterpret_cast<float*>(smem_raw);                 // [FR_ROWS][Dp4]
@@ -348,7 +362,6 @@ __global__ void __launch_bounds__(FR_THREADS) full_recheck_kernel(
   __shared__ int n64;
   const int n = *count;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float e2max = hdr->e2max;
   if (threadIdx.x == 0) n64 = 0;
   for (int b0 = blockIdx.x * FR_ROWS; b0 < n; b0 += gridDim.x * FR_ROWS) {
     __syncthreads();
@@ -416,7 +429,9 @@ __global__ void __launch_bounds__(FR_THREADS) full_recheck_kernel(
         v2 = nv2;
       }
       // per-code error: D sequential FMA roundings on the dot, one on e2, one on d; a gap can be off by twice that
-      const float tau = 4.f * (float)(D + 2) * kU32 * sqrtf(z2s[r] * e2max) + 4.f * kU32 * (e2max + fabsf(v1));
+      const float zn = sqrtf(z2s[r]) * 1.0001f;
+      const float cu = reachable_norm(ntab, zn, z2s[r] + v1);
+      const float tau = 4.f * (float)(D + 2) * kU32 * zn * cu + 4.f * kU32 * (cu * cu + fabsf(v1));
       int need = 0;
       if (rows[r] >= 0) {
         idx_out[rows[r]] = id;
@@ -702,12 +717,14 @@ inline int grid_for(long long work_items, int per_block, int cap_mult) {
 int launch_codebook_prepare(const float* E, int K, int D, void* cb, cudaStream_t st) {
   const int Kp = round_up(K, 256), Dp = round_up(D, 16);
   auto* hdr = reinterpret_cast<CbHeader*>(cb);
+  float* ntab = reinterpret_cast<float*>(reinterpret_cast<char*>(cb) + cb_tab_offset());
   float* e2 = reinterpret_cast<float*>(reinterpret_cast<char*>(cb) + cb_e2_offset());
   __half* e16 = reinterpret_cast<__half*>(reinterpret_cast<char*>(cb) + cb_e16_offset(K));
-  G2V_CUDA_CHECK(cudaMemsetAsync(hdr, 0, sizeof(CbHeader), st));
-  cb_rows_kernel<<<(Kp * 32 + 255) / 256, 256, 0, st>>>(E, K, D, Kp, hdr, e2);
+  G2V_CUDA_CHECK(cudaMemsetAsync(hdr, 0, cb_e2_offset(), st));                  // header + norm table
+  G2V_CUDA_CHECK(cudaMemsetAsync(&hdr->e2min, 0x7f, sizeof(float), st));        // large positive for atomicMin
+  cb_rows_kernel<<<(Kp * 32 + 255) / 256, 256, 0, st>>>(E, K, D, Kp, hdr, ntab, e2);
   G2V_LAUNCH_CHECK("cb_rows_kernel");
-  cb_header_kernel<<<1, 1, 0, st>>>(hdr, K, D, Kp, Dp);
+  cb_header_kernel<<<1, 1, 0, st>>>(hdr, ntab, K, D, Kp, Dp);
   G2V_LAUNCH_CHECK("cb_header_kernel");
   cb_fp16_kernel<<<(Kp * 32 + 255) / 256, 256, 0, st>>>(E, K, D, Kp, Dp, hdr, e16);
   G2V_LAUNCH_CHECK("cb_fp16_kernel");
@@ -723,16 +740,16 @@ static int launch_full_recheck_t(const ZT* z, const float* E, const void* cb, in
   long long batches = (max_rows + FR_ROWS - 1) / FR_ROWS;
   long long cap = (long long)num_sms() * 2;
   const int grid = (int)(batches < 1 ? 1 : (batches < cap ? batches : cap));
-  const auto* hdr = reinterpret_cast<const CbHeader*>(cb);
+  const float* ntab = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_tab_offset());
   const float* e2 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_e2_offset());
   if (vec) {
     if (smem > 40 * 1024)
       G2V_CUDA_CHECK(cudaFuncSetAttribute(full_recheck_kernel<ZT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    full_recheck_kernel<ZT, true><<<grid, FR_THREADS, smem, st>>>(z, E, e2, hdr, K, D, list, count, idx, stats);
+    full_recheck_kernel<ZT, true><<<grid, FR_THREADS, smem, st>>>(z, E, e2, ntab, K, D, list, count, idx, stats);
   } else {
     if (smem > 40 * 1024)
       G2V_CUDA_CHECK(cudaFuncSetAttribute(full_recheck_kernel<ZT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    full_recheck_kernel<ZT, false><<<grid, FR_THREADS, smem, st>>>(z, E, e2, hdr, K, D, list, count, idx, stats);
+    full_recheck_kernel<ZT, false><<<grid, FR_THREADS, smem, st>>>(z, E, e2, ntab, K, D, list, count, idx, stats);
   }
   G2V_LAUNCH_CHECK("full_recheck_kernel");
   return G2V_OK;
@@ -753,23 +770,27 @@ template <typename ZT>
 static int launch_search_simt_t(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, int K, int D,
                                 int32_t* full_list, int32_t* full_count, int32_t* idx,
                                 unsigned long long* stats, cudaStream_t st) {
-  const auto* hdr = reinterpret_cast<const CbHeader*>(cb);
+  const float* ntab = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_tab_offset());
   const float* e2 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_e2_offset());
   // vector path: 8 elements per load must stay 16-byte aligned in every row
   const bool vec = ((size_t)D * sizeof(ZT) % 16 == 0) && (D % 4 == 0) && aligned16(z) && aligned16(E);
   const size_t smem = sizeof(SearchSmem);
   G2V_CUDA_CHECK(cudaMemsetAsync(full_count, 0, sizeof(int32_t), st));
+  cudaEvent_t pev0, pev1;
+  profile_take(&pev0, &pev1);
+  if (pev0) G2V_CUDA_CHECK(cudaEventRecord(pev0, st));
   // persistent grid: two CTAs per SM, each walks row tiles
   long long tiles = (N + BM - 1) / BM;
   int grid = (int)((tiles < (long long)num_sms() * 2) ? (tiles > 0 ? tiles : 1) : (long long)num_sms() * 2);
   if (vec) {
     G2V_CUDA_CHECK(cudaFuncSetAttribute(search_simt_kernel<true, ZT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    search_simt_kernel<true, ZT><<<grid, NT, smem, st>>>(z, E, e2, hdr, N, K, D, full_list, full_count, idx);
+    search_simt_kernel<true, ZT><<<grid, NT, smem, st>>>(z, E, e2, ntab, N, K, D, full_list, full_count, idx);
   } else {
     G2V_CUDA_CHECK(cudaFuncSetAttribute(search_simt_kernel<false, ZT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    search_simt_kernel<false, ZT><<<grid, NT, smem, st>>>(z, E, e2, hdr, N, K, D, full_list, full_count, idx);
+    search_simt_kernel<false, ZT><<<grid, NT, smem, st>>>(z, E, e2, ntab, N, K, D, full_list, full_count, idx);
   }
   G2V_LAUNCH_CHECK("search_simt_kernel");
+  if (pev1) G2V_CUDA_CHECK(cudaEventRecord(pev1, st));
   return launch_full_recheck_t(z, E, cb, K, D, full_list, full_count, N, idx, stats, st);
 }
 

@@ -40,16 +40,19 @@ constexpr int MAX_CHUNKS = 12;
 constexpr int NTHREADS = 384;           // 4 producer/MMA warps + 8 epilogue warps
 constexpr int EPI_WARP0 = 4;
 constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23: float bits = 0x4B400000 + round(v)
+constexpr float kKeyCap = 16777215.0f;  // kMagic + 2^22 - 1: largest key value
 constexpr int kMaxDp = 496;
 constexpr int kMaxK = 16384;            // 9-bit column-group field of the key
 constexpr unsigned kDbgSkipMma = 0x100u, kDbgSkipEpi = 0x200u;   // G2V_TC_DEBUG bring-up switches (timing only)
 
-struct RowInfo {       // 16 bytes per row, written by row_prep_kernel
+struct RowInfo {       // 32 bytes per row, written by row_prep_kernel
   float cS;            // -2 / (scale_z * scale_e) * S
   float S;             // fixed-point scale (power of two)
-  float tauI;          // certification threshold in fixed-point units
-  float pad;
+  float a1, a0;        // |dot_hat - dot| <= a1*c + a0 for a code of norm c
+  float znorm, z2;     // ||z|| (rounded up), ||z||^2
+  float pad0, pad1;
 };
+static_assert(sizeof(RowInfo) == 32, "RowInfo is read as two float4");
 
 struct TcParams {
   long long N;
@@ -59,6 +62,7 @@ struct TcParams {
   int n_row_tiles;
   int nstage;                   // depth of the codebook-stage ring
   const RowInfo* rowinfo;
+  const float* ntab;            // reachable-norm table of the codebook (g2v_common.cuh)
   const float* e2;
   int* idx;
   int* pair_list;               // 3 ints per entry: row, code a, code b
@@ -237,6 +241,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[16], const float* 
     for (int u = 0; u < 4; ++u) {
       const int j = 4 * j4 + u;
       float x = fmaf(__uint_as_float(v[j]), cS, fmaf(ee[u], S, kMagic));
+      x = fminf(x, kKeyCap);                         // far codes saturate instead of wrapping
       uint32_t key = __float_as_uint(x) * 512u + group;
       if (PARTIAL && j >= nvalid) key = 0xFFFFFFFFu;
       m2[j] = max(m1[j], min(m2[j], key));
@@ -422,7 +427,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int tile = group; tile < P.n_row_tiles; tile += n_groups) {
       const long long row = ((long long)tile * CG + cta_rank) * TM + r;
       const bool valid = row < P.N;
-      RowInfo ri = valid ? P.rowinfo[row] : RowInfo{0.f, 0.f, 0.f, 0.f};
+      RowInfo ri = valid ? P.rowinfo[row] : RowInfo{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       uint32_t m1[16], m2[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) { m1[j] = 0xFFFFFFFFu; m2[j] = 0xFFFFFFFFu; }
@@ -499,8 +504,14 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           t3 = min(min(c1.key2, c2.key2), k3);
         }
         if (valid) {
-          const uint32_t tau = (uint32_t)fminf(ri.tauI, 4194304.f);
           const uint32_t v1 = t1 >> 9, v2 = t2 >> 9, v3 = t3 >> 9;
+          // certification threshold: per-code error at the largest norm that can still win this row
+          // (twice for the distance, twice for a gap of two codes), the fp32 rounding of e2, and the
+          // fixed-point rounding of both keys
+          const float d1 = ri.z2 + ((float)(int)v1 - 4194304.f) / ri.S;
+          const float cu = reachable_norm(P.ntab, ri.znorm, d1);
+          const float tauf = (4.f * (ri.a1 * cu + ri.a0) + 2.3841858e-7f * cu * cu) * ri.S + 4.f;
+          const uint32_t tau = (uint32_t)fminf(tauf, 4194304.f);
           if (!(P.flags & G2V_NO_RECHECK) && (v2 - v1 <= tau)) {
             if (!same_chain && (v3 - v1 > tau) && code2 < P.K) {
               const int slot = atomicAdd(P.counters + 0, 1);
@@ -577,25 +588,30 @@ __global__ void __launch_bounds__(256) row_prep_kernel(const ZT* __restrict__ z,
   for (int off = 16; off > 0; off >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, off);
   if (lane == 0) {
     const float znorm = sqrtf(s2) * 1.0001f, rnorm = sqrtf(r2) * 1.0001f;
-    const float enorm = sqrtf(hdr->e2max) * 1.0001f, snorm = hdr->smax;
-    // |dot_hat - dot| <= |r||e| + |z||s| + |r||s|  (operand rounding, Cauchy-Schwarz on the actual
-    // residuals) + tensor-core accumulation (2^-19 alignment + one fp32 rounding per K step)
-    const float acc = (1.9073486e-6f + (float)(n_ksteps + 2) * 1.1920929e-7f) * znorm * enorm;
-    const float err_dot = rnorm * enorm + znorm * snorm + rnorm * snorm + acc;
-    // distance = e2 - 2 dot; a gap of two codes can be off by twice the per-code error
-    float tau = 4.f * err_dot + 4.f * 5.9604645e-8f * hdr->e2max;
-    const float R = hdr->e2max + 2.f * znorm * enorm;
+    // |dot_hat - dot| for a code of norm c:
+    //   operand rounding (Cauchy-Schwarz on the measured residuals; ||r_e|| <= sfrac c):
+    //        |r_z| c + |z| sfrac c + |r_z| sfrac c
+    //   tensor-core accumulation: (2^-19 alignment + one fp32 rounding per K step) |z| c
+    // = a1 c + a0.  The epilogue evaluates it at the largest code norm that can still win the row.
+    const float acc = 1.9073486e-6f + (float)(n_ksteps + 2) * 1.1920929e-7f;
+    RowInfo ri;
+    ri.a1 = rnorm * (1.f + hdr->sfrac) + znorm * (hdr->sfrac + acc);
+    ri.a0 = 0.f;
+    ri.znorm = znorm;
+    ri.z2 = s2;
+    // fixed-point range: keys of codes that can still win lie in [-|z|^2, (|z| + c_min)^2]; anything
+    // larger saturates in the epilogue
+    const float cmin = sqrtf(hdr->e2min);
+    const float R = 2.f * (znorm + cmin) * (znorm + cmin) + 1e-30f;
     float S = 1.f;
-    if (R > 0.f && isfinite(R)) {
+    if (isfinite(R)) {
       int e;
       frexpf(R, &e);                                    // R < 2^e
-      S = ldexpf(1.f, max(min(21 - e, 100), -100));     // |d| * S < 2^21
+      S = ldexpf(1.f, max(min(21 - e, 100), -100));     // R * S < 2^21
     }
-    RowInfo ri;
     ri.S = S;
     ri.cS = (-2.f * inv / hdr->scale_e) * S;
-    ri.tauI = fminf(tau * S + 4.f, 4194304.f);          // + fixed-point rounding of both keys
-    ri.pad = 0.f;
+    ri.pad0 = ri.pad1 = 0.f;
     rowinfo[row] = ri;
   }
 }
@@ -753,6 +769,7 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
   P.n_last_mma = round_up(K - (P.n_ntiles - 1) * TN, 16 * cg);
   P.n_row_tiles = (int)((N + (long long)TM * cg - 1) / ((long long)TM * cg));   // tiles of 128*cg rows
   P.rowinfo = rowinfo; P.e2 = e2; P.idx = idx;
+  P.ntab = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_tab_offset());
   P.pair_list = pairs; P.full_list = fulls; P.counters = counters; P.flags = flags;
   if (const char* env = getenv("G2V_TC_DEBUG")) P.flags |= ((unsigned)atoi(env) & 3u) << 8;   // results are wrong with these
 
@@ -784,6 +801,9 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
   P.nstage = nstage;
   const SmemPlan sp = smem_plan(P.n_full, P.n_tail, cg, nstage);
   const size_t smem = sp.total + 1024;
+  cudaEvent_t pev0, pev1;
+  profile_take(&pev0, &pev1);
+  if (pev0) G2V_CUDA_CHECK(cudaEventRecord(pev0, st));
   const int max_groups = num_sms() / cg;
   const int groups = P.n_row_tiles < max_groups ? P.n_row_tiles : max_groups;
   if (cg == 1) {
@@ -806,6 +826,7 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
     G2V_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_search_kernel<2>, tmA, tmAt, tmB, tmBt, tmBl, tmBlt, P));
   }
   G2V_LAUNCH_CHECK("tc_search_kernel");
+  if (pev1) G2V_CUDA_CHECK(cudaEventRecord(pev1, st));
 
   if (!(flags & G2V_NO_RECHECK)) {
     const int pgrid = num_sms() * 2;

@@ -48,12 +48,16 @@ class StatsAllReduce:
 
 def enable_data_parallel_ema(layer: torch.nn.Module, group: Optional[dist.ProcessGroup] = None,
                              ddp_mean_gradients: bool = True) -> StatsAllReduce:
-    """Turn on the statistics all-reduce for an EMA quantizer.  With `ddp_mean_gradients` the
-    input gradient is scaled by the world size, so that after DDP's gradient averaging the encoder
-    sees exactly the gradient of the single-process loss on the concatenated batch."""
+    """Turn on the statistics all-reduce for an EMA quantizer.
+
+    The returned loss is the loss of the concatenated batch (from the all-reduced SSE / row count).
+    The input gradient keeps the local-mean convention, 2*beta*(x-q)/(N_local*D): averaged over
+    ranks by DDP (`ddp_mean_gradients=True`) it equals the single-process gradient on the
+    concatenated batch; if the caller SUMS gradients across ranks instead, it is divided by the
+    world size here."""
     red = StatsAllReduce(group)
     layer.stats_reduce = red
-    layer.grad_scale = float(dist.get_world_size(group)) if ddp_mean_gradients else 1.0
+    layer.grad_scale = 1.0 if ddp_mean_gradients else 1.0 / float(dist.get_world_size(group))
     return red
 
 

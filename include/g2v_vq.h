@@ -74,6 +74,11 @@ int g2v_codebook_prepare(const float* E, int K, int D, void* cb, size_t cb_bytes
  * (negative error if G2V_ALGO_TC is forced on a shape it does not cover). */
 int g2v_search_path(int K, int D, unsigned flags);
 
+/* Measurement aid: the NEXT g2v_vq_search on this host thread records `ev_start` / `ev_stop`
+ * (cudaEvent_t) on its stream immediately around its dominant kernel (the tcgen05 sweep, or the
+ * fp32 sweep on the SIMT path), so a benchmark can time that kernel alone inside a timed region. */
+int g2v_profile_next_search(void* ev_start, void* ev_stop);
+
 /* Scratch needed by g2v_vq_search for N rows. */
 size_t g2v_workspace_bytes(int64_t N, int K, int D, int z_dtype, unsigned flags);
 

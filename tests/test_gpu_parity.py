@@ -120,8 +120,15 @@ def test_degenerate_ema_codebook():
     layer.forward(z[:128])
     E1 = layer.E
     assert np.abs(E1).max() > 1e3
-    idx = g.vq_search(_t(z), _t(E1)).cpu().numpy()
-    assert O.audit_indices(z, E1, idx, O.nearest_code_f64(z, E1))["hard"] == 0
+    from gesture2vec_b200 import _lib
+    for flags in (_lib.ALGO_AUTO, _lib.ALGO_SIMT):
+        stats = torch.zeros(8, dtype=torch.int64, device=_dev())
+        idx = g.vq_search(_t(z), _t(E1), flags=flags, stats=stats).cpu().numpy()
+        assert O.audit_indices(z, E1, idx, O.nearest_code_f64(z, E1))["hard"] == 0
+        # dead codes with huge norms must not push ordinary rows onto the slow exact paths: the error
+        # bounds use the largest code norm that can still win a row, not the global maximum
+        st = stats.cpu().numpy()
+        assert st[_lib.STAT_FALLBACK_ROWS] + st[_lib.STAT_FULL_RECHECK] <= N // 10, st
 
 
 # ---------------------------------------------------------------------------------------------
