@@ -38,12 +38,19 @@ constexpr int B_PANEL = TN * KC * 2;    // 32768
 constexpr int B_TAIL = TN * KT * 2;     // 8192
 constexpr int MAX_CHUNKS = 12;
 constexpr int NTHREADS = 384;           // 4 producer/MMA warps + 8 epilogue warps
+constexpr int NTHREADS_FUSED = 512;     // + 4 warps converting fp32 rows to the fp16 operand tile
+constexpr int CONV_WARP0 = 12;
+constexpr int MAX_ZSLOTS = 8;           // fp32 staging slots: 64 rows x 64 columns (256-byte rows keep the
+constexpr int ZROWS = 64;               // TMA request count per byte low); the D % 64 tail uses 128 x 16
+constexpr int ZSLOT = ZROWS * KC * 4;   // 16384 bytes
+constexpr int kPfTiles = 2;             // L2 prefetch distance of the row tiles
+constexpr int RS_RING = 4;              // row-statistics ring (tiles in flight between converter and epilogue)
 constexpr int EPI_WARP0 = 4;
 constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23: float bits = 0x4B400000 + round(v)
 constexpr float kKeyCap = 16777215.0f;  // kMagic + 2^22 - 1: largest key value
 constexpr int kMaxDp = 496;
 constexpr int kMaxK = 16384;            // 9-bit column-group field of the key
-constexpr unsigned kDbgSkipMma = 0x100u, kDbgSkipEpi = 0x200u;   // G2V_TC_DEBUG bring-up switches (timing only)
+constexpr unsigned kDbgSkipMma = 0x100u, kDbgSkipEpi = 0x200u, kDbgSkipConv = 0x400u, kDbgPrefetch = 0x800u;   // G2V_TC_DEBUG bring-up switches (timing only)
 
 struct RowInfo {       // 32 bytes per row, written by row_prep_kernel
   float cS;            // -2 / (scale_z * scale_e) * S
@@ -61,6 +68,10 @@ struct TcParams {
   int n_ntiles, n_last_mma;     // code tiles; UMMA N of the last one (multiple of 16)
   int n_row_tiles;
   int nstage;                   // depth of the codebook-stage ring
+  int nzslot;                   // fused variant: depth of the fp32 staging ring
+  int n_ksteps;                 // Dp / 16
+  const CbHeader* hdr;
+  long long* trace;             // bring-up aid: [role][event] timestamps of CTA 0 (nullptr = off)
   const RowInfo* rowinfo;
   const float* ntab;            // reachable-norm table of the codebook (g2v_common.cuh)
   const float* e2;
@@ -99,6 +110,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 // TMA tile load.  CG == 2: the .cta_group::2 form, whose completion bytes are credited to the
 // mbarrier at the same offset in the LEADER CTA (peer bit of the shared::cluster address cleared).
+// wait with cluster-scope acquire (pairs with a peer CTA's release.cluster arrive)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP_C:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE_C;\n\t"
+      "bra.uni WAIT_LOOP_C;\n\t"
+      "WAIT_DONE_C:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+// make generic-proxy shared-memory writes visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 template <int CG>
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
   if constexpr (CG == 1) {
@@ -125,6 +152,10 @@ __device__ __forceinline__ bool elect_one() {
       "}"
       : "=r"(pred));
   return pred != 0;
+}
+// pull a tile into L2 ahead of time (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -207,11 +238,12 @@ __device__ __forceinline__ uint32_t umma_idesc(int m, int n) {
 // shared memory plan
 // ------------------------------------------------------------------------------------------
 struct SmemPlan {
-  uint32_t a_off, b_off, b_stage, e2_off, xch_off, bar_off, tmem_off, total;
+  uint32_t a_off, b_off, b_stage, e2_off, xch_off, zst_off, rs_off, bar_off, tmem_off, total;
 };
 // cg = CTAs cooperating on one MMA (cta_group): each holds its own 128-row A tile and 1/cg of every
 // codebook stage
-__host__ __device__ inline SmemPlan smem_plan(int n_full, int n_tail, int cg, int nstage) {
+// nzslot > 0: fused variant (fp32 staging ring + row statistics ring)
+__host__ __device__ inline SmemPlan smem_plan(int n_full, int n_tail, int cg, int nstage, int nzslot = 0) {
   SmemPlan p;
   p.a_off = 0;
   uint32_t a_bytes = (uint32_t)n_full * A_PANEL + (uint32_t)n_tail * A_TAIL;
@@ -219,8 +251,10 @@ __host__ __device__ inline SmemPlan smem_plan(int n_full, int n_tail, int cg, in
   p.b_stage = B_PANEL / cg;
   p.e2_off = p.b_off + (uint32_t)nstage * p.b_stage;
   p.xch_off = p.e2_off + 2 * TN * 4;          // 128 rows x 8 words: epilogue half 1 -> half 0
-  p.bar_off = p.xch_off + TM * 8 * 4;
-  p.tmem_off = p.bar_off + 8 * (2 * MAX_STAGES + 2 * MAX_CHUNKS + 4);
+  p.zst_off = (p.xch_off + TM * 8 * 4 + 127u) & ~127u;
+  p.rs_off = p.zst_off + (uint32_t)nzslot * ZSLOT;
+  p.bar_off = p.rs_off + (nzslot > 0 ? RS_RING * TM * 8 : 0);
+  p.tmem_off = p.bar_off + 8 * (2 * MAX_STAGES + 2 * MAX_CHUNKS + 4 + 2 * MAX_ZSLOTS + RS_RING);
   p.total = p.tmem_off + 16;
   return p;
 }
@@ -266,20 +300,51 @@ __device__ __forceinline__ void cand_insert(Cand& c1, Cand& c2, uint32_t& k3, co
   }
 }
 
+// Per-row constants from ||z||^2 and the squared norm of the fp16 rounding residual of the row.
+//   |dot_hat - dot| for a code of norm c:
+//     operand rounding (Cauchy-Schwarz on the measured residuals; ||r_e|| <= sfrac c):
+//          |r_z| c + |z| sfrac c + |r_z| sfrac c
+//     tensor-core accumulation: (2^-19 alignment + one fp32 rounding per K step) |z| c
+//   = a1 c.  The epilogue evaluates it at the largest code norm that can still win the row.
+//   Fixed-point range: keys of codes that can still win lie in [-|z|^2, (|z| + c_min)^2]; anything
+//   larger saturates in the epilogue.
+__device__ __forceinline__ RowInfo make_rowinfo(float z2, float r2, float inv_scale_z, float sfrac, float e2min,
+                                                float scale_e, int n_ksteps) {
+  const float znorm = sqrtf(z2) * 1.0001f, rnorm = sqrtf(r2) * 1.0001f;
+  const float acc = 1.9073486e-6f + (float)(n_ksteps + 2) * 1.1920929e-7f;
+  RowInfo ri;
+  ri.a1 = rnorm * (1.f + sfrac) + znorm * (sfrac + acc);
+  ri.a0 = 0.f;
+  ri.znorm = znorm;
+  ri.z2 = z2;
+  const float cmin = sqrtf(e2min);
+  const float R = 2.f * (znorm + cmin) * (znorm + cmin) + 1e-30f;
+  float S = 1.f;
+  if (isfinite(R)) {
+    int e;
+    frexpf(R, &e);                                    // R < 2^e
+    S = ldexpf(1.f, max(min(21 - e, 100), -100));     // R * S < 2^21
+  }
+  ri.S = S;
+  ri.cS = (-2.f * inv_scale_z / scale_e) * S;
+  ri.pad0 = ri.pad1 = 0.f;
+  return ri;
+}
+
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
-template <int CG>
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int CG, bool FUSED>
+__global__ void __launch_bounds__(FUSED ? NTHREADS_FUSED : NTHREADS, 1)
 tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAt,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBt,
                  const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmBlt,
-                 const TcParams P) {
+                 const __grid_constant__ CUtensorMap tmPf, const TcParams P) {
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t raw = smem_u32(smem_dyn);
   const uint32_t base = (raw + 1023u) & ~1023u;
   unsigned char* gbase = smem_dyn + (base - raw);
-  const SmemPlan sp = smem_plan(P.n_full, P.n_tail, CG, P.nstage);
+  const SmemPlan sp = smem_plan(P.n_full, P.n_tail, CG, P.nstage, FUSED ? P.nzslot : 0);
   const uint32_t NST = (uint32_t)P.nstage;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
@@ -296,6 +361,11 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto bar_aempty = [&](int c) { return bars + 8u * (2 * MAX_STAGES + MAX_CHUNKS + c); };
   auto bar_accfull = [&](int a) { return bars + 8u * (2 * MAX_STAGES + 2 * MAX_CHUNKS + a); };
   auto bar_accempty = [&](int a) { return bars + 8u * (2 * MAX_STAGES + 2 * MAX_CHUNKS + 2 + a); };
+  auto bar_zfull = [&](int s) { return bars + 8u * (2 * MAX_STAGES + 2 * MAX_CHUNKS + 4 + s); };
+  auto bar_zempty = [&](int s) { return bars + 8u * (2 * MAX_STAGES + 2 * MAX_CHUNKS + 4 + MAX_ZSLOTS + s); };
+  auto bar_rsfull = [&](int s) { return bars + 8u * (2 * MAX_STAGES + 2 * MAX_CHUNKS + 4 + 2 * MAX_ZSLOTS + s); };
+  const uint32_t sZ = base + sp.zst_off;
+  float2* rowstat = reinterpret_cast<float2*>(gbase + sp.rs_off);      // [RS_RING][TM]: (||z||^2, ||z - z16||^2)
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + sp.tmem_off);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -303,7 +373,10 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    for (int c = 0; c < MAX_CHUNKS; ++c) { mbar_init(bar_afull(c), 1); mbar_init(bar_aempty(c), 1); }
+    // fused: the A panels are written by 4 converter warps in each CTA of the group instead of by TMA
+    for (int c = 0; c < MAX_CHUNKS; ++c) { mbar_init(bar_afull(c), FUSED ? CG : 1); mbar_init(bar_aempty(c), 1); }
+    for (int s = 0; s < MAX_ZSLOTS; ++s) { mbar_init(bar_zfull(s), 1); mbar_init(bar_zempty(s), 4); }
+    for (int s = 0; s < RS_RING; ++s) mbar_init(bar_rsfull(s), 4);
     for (int a = 0; a < 2; ++a) { mbar_init(bar_accfull(a), 1); mbar_init(bar_accempty(a), 8 * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -326,6 +399,17 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // bring-up trace: role r (0 B-prod, 1 MMA, 2 A-prod, 3 epilogue warp 4, 4 converter warp 12), up to 512 events each
+  int trace_n = 0;
+  auto TRACE = [&](int role, int tag) {
+    if (P.trace && blockIdx.x == 0 && lane == 0 && trace_n < 512) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      P.trace[(role * 512 + trace_n) * 2] = tag;
+      P.trace[(role * 512 + trace_n) * 2 + 1] = t;
+      ++trace_n;
+    }
+  };
   // chunk geometry: chunk c < n_full is a 64-wide SW128 panel, otherwise a 16-wide SW32 tail
   auto a_chunk_addr = [&](int c) { return c < n_full ? sA + (uint32_t)c * A_PANEL : sA + (uint32_t)n_full * A_PANEL + (uint32_t)(c - n_full) * A_TAIL; };
   auto chunk_col = [&](int c) { return c < n_full ? c * KC : n_full * KC + (c - n_full) * KT; };
@@ -358,7 +442,39 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 2) {
     // =========================== A producer ===========================
-    {
+    if constexpr (FUSED) {
+      // fp32 rows, 16 columns at a time, into the staging ring (tmA is the fp32 map here)
+      // per row tile: for every full 64-column panel two half-tiles of 64 rows (tmA, 256-byte rows), then
+      // the 16-column tails for all 128 rows (tmAt, fp32)
+      // The ring holds only ~48 KB, far less than HBM latency x per-SM bandwidth, so every row tile
+      // is first pulled into L2 (TMA prefetch, 128 rows x 64 columns per request) kPfTiles tiles ahead.
+      uint32_t slot = 0, zphase = 0;
+      const bool use_pf = (P.flags & kDbgPrefetch) != 0;   // measured: no gain (the stream is not DRAM-latency-bound)
+      auto prefetch_tile = [&](int t) {
+        if (use_pf && t < P.n_row_tiles && elect_one())
+          for (int c0 = 0; c0 < P.D; c0 += KC) tma_prefetch_2d(&tmPf, c0, (t * CG + (int)cta_rank) * TM);
+        __syncwarp();
+      };
+      for (int a = 0; a < kPfTiles; ++a) prefetch_tile(group + a * n_groups);
+      for (int tile = group; tile < P.n_row_tiles; tile += n_groups) {
+        prefetch_tile(tile + kPfTiles * n_groups);
+        const int row0 = (tile * CG + (int)cta_rank) * TM;
+        for (int u = 0; u < 2 * n_full + P.n_tail; ++u) {
+          mbar_wait(bar_zempty(slot), zphase ^ 1u);
+          if (elect_one()) {
+            if (u < 2 * n_full) {
+              mbar_expect_tx(bar_zfull(slot), ZSLOT);
+              tma_load_2d<1>(sZ + slot * ZSLOT, &tmA, (u >> 1) * KC, row0 + (u & 1) * ZROWS, bar_zfull(slot));
+            } else {
+              mbar_expect_tx(bar_zfull(slot), TM * KT * 4);
+              tma_load_2d<1>(sZ + slot * ZSLOT, &tmAt, n_full * KC + (u - 2 * n_full) * KT, row0, bar_zfull(slot));
+            }
+          }
+          __syncwarp();
+          if (++slot == (uint32_t)P.nzslot) { slot = 0; zphase ^= 1u; }
+        }
+      }
+    } else {
       uint32_t ti = 0;
       for (int tile = group; tile < P.n_row_tiles; tile += n_groups, ++ti) {
         for (int c = 0; c < n_chunks; ++c) {
@@ -382,14 +498,22 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t as = it & 1u, around = it >> 1;
           const bool last_nt = (nt == P.n_ntiles - 1);
           const uint32_t idesc = umma_idesc(TM * CG, last_nt ? P.n_last_mma : TN);
+          TRACE(1, 100 + nt);
           mbar_wait(bar_accempty(as), (around & 1u) ^ 1u);
+          TRACE(1, 200 + nt);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + as * TN;
           for (int c = 0; c < n_chunks; ++c, ++g) {
             const int s = g % NST;
             const uint32_t round = g / NST;
-            if (nt == 0) mbar_wait(bar_afull(c), ti & 1u);
+            if (nt == 0) {
+              if (FUSED && CG == 2) mbar_wait_cluster(bar_afull(c), ti & 1u);
+              else mbar_wait(bar_afull(c), ti & 1u);
+              if (FUSED) fence_proxy_async();
+              TRACE(1, 300 + c);
+            }
             mbar_wait(bar_full(s), round & 1u);
+            TRACE(1, 400 + c);
             tc_fence_after();
             const uint32_t a_addr = a_chunk_addr(c), b_addr = sB + (uint32_t)s * sp.b_stage;
             const bool fullp = c < n_full;
@@ -414,7 +538,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp >= EPI_WARP0) {
+  } else if (warp >= EPI_WARP0 && warp < CONV_WARP0) {
     // =========================== epilogue ===========================
     // 8 warps: two per TMEM lane quarter, each taking 16 of every 32 columns (so every scheduler
     // has two epilogue warps to interleave).  Thread = one row; 16 running top-2 chains per thread.
@@ -423,11 +547,21 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int r = q * 32 + lane;                     // row within the tile == TMEM lane
     const int et = threadIdx.x - EPI_WARP0 * 32;     // 0..255
     uint32_t* xrow = xch + (size_t)r * 8;            // hand-off slot of this row (half 1 -> half 0)
-    uint32_t it = 0;
-    for (int tile = group; tile < P.n_row_tiles; tile += n_groups) {
+    uint32_t it = 0, ti = 0;
+    const float h_sfrac = FUSED ? P.hdr->sfrac : 0.f, h_e2min = FUSED ? P.hdr->e2min : 0.f,
+                h_scale_e = FUSED ? P.hdr->scale_e : 1.f;
+    for (int tile = group; tile < P.n_row_tiles; tile += n_groups, ++ti) {
       const long long row = ((long long)tile * CG + cta_rank) * TM + r;
       const bool valid = row < P.N;
-      RowInfo ri = valid ? P.rowinfo[row] : RowInfo{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      RowInfo ri;
+      if constexpr (FUSED) {
+        // statistics of this tile's rows come from the converter warps (same CTA)
+        mbar_wait(bar_rsfull(ti % RS_RING), (ti / RS_RING) & 1u);
+        const float2 st = rowstat[(ti % RS_RING) * TM + r];
+        ri = make_rowinfo(st.x, st.y, 1.f, h_sfrac, h_e2min, h_scale_e, P.n_ksteps);
+      } else {
+        ri = valid ? P.rowinfo[row] : RowInfo{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      }
       uint32_t m1[16], m2[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) { m1[j] = 0xFFFFFFFFu; m2[j] = 0xFFFFFFFFu; }
@@ -440,7 +574,9 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           e2c[et] = (k0 < P.K) ? __ldg(P.e2 + k0) : 0.f;
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (warp == EPI_WARP0) TRACE(3, 100 + nt);
         mbar_wait(bar_accfull(as), around & 1u);
+        if (warp == EPI_WARP0) TRACE(3, 200 + nt);
         tc_fence_after();
         const int ncols = min(TN, P.K - nt * TN);
         const int nch = (ncols + 31) >> 5;
@@ -466,6 +602,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // all TMEM reads of this stage are complete (last wait::ld above): hand it back
         tc_fence_before();
         __syncwarp();
+        if (warp == EPI_WARP0) TRACE(3, 300 + nt);
         if (lane == 0) {
           if (CG == 1 || leader) mbar_arrive(bar_accempty(as));
           else mbar_arrive_cluster(bar_accempty(as), 0);      // the leader's MMA thread waits for both CTAs
@@ -530,6 +667,95 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   }
 
+  if constexpr (FUSED) {
+    if (warp >= CONV_WARP0) {
+      // =========================== converters ===========================
+      // fp32 staging slot (128 rows x 16 columns) -> fp16 into the swizzled A panels; lane = (row % 8,
+      // float4 of the row), so a warp reads 512 contiguous bytes and its 8-byte stores hit 8 rows whose
+      // 16-byte chunks the swizzle spreads over all banks.
+      // lane = (which of 2 rows, which float4 of the 64-column row): a warp reads 2 x 256 contiguous
+      // bytes per step and writes two 128-byte panel rows whose 16-byte chunks the swizzle permutes.
+      // Each lane owns rows {h*64 + cw*16 + 2i + rsel} and keeps their |z|^2 / |z - z16|^2 in registers.
+      const int cw = warp - CONV_WARP0;
+      const int q = lane & 15, rsel = lane >> 4;
+      uint32_t slot = 0, zphase = 0, ti = 0;
+      for (int tile = group; tile < P.n_row_tiles; tile += n_groups, ++ti) {
+        float z2[16], r2[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { z2[i] = 0.f; r2[i] = 0.f; }
+        for (int c = 0; c < n_chunks; ++c) {
+          const bool fullp = c < n_full;
+          if (warp == CONV_WARP0) TRACE(4, 100 + c);
+          mbar_wait(bar_aempty(c), (ti & 1u) ^ 1u);                     // MMA finished with the previous tile's panel
+          if (warp == CONV_WARP0) TRACE(4, 200 + c);
+          const uint32_t abase = a_chunk_addr(c);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (fullp || h == 0) mbar_wait(bar_zfull(slot), zphase);    // tail: one slot holds all 128 rows
+            if (warp == CONV_WARP0) TRACE(4, 300 + 2 * c + h);
+            const unsigned char* zsrc = gbase + sp.zst_off + slot * ZSLOT;
+            float4 v[8];
+            if (fullp) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                v[i] = *reinterpret_cast<const float4*>(zsrc + (cw * 16 + 2 * i + rsel) * (KC * 4) + q * 16);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                v[i] = (q < 4) ? *reinterpret_cast<const float4*>(zsrc + (h * 64 + cw * 16 + 2 * i + rsel) * (KT * 4) + q * 16)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncwarp();
+            if (fullp || h == 1) {
+              if (lane == 0) mbar_arrive(bar_zempty(slot));             // slot is in registers
+              if (++slot == (uint32_t)P.nzslot) { slot = 0; zphase ^= 1u; }
+            }
+            if (!(P.flags & kDbgSkipConv))
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t rr = (uint32_t)(h * 64 + cw * 16 + 2 * i + rsel);
+              const __half2 h01 = __floats2half2_rn(v[i].x, v[i].y), h23 = __floats2half2_rn(v[i].z, v[i].w);
+              const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+              const float e0 = v[i].x - f01.x, e1 = v[i].y - f01.y, e2r = v[i].z - f23.x, e3 = v[i].w - f23.y;
+              z2[h * 8 + i] = fmaf(v[i].x, v[i].x, fmaf(v[i].y, v[i].y, fmaf(v[i].z, v[i].z, fmaf(v[i].w, v[i].w, z2[h * 8 + i]))));
+              r2[h * 8 + i] = fmaf(e0, e0, fmaf(e1, e1, fmaf(e2r, e2r, fmaf(e3, e3, r2[h * 8 + i]))));
+              uint32_t dst;
+              if (fullp) dst = abase + rr * 128u + ((((uint32_t)q >> 1) ^ (rr & 7u)) << 4) + ((uint32_t)q & 1u) * 8u;
+              else dst = abase + rr * 32u + (((((uint32_t)q >> 1) & 1u) ^ ((rr >> 2) & 1u)) << 4) + ((uint32_t)q & 1u) * 8u;
+              if (fullp || q < 4)
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(*reinterpret_cast<const uint32_t*>(&h01)),
+                             "r"(*reinterpret_cast<const uint32_t*>(&h23))
+                             : "memory");
+            }
+          }
+          if (c == n_chunks - 1) {
+            // row statistics of the finished tile, before the last panel is published
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float a = z2[i], b = r2[i];
+#pragma unroll
+              for (int o = 1; o < 16; o <<= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+                b += __shfl_xor_sync(0xffffffffu, b, o);
+              }
+              if (q == 0) rowstat[(ti % RS_RING) * TM + (i >> 3) * 64 + cw * 16 + 2 * (i & 7) + rsel] = make_float2(a, b);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_rsfull(ti % RS_RING));
+          }
+          if (warp == CONV_WARP0) TRACE(4, 400 + c);
+          fence_proxy_async();                                          // my stores -> visible to the MMA's reads
+          asm volatile("bar.sync 7, 128;" ::: "memory");                // all four converter warps
+          if (warp == CONV_WARP0) TRACE(4, 500 + c);
+          if (threadIdx.x == CONV_WARP0 * 32) {                         // one arrive per CTA and panel
+            if (CG == 1 || leader) mbar_arrive(bar_afull(c));
+            else mbar_arrive_cluster(bar_afull(c), 0);
+          }
+        }
+      }
+    }
+  }
+
   tc_fence_before();
   if constexpr (CG == 1) __syncthreads();
   else cluster_sync_all();       // neither CTA may leave while the other still reads its smem / TMEM
@@ -587,31 +813,7 @@ __global__ void __launch_bounds__(256) row_prep_kernel(const ZT* __restrict__ z,
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, off);
   if (lane == 0) {
-    const float znorm = sqrtf(s2) * 1.0001f, rnorm = sqrtf(r2) * 1.0001f;
-    // |dot_hat - dot| for a code of norm c:
-    //   operand rounding (Cauchy-Schwarz on the measured residuals; ||r_e|| <= sfrac c):
-    //        |r_z| c + |z| sfrac c + |r_z| sfrac c
-    //   tensor-core accumulation: (2^-19 alignment + one fp32 rounding per K step) |z| c
-    // = a1 c + a0.  The epilogue evaluates it at the largest code norm that can still win the row.
-    const float acc = 1.9073486e-6f + (float)(n_ksteps + 2) * 1.1920929e-7f;
-    RowInfo ri;
-    ri.a1 = rnorm * (1.f + hdr->sfrac) + znorm * (hdr->sfrac + acc);
-    ri.a0 = 0.f;
-    ri.znorm = znorm;
-    ri.z2 = s2;
-    // fixed-point range: keys of codes that can still win lie in [-|z|^2, (|z| + c_min)^2]; anything
-    // larger saturates in the epilogue
-    const float cmin = sqrtf(hdr->e2min);
-    const float R = 2.f * (znorm + cmin) * (znorm + cmin) + 1e-30f;
-    float S = 1.f;
-    if (isfinite(R)) {
-      int e;
-      frexpf(R, &e);                                    // R < 2^e
-      S = ldexpf(1.f, max(min(21 - e, 100), -100));     // R * S < 2^21
-    }
-    ri.S = S;
-    ri.cS = (-2.f * inv / hdr->scale_e) * S;
-    ri.pad0 = ri.pad1 = 0.f;
+    const RowInfo ri = make_rowinfo(s2, r2, inv, hdr->sfrac, hdr->e2min, hdr->scale_e, n_ksteps);
     rowinfo[row] = ri;
   }
 }
@@ -703,17 +905,18 @@ EncodeTiledFn get_encode_fn() {
 }
 
 int make_map(CUtensorMap* tm, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows,
-             CUtensorMapSwizzle sw) {
+             CUtensorMapSwizzle sw, bool f32 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error_detail("cuTensorMapEncodeTiled entry point not available");
     return G2V_ERR_CUDA;
   }
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstr[1] = {cols * 2};
+  cuuint64_t gstr[1] = {cols * (f32 ? 4u : 2u)};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(gptr), gdim, gstr, box, estr,
+  CUresult r = fn(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                  const_cast<void*>(gptr), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -761,33 +964,58 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
   P.n_full = Dp / KC;
   P.n_tail = (Dp % KC) / KT;
   P.n_chunks = P.n_full + P.n_tail;
-  // CTA pairs (cta_group::2: M = 256 per MMA, each CTA streams half of every codebook stage) as soon
-  // as there are two row tiles; G2V_TC_CG=1 forces the single-CTA kernel
-  int cg = (N > TM) ? 2 : 1;
-  if (const char* env = getenv("G2V_TC_CG")) cg = (atoi(env) == 1) ? 1 : cg;
+  // Two regimes (measured, see profiles/):
+  //  * K <= 512, fp32 rows: HBM-bound.  One kernel reads the fp32 rows once and converts them on the
+  //    fly ("fused"); single-CTA MMAs, because a CTA pair needs a cluster-scope release per operand
+  //    panel from the peer's converter warps (~2 us of latency per row tile).
+  //  * larger K or 16-bit rows: tensor-bound.  row_prep_kernel + CTA pairs (cta_group::2: M = 256 per
+  //    MMA, each CTA streams half of every codebook stage through a deep ring).
+  // G2V_TC_CG=1|2 and G2V_TC_FUSED=0|1 override the choice.
   P.n_ntiles = (K + TN - 1) / TN;
+  bool fused = (z_dtype == G2V_F32) && (D % 4 == 0) && (D >= KC) && P.n_ntiles <= 2 &&
+               ((reinterpret_cast<uintptr_t>(z) & 15) == 0);
+  if (const char* env = getenv("G2V_TC_FUSED")) {
+    if (atoi(env) == 0) fused = false;
+    else fused = (z_dtype == G2V_F32) && (D % 4 == 0) && (D >= KC) && ((reinterpret_cast<uintptr_t>(z) & 15) == 0);
+  }
+  int cg = fused ? 1 : ((N > TM) ? 2 : 1);
+  if (const char* env = getenv("G2V_TC_CG")) cg = (atoi(env) == 1) ? 1 : ((N > TM) ? 2 : 1);
+  if (fused && smem_plan(P.n_full, P.n_tail, cg, 2, 3).total + 1024 > 227 * 1024) fused = false;   // needs >= 3 staging slots
   P.n_last_mma = round_up(K - (P.n_ntiles - 1) * TN, 16 * cg);
   P.n_row_tiles = (int)((N + (long long)TM * cg - 1) / ((long long)TM * cg));   // tiles of 128*cg rows
   P.rowinfo = rowinfo; P.e2 = e2; P.idx = idx;
   P.ntab = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_tab_offset());
   P.pair_list = pairs; P.full_list = fulls; P.counters = counters; P.flags = flags;
-  if (const char* env = getenv("G2V_TC_DEBUG")) P.flags |= ((unsigned)atoi(env) & 3u) << 8;   // results are wrong with these
+  P.trace = nullptr;
+  if (const char* env = getenv("G2V_TC_TRACE")) P.trace = reinterpret_cast<long long*>(strtoull(env, nullptr, 0));
+  if (const char* env = getenv("G2V_TC_DEBUG")) P.flags |= ((unsigned)atoi(env) & 15u) << 8;   // results are wrong with these
 
   const int n_ksteps = P.n_full * (KC / KT) + P.n_tail;
-  {
+  P.n_ksteps = n_ksteps;
+  P.hdr = hdr;
+  if (fused) {
+    G2V_CUDA_CHECK(cudaMemsetAsync(counters, 0, 16, st));
+  } else {
     const long long threads = N * 32;
     const int grid = (int)((threads + 255) / 256);
     row_prep_kernel<ZT><<<grid, 256, 0, st>>>(z, N, D, Dp, hdr, z16, rowinfo, counters, n_ksteps);
     G2V_LAUNCH_CHECK("row_prep_kernel");
   }
 
-  alignas(64) CUtensorMap tmA, tmAt, tmB, tmBt, tmBl, tmBlt;
+  alignas(64) CUtensorMap tmA, tmAt, tmB, tmBt, tmBl, tmBlt, tmPf;
   int rc;
   // main maps need a 64-wide box; if D < 64 there are no full panels and the main maps are unused
   const uint32_t main_box = (Dp >= KC) ? KC : KT;
   const CUtensorMapSwizzle main_sw = (Dp >= KC) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
-  if ((rc = make_map(&tmA, z16, (uint64_t)N, (uint64_t)Dp, main_box, TM, main_sw))) return rc;
-  if ((rc = make_map(&tmAt, z16, (uint64_t)N, (uint64_t)Dp, KT, TM, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  if (fused) {
+    if ((rc = make_map(&tmA, z, (uint64_t)N, (uint64_t)D, KC, ZROWS, CU_TENSOR_MAP_SWIZZLE_NONE, true))) return rc;
+    if ((rc = make_map(&tmAt, z, (uint64_t)N, (uint64_t)D, KT, TM, CU_TENSOR_MAP_SWIZZLE_NONE, true))) return rc;
+    if ((rc = make_map(&tmPf, z, (uint64_t)N, (uint64_t)D, KC, TM, CU_TENSOR_MAP_SWIZZLE_NONE, true))) return rc;
+  } else {
+    if ((rc = make_map(&tmA, z16, (uint64_t)N, (uint64_t)Dp, main_box, TM, main_sw))) return rc;
+    if ((rc = make_map(&tmPf, z16, (uint64_t)N, (uint64_t)Dp, Dp < 64 ? (uint32_t)Dp : 64u, TM, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+  }
+  if (!fused && (rc = make_map(&tmAt, z16, (uint64_t)N, (uint64_t)Dp, KT, TM, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
   const uint32_t brow = TN / cg, blast = (uint32_t)P.n_last_mma / cg;     // code rows each CTA fetches per stage
   if ((rc = make_map(&tmB, e16, (uint64_t)Kp, (uint64_t)Dp, main_box, brow, main_sw))) return rc;
   if ((rc = make_map(&tmBt, e16, (uint64_t)Kp, (uint64_t)Dp, KT, brow, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
@@ -796,10 +1024,17 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
 
   // ring depth: whatever shared memory is left after the resident row tile, capped at MAX_STAGES
   // (the ring has to cover the TMA round trip, ~2.5k cycles, at 512 MMA cycles per full panel)
-  int nstage = MAX_STAGES;
+  int nstage = fused ? (cg == 2 ? 4 : 2) : MAX_STAGES, nzslot = 0;
+  if (const char* env = getenv("G2V_TC_BSTAGES")) nstage = atoi(env) >= 2 && atoi(env) <= MAX_STAGES ? atoi(env) : nstage;
   while (nstage > 2 && smem_plan(P.n_full, P.n_tail, cg, nstage).total + 1024 > 227 * 1024) --nstage;
+  if (fused) {      // the rest of shared memory becomes the fp32 staging ring (>= 3 slots or give up fusing)
+    nzslot = MAX_ZSLOTS;
+    while (nzslot > 0 && smem_plan(P.n_full, P.n_tail, cg, nstage, nzslot).total + 1024 > 227 * 1024) --nzslot;
+    if (nzslot < 3) return G2V_ERR_UNSUPPORTED;   // cannot happen: checked when `fused` was decided
+  }
   P.nstage = nstage;
-  const SmemPlan sp = smem_plan(P.n_full, P.n_tail, cg, nstage);
+  P.nzslot = nzslot;
+  const SmemPlan sp = smem_plan(P.n_full, P.n_tail, cg, nstage, nzslot);
   const size_t smem = sp.total + 1024;
   cudaEvent_t pev0, pev1;
   profile_take(&pev0, &pev1);
@@ -807,13 +1042,21 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
   const int max_groups = num_sms() / cg;
   const int groups = P.n_row_tiles < max_groups ? P.n_row_tiles : max_groups;
   if (cg == 1) {
-    G2V_CUDA_CHECK(cudaFuncSetAttribute(tc_search_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_search_kernel<1><<<groups, NTHREADS, smem, st>>>(tmA, tmAt, tmB, tmBt, tmBl, tmBlt, P);
+    if (fused) {
+      G2V_CUDA_CHECK(cudaFuncSetAttribute(tc_search_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      tc_search_kernel<1, true><<<groups, NTHREADS_FUSED, smem, st>>>(tmA, tmAt, tmB, tmBt, tmBl, tmBlt, tmPf, P);
+    } else {
+      G2V_CUDA_CHECK(cudaFuncSetAttribute(tc_search_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      tc_search_kernel<1, false><<<groups, NTHREADS, smem, st>>>(tmA, tmAt, tmB, tmBt, tmBl, tmBlt, tmPf, P);
+    }
   } else {
-    G2V_CUDA_CHECK(cudaFuncSetAttribute(tc_search_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (fused)
+      G2V_CUDA_CHECK(cudaFuncSetAttribute(tc_search_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+      G2V_CUDA_CHECK(cudaFuncSetAttribute(tc_search_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(groups * 2);
-    cfg.blockDim = dim3(NTHREADS);
+    cfg.blockDim = dim3(fused ? NTHREADS_FUSED : NTHREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -823,7 +1066,8 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    G2V_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_search_kernel<2>, tmA, tmAt, tmB, tmBt, tmBl, tmBlt, P));
+    if (fused) G2V_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_search_kernel<2, true>, tmA, tmAt, tmB, tmBt, tmBl, tmBlt, tmPf, P));
+    else G2V_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_search_kernel<2, false>, tmA, tmAt, tmB, tmBt, tmBl, tmBlt, tmPf, P));
   }
   G2V_LAUNCH_CHECK("tc_search_kernel");
   if (pev1) G2V_CUDA_CHECK(cudaEventRecord(pev1, st));
