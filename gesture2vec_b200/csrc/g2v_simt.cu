@@ -314,14 +314,19 @@ __global__ void __launch_bounds__(NT) search_simt_kernel(
 // gap exceeds the fp32 error bound; phase B re-scans an uncertified row with the same arithmetic
 // and evaluates in fp64 only the codes within the bound of its minimum.
 // ------------------------------------------------------------------------------------------
-constexpr int FR_ROWS = 16, FR_THREADS = 256;
+constexpr int FR_THREADS = 256;
 
-// fp32 dot products of one code row with R latent rows (sequential over D: same order everywhere)
-template <int R, bool VEC>
+// fp32 dot products of one code row with R latent rows.  NP independent partial sums per row (column
+// j goes to partial j % NP, NP in {1, 4}) shorten the rounding chain to D/NP + NP steps; the order is
+// fixed, so re-evaluating a row gives bit-identical values.
+template <int R, int NP, bool VEC>
 __device__ __forceinline__ void fr_dots(const float* __restrict__ er, const float* __restrict__ zs, int Dp4, int D,
-                                        float (&acc)[R]) {
+                                        float (&out)[R]) {
+  float acc[R][NP];
 #pragma unroll
-  for (int r = 0; r < R; ++r) acc[r] = 0.f;
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int p = 0; p < NP; ++p) acc[r][p] = 0.f;
   if (VEC) {
 #pragma unroll 2
     for (int j = 0; j < D; j += 4) {
@@ -329,22 +334,24 @@ __device__ __forceinline__ void fr_dots(const float* __restrict__ er, const floa
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const float4 zv = *reinterpret_cast<const float4*>(zs + r * Dp4 + j);
-        acc[r] = fmaf(zv.x, e.x, acc[r]);
-        acc[r] = fmaf(zv.y, e.y, acc[r]);
-        acc[r] = fmaf(zv.z, e.z, acc[r]);
-        acc[r] = fmaf(zv.w, e.w, acc[r]);
+        acc[r][0] = fmaf(zv.x, e.x, acc[r][0]);
+        acc[r][1 % NP] = fmaf(zv.y, e.y, acc[r][1 % NP]);
+        acc[r][2 % NP] = fmaf(zv.z, e.z, acc[r][2 % NP]);
+        acc[r][3 % NP] = fmaf(zv.w, e.w, acc[r][3 % NP]);
       }
     }
   } else {
     for (int j = 0; j < D; ++j) {
       const float e = __ldg(er + j);
 #pragma unroll
-      for (int r = 0; r < R; ++r) acc[r] = fmaf(zs[r * Dp4 + j], e, acc[r]);
+      for (int r = 0; r < R; ++r) acc[r][0] = fmaf(zs[r * Dp4 + j], e, acc[r][0]);
     }
   }
+#pragma unroll
+  for (int r = 0; r < R; ++r) out[r] = (NP == 4) ? (acc[r][0] + acc[r][1 % NP]) + (acc[r][2 % NP] + acc[r][3 % NP]) : acc[r][0];
 }
 
-template <typename ZT, bool VEC>
+template <typename ZT, bool VEC, int FR_ROWS, int NP>
 __global__ void __launch_bounds__(FR_THREADS) full_recheck_kernel(
     const ZT* __restrict__ z, const float* __restrict__ E, const float* __restrict__ e2,
     const float* __restrict__ ntab, int K, int D, const int* __restrict__ list,
@@ -362,6 +369,8 @@ __global__ void __launch_bounds__(FR_THREADS) full_recheck_kernel(
   __shared__ int n64;
   const int n = *count;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // rounding steps on a dot product: the FMA chain of one partial, the partial merge, e2 and the final fma
+  const float nround = (VEC && NP == 4) ? (float)(D / 4 + 6) : (float)(D + 2);
   if (threadIdx.x == 0) n64 = 0;
   for (int b0 = blockIdx.x * FR_ROWS; b0 < n; b0 += gridDim.x * FR_ROWS) {
     __syncthreads();
@@ -386,7 +395,7 @@ __global__ void __launch_bounds__(FR_THREADS) full_recheck_kernel(
     for (int r = 0; r < FR_ROWS; ++r) { m1[r] = INFINITY; m2[r] = INFINITY; i1[r] = 0x7fffffff; }
     for (int k = threadIdx.x; k < K; k += FR_THREADS) {
       float acc[FR_ROWS];
-      fr_dots<FR_ROWS, VEC>(E + (size_t)k * D, zs, Dp4, D, acc);
+      fr_dots<FR_ROWS, NP, VEC>(E + (size_t)k * D, zs, Dp4, D, acc);
       const float ek = __ldg(e2 + k);
 #pragma unroll
       for (int r = 0; r < FR_ROWS; ++r) {
@@ -428,10 +437,10 @@ __global__ void __launch_bounds__(FR_THREADS) full_recheck_kernel(
         id = take ? oi : id;
         v2 = nv2;
       }
-      // per-code error: D sequential FMA roundings on the dot, one on e2, one on d; a gap can be off by twice that
+      // per-code error: `nround` roundings of at most u*|z||e| each; a gap can be off by twice that
       const float zn = sqrtf(z2s[r]) * 1.0001f;
       const float cu = reachable_norm(ntab, zn, z2s[r] + v1);
-      const float tau = 4.f * (float)(D + 2) * kU32 * zn * cu + 4.f * kU32 * (cu * cu + fabsf(v1));
+      const float tau = 4.f * nround * kU32 * zn * cu + 4.f * kU32 * (cu * cu + fabsf(v1));
       int need = 0;
       if (rows[r] >= 0) {
         idx_out[rows[r]] = id;
@@ -451,7 +460,7 @@ __global__ void __launch_bounds__(FR_THREADS) full_recheck_kernel(
       int besti = 0x7fffffff;
       for (int k = threadIdx.x; k < K; k += FR_THREADS) {
         float acc[1];
-        fr_dots<1, VEC>(E + (size_t)k * D, zs + r * Dp4, Dp4, D, acc);
+        fr_dots<1, NP, VEC>(E + (size_t)k * D, zs + r * Dp4, Dp4, D, acc);
         const float d = fmaf(-2.f, acc[0], __ldg(e2 + k));
         if (d <= lim) {
           const float* er = E + (size_t)k * D;
@@ -731,28 +740,33 @@ int launch_codebook_prepare(const float* E, int K, int D, void* cb, cudaStream_t
   return G2V_OK;
 }
 
+template <typename ZT, bool VEC, int R, int NP>
+static int launch_full_recheck_v(const ZT* z, const float* E, const void* cb, int K, int D, const int32_t* list,
+                                 const int32_t* count, int64_t max_rows, int32_t* idx,
+                                 unsigned long long* stats, cudaStream_t st) {
+  const size_t smem = (size_t)R * ((D + 3) / 4 * 4) * sizeof(float);
+  long long batches = (max_rows + R - 1) / R;
+  long long cap = (long long)num_sms() * 4;
+  const int grid = (int)(batches < 1 ? 1 : (batches < cap ? batches : cap));
+  const float* ntab = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_tab_offset());
+  const float* e2 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_e2_offset());
+  if (smem > 40 * 1024)
+    G2V_CUDA_CHECK(cudaFuncSetAttribute(full_recheck_kernel<ZT, VEC, R, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  full_recheck_kernel<ZT, VEC, R, NP><<<grid, FR_THREADS, smem, st>>>(z, E, e2, ntab, K, D, list, count, idx, stats);
+  G2V_LAUNCH_CHECK("full_recheck_kernel");
+  return G2V_OK;
+}
+
 template <typename ZT>
 static int launch_full_recheck_t(const ZT* z, const float* E, const void* cb, int K, int D, const int32_t* list,
                                  const int32_t* count, int64_t max_rows, int32_t* idx,
                                  unsigned long long* stats, cudaStream_t st) {
-  const size_t smem = (size_t)FR_ROWS * ((D + 3) / 4 * 4) * sizeof(float);
   const bool vec = (D % 4 == 0) && aligned16(E);
-  long long batches = (max_rows + FR_ROWS - 1) / FR_ROWS;
-  long long cap = (long long)num_sms() * 2;
-  const int grid = (int)(batches < 1 ? 1 : (batches < cap ? batches : cap));
-  const float* ntab = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_tab_offset());
-  const float* e2 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_e2_offset());
-  if (vec) {
-    if (smem > 40 * 1024)
-      G2V_CUDA_CHECK(cudaFuncSetAttribute(full_recheck_kernel<ZT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    full_recheck_kernel<ZT, true><<<grid, FR_THREADS, smem, st>>>(z, E, e2, ntab, K, D, list, count, idx, stats);
-  } else {
-    if (smem > 40 * 1024)
-      G2V_CUDA_CHECK(cudaFuncSetAttribute(full_recheck_kernel<ZT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    full_recheck_kernel<ZT, false><<<grid, FR_THREADS, smem, st>>>(z, E, e2, ntab, K, D, list, count, idx, stats);
-  }
-  G2V_LAUNCH_CHECK("full_recheck_kernel");
-  return G2V_OK;
+  // small codebooks: 8 rows per CTA (more CTAs in flight, 4 partial sums -> tight fp32 bound);
+  // large codebooks: 16 rows per CTA so each codebook row fetched from L2 serves more latents
+  if (!vec) return launch_full_recheck_v<ZT, false, 8, 1>(z, E, cb, K, D, list, count, max_rows, idx, stats, st);
+  if (K <= 2048) return launch_full_recheck_v<ZT, true, 8, 4>(z, E, cb, K, D, list, count, max_rows, idx, stats, st);
+  return launch_full_recheck_v<ZT, true, 16, 1>(z, E, cb, K, D, list, count, max_rows, idx, stats, st);
 }
 
 int launch_full_recheck(const void* z, int z_dtype, const float* E, const void* cb, int K, int D, const int32_t* list,

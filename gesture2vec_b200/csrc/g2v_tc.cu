@@ -76,7 +76,7 @@ struct TcParams {
   const float* ntab;            // reachable-norm table of the codebook (g2v_common.cuh)
   const float* e2;
   int* idx;
-  int* pair_list;               // 3 ints per entry: row, code a, code b
+  int* pair_list;               // int4 per entry: row, code a, code b, code c (-1 if only two)
   int* full_list;               // 1 int per entry: row
   int* counters;                // [0] pairs, [1] fallback rows
   unsigned flags;
@@ -250,8 +250,8 @@ __host__ __device__ inline SmemPlan smem_plan(int n_full, int n_tail, int cg, in
   p.b_off = (a_bytes + 1023u) & ~1023u;
   p.b_stage = B_PANEL / cg;
   p.e2_off = p.b_off + (uint32_t)nstage * p.b_stage;
-  p.xch_off = p.e2_off + 2 * TN * 4;          // 128 rows x 8 words: epilogue half 1 -> half 0
-  p.zst_off = (p.xch_off + TM * 8 * 4 + 127u) & ~127u;
+  p.xch_off = p.e2_off + 2 * TN * 4;          // 128 rows x 12 words: epilogue half 1 -> half 0
+  p.zst_off = (p.xch_off + TM * 12 * 4 + 127u) & ~127u;
   p.rs_off = p.zst_off + (uint32_t)nzslot * ZSLOT;
   p.bar_off = p.rs_off + (nzslot > 0 ? RS_RING * TM * 8 : 0);
   p.tmem_off = p.bar_off + 8 * (2 * MAX_STAGES + 2 * MAX_CHUNKS + 4 + 2 * MAX_ZSLOTS + RS_RING);
@@ -289,14 +289,16 @@ struct Cand {
   uint32_t key2;   // second-best key of the same chain
   int j;           // chain id = column % 32
 };
-// keep the two smallest chain minima (c1 <= c2) and the third smallest key (k3)
-__device__ __forceinline__ void cand_insert(Cand& c1, Cand& c2, uint32_t& k3, const Cand n) {
+// keep the three smallest chain minima (c1 <= c2 <= c3) and the fourth smallest key (k4)
+__device__ __forceinline__ void cand_insert(Cand& c1, Cand& c2, Cand& c3, uint32_t& k4, const Cand n) {
   if (n.key < c1.key) {
-    k3 = c2.key; c2 = c1; c1 = n;
+    k4 = c3.key; c3 = c2; c2 = c1; c1 = n;
   } else if (n.key < c2.key) {
-    k3 = c2.key; c2 = n;
+    k4 = c3.key; c3 = c2; c2 = n;
+  } else if (n.key < c3.key) {
+    k4 = c3.key; c3 = n;
   } else {
-    k3 = min(k3, n.key);
+    k4 = min(k4, n.key);
   }
 }
 
@@ -546,7 +548,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int eh = (warp - EPI_WARP0) >> 2;          // which 16-column half of each 32-column chunk
     const int r = q * 32 + lane;                     // row within the tile == TMEM lane
     const int et = threadIdx.x - EPI_WARP0 * 32;     // 0..255
-    uint32_t* xrow = xch + (size_t)r * 8;            // hand-off slot of this row (half 1 -> half 0)
+    uint32_t* xrow = xch + (size_t)r * 12;           // hand-off slot of this row (half 1 -> half 0)
     uint32_t it = 0, ti = 0;
     const float h_sfrac = FUSED ? P.hdr->sfrac : 0.f, h_e2min = FUSED ? P.hdr->e2min : 0.f,
                 h_scale_e = FUSED ? P.hdr->scale_e : 1.f;
@@ -610,38 +612,29 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
 
       // ---- per-row decision ----
-      // best two chain minima (with the runner-up of their own chain) and the third chain minimum,
-      // first over this thread's 16 chains, then merged with the other half's
-      Cand c1{0xFFFFFFFFu, 0xFFFFFFFFu, 0}, c2{0xFFFFFFFFu, 0xFFFFFFFFu, 0};
-      uint32_t k3 = 0xFFFFFFFFu;
+      // the three best chain minima (each with the runner-up of its own chain) and the fourth chain
+      // minimum: first over this thread's 16 chains, then merged with the other half's
+      const Cand none{0xFFFFFFFFu, 0xFFFFFFFFu, 0};
+      Cand c1 = none, c2 = none, c3 = none;
+      uint32_t k4 = 0xFFFFFFFFu;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) cand_insert(c1, c2, k3, Cand{m1[j], m2[j], eh * 16 + j});
+      for (int j = 0; j < 16; ++j) cand_insert(c1, c2, c3, k4, Cand{m1[j], m2[j], eh * 16 + j});
       if (eh == 1) {
         xrow[0] = c1.key; xrow[1] = c1.key2; xrow[2] = (uint32_t)c1.j;
         xrow[3] = c2.key; xrow[4] = c2.key2; xrow[5] = (uint32_t)c2.j;
-        xrow[6] = k3;
+        xrow[6] = c3.key; xrow[7] = c3.key2; xrow[8] = (uint32_t)c3.j;
+        xrow[9] = k4;
       }
       asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");     // the two warps of this lane quarter
       if (eh == 0) {
-        const Cand o1{xrow[0], xrow[1], (int)xrow[2]}, o2{xrow[3], xrow[4], (int)xrow[5]};
-        const uint32_t ok3 = xrow[6];
-        cand_insert(c1, c2, k3, o1);
-        cand_insert(c1, c2, k3, o2);
-        k3 = min(k3, ok3);
-        // candidates ordered over all codes: t1 <= t2 <= t3
+        cand_insert(c1, c2, c3, k4, Cand{xrow[0], xrow[1], (int)xrow[2]});
+        cand_insert(c1, c2, c3, k4, Cand{xrow[3], xrow[4], (int)xrow[5]});
+        cand_insert(c1, c2, c3, k4, Cand{xrow[6], xrow[7], (int)xrow[8]});
+        k4 = min(k4, xrow[9]);
         const uint32_t t1 = c1.key;
         const int code1 = (int)(t1 & 511u) * 32 + c1.j;
-        uint32_t t2, t3;
-        int code2;
-        bool same_chain;
-        if (c1.key2 < c2.key) {            // runner-up sits in the winner's own chain: its third is unknown
-          t2 = c1.key2; code2 = (int)(t2 & 511u) * 32 + c1.j; same_chain = true; t3 = c2.key;
-        } else {
-          t2 = c2.key; code2 = (int)(t2 & 511u) * 32 + c2.j; same_chain = false;
-          t3 = min(min(c1.key2, c2.key2), k3);
-        }
         if (valid) {
-          const uint32_t v1 = t1 >> 9, v2 = t2 >> 9, v3 = t3 >> 9;
+          const uint32_t v1 = t1 >> 9;
           // certification threshold: per-code error at the largest norm that can still win this row
           // (twice for the distance, twice for a gap of two codes), the fp32 rounding of e2, and the
           // fixed-point rounding of both keys
@@ -649,12 +642,17 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const float cu = reachable_norm(P.ntab, ri.znorm, d1);
           const float tauf = (4.f * (ri.a1 * cu + ri.a0) + 2.3841858e-7f * cu * cu) * ri.S + 4.f;
           const uint32_t tau = (uint32_t)fminf(tauf, 4194304.f);
-          if (!(P.flags & G2V_NO_RECHECK) && (v2 - v1 <= tau)) {
-            if (!same_chain && (v3 - v1 > tau) && code2 < P.K) {
+          auto near = [&](uint32_t key) { return (key >> 9) - v1 <= tau; };   // keys are >= t1
+          if (!(P.flags & G2V_NO_RECHECK) && (near(c2.key) || near(c1.key2))) {
+            // Exact candidates are known only if no chain hides a code: a chain's third-best is unknown,
+            // so a runner-up within tau (of any of the three chains) or a fourth chain within tau means
+            // the whole row must be re-ranked.  Otherwise the candidates are the chain minima within tau.
+            const bool hidden = near(c1.key2) || near(c2.key2) || (near(c3.key) && near(c3.key2)) || near(k4);
+            const int code2 = (int)(c2.key & 511u) * 32 + c2.j;
+            const int code3 = near(c3.key) ? (int)(c3.key & 511u) * 32 + c3.j : -1;
+            if (!hidden && code2 < P.K && code3 < P.K) {
               const int slot = atomicAdd(P.counters + 0, 1);
-              P.pair_list[3 * slot + 0] = (int)row;
-              P.pair_list[3 * slot + 1] = code1;
-              P.pair_list[3 * slot + 2] = code2;
+              reinterpret_cast<int4*>(P.pair_list)[slot] = make_int4((int)row, code1, code2, code3);
             } else {
               const int slot = atomicAdd(P.counters + 1, 1);
               P.full_list[slot] = (int)row;
@@ -678,78 +676,110 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // Each lane owns rows {h*64 + cw*16 + 2i + rsel} and keeps their |z|^2 / |z - z16|^2 in registers.
       const int cw = warp - CONV_WARP0;
       const int q = lane & 15, rsel = lane >> 4;
+      // per-lane constants: row of step i inside a half is r_i = cw*16 + 2i + rsel, and (h*64 + r_i) & 7
+      // == (2i + rsel) & 7, so the swizzled 16-byte chunk of this lane depends on i only
+      const uint32_t src_lane = (uint32_t)((cw * 16 + rsel) * (KC * 4) + q * 16);          // + i * 2 rows
+      const uint32_t dst_lane = (uint32_t)((cw * 16 + rsel) * 128 + (q & 1) * 8);          // + i * 2 rows + swizzle
+      uint32_t swz[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) swz[i] = ((((uint32_t)q >> 1) ^ (uint32_t)((2 * i + rsel) & 7)) << 4) + (uint32_t)i * 256u;
       uint32_t slot = 0, zphase = 0, ti = 0;
       for (int tile = group; tile < P.n_row_tiles; tile += n_groups, ++ti) {
         float z2[16], r2[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) { z2[i] = 0.f; r2[i] = 0.f; }
-        for (int c = 0; c < n_chunks; ++c) {
-          const bool fullp = c < n_full;
-          if (warp == CONV_WARP0) TRACE(4, 100 + c);
+        // ---- full 64-column panels: two 64-row slots each ----
+        for (int c = 0; c < n_full; ++c) {
           mbar_wait(bar_aempty(c), (ti & 1u) ^ 1u);                     // MMA finished with the previous tile's panel
-          if (warp == CONV_WARP0) TRACE(4, 200 + c);
-          const uint32_t abase = a_chunk_addr(c);
+          const uint32_t abase = sA + (uint32_t)c * A_PANEL + dst_lane;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            if (fullp || h == 0) mbar_wait(bar_zfull(slot), zphase);    // tail: one slot holds all 128 rows
-            if (warp == CONV_WARP0) TRACE(4, 300 + 2 * c + h);
-            const unsigned char* zsrc = gbase + sp.zst_off + slot * ZSLOT;
+            mbar_wait(bar_zfull(slot), zphase);
+            const unsigned char* zsrc = gbase + sp.zst_off + slot * ZSLOT + src_lane;
             float4 v[8];
-            if (fullp) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                v[i] = *reinterpret_cast<const float4*>(zsrc + (cw * 16 + 2 * i + rsel) * (KC * 4) + q * 16);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                v[i] = (q < 4) ? *reinterpret_cast<const float4*>(zsrc + (h * 64 + cw * 16 + 2 * i + rsel) * (KT * 4) + q * 16)
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(zsrc + i * 2 * (KC * 4));
             __syncwarp();
-            if (fullp || h == 1) {
-              if (lane == 0) mbar_arrive(bar_zempty(slot));             // slot is in registers
-              if (++slot == (uint32_t)P.nzslot) { slot = 0; zphase ^= 1u; }
-            }
-            if (!(P.flags & kDbgSkipConv))
+            if (lane == 0) mbar_arrive(bar_zempty(slot));               // slot is in registers
+            if (++slot == (uint32_t)P.nzslot) { slot = 0; zphase ^= 1u; }
+            if (!(P.flags & kDbgSkipConv)) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const uint32_t rr = (uint32_t)(h * 64 + cw * 16 + 2 * i + rsel);
-              const __half2 h01 = __floats2half2_rn(v[i].x, v[i].y), h23 = __floats2half2_rn(v[i].z, v[i].w);
-              const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-              const float e0 = v[i].x - f01.x, e1 = v[i].y - f01.y, e2r = v[i].z - f23.x, e3 = v[i].w - f23.y;
-              z2[h * 8 + i] = fmaf(v[i].x, v[i].x, fmaf(v[i].y, v[i].y, fmaf(v[i].z, v[i].z, fmaf(v[i].w, v[i].w, z2[h * 8 + i]))));
-              r2[h * 8 + i] = fmaf(e0, e0, fmaf(e1, e1, fmaf(e2r, e2r, fmaf(e3, e3, r2[h * 8 + i]))));
-              uint32_t dst;
-              if (fullp) dst = abase + rr * 128u + ((((uint32_t)q >> 1) ^ (rr & 7u)) << 4) + ((uint32_t)q & 1u) * 8u;
-              else dst = abase + rr * 32u + (((((uint32_t)q >> 1) & 1u) ^ ((rr >> 2) & 1u)) << 4) + ((uint32_t)q & 1u) * 8u;
-              if (fullp || q < 4)
-                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(*reinterpret_cast<const uint32_t*>(&h01)),
-                             "r"(*reinterpret_cast<const uint32_t*>(&h23))
+              for (int i = 0; i < 8; ++i) {
+                const __half2 h01 = __floats2half2_rn(v[i].x, v[i].y), h23 = __floats2half2_rn(v[i].z, v[i].w);
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                const float e0 = v[i].x - f01.x, e1 = v[i].y - f01.y, e2r = v[i].z - f23.x, e3 = v[i].w - f23.y;
+                z2[h * 8 + i] = fmaf(v[i].x, v[i].x, fmaf(v[i].y, v[i].y, fmaf(v[i].z, v[i].z, fmaf(v[i].w, v[i].w, z2[h * 8 + i]))));
+                r2[h * 8 + i] = fmaf(e0, e0, fmaf(e1, e1, fmaf(e2r, e2r, fmaf(e3, e3, r2[h * 8 + i]))));
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(abase + (uint32_t)h * (64u * 128u) + swz[i]),
+                             "r"(*reinterpret_cast<const uint32_t*>(&h01)), "r"(*reinterpret_cast<const uint32_t*>(&h23))
                              : "memory");
-            }
-          }
-          if (c == n_chunks - 1) {
-            // row statistics of the finished tile, before the last panel is published
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float a = z2[i], b = r2[i];
-#pragma unroll
-              for (int o = 1; o < 16; o <<= 1) {
-                a += __shfl_xor_sync(0xffffffffu, a, o);
-                b += __shfl_xor_sync(0xffffffffu, b, o);
               }
-              if (q == 0) rowstat[(ti % RS_RING) * TM + (i >> 3) * 64 + cw * 16 + 2 * (i & 7) + rsel] = make_float2(a, b);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_rsfull(ti % RS_RING));
           }
-          if (warp == CONV_WARP0) TRACE(4, 400 + c);
           fence_proxy_async();                                          // my stores -> visible to the MMA's reads
           asm volatile("bar.sync 7, 128;" ::: "memory");                // all four converter warps
-          if (warp == CONV_WARP0) TRACE(4, 500 + c);
           if (threadIdx.x == CONV_WARP0 * 32) {                         // one arrive per CTA and panel
             if (CG == 1 || leader) mbar_arrive(bar_afull(c));
             else mbar_arrive_cluster(bar_afull(c), 0);
+          }
+        }
+        // ---- 16-column tails: one slot holds all 128 rows; only lanes q < 4 carry data ----
+        for (int c = n_full; c < n_chunks; ++c) {
+          mbar_wait(bar_aempty(c), (ti & 1u) ^ 1u);
+          mbar_wait(bar_zfull(slot), zphase);
+          const unsigned char* zsrc = gbase + sp.zst_off + slot * ZSLOT;
+          const uint32_t abase = a_chunk_addr(c);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t rr = (uint32_t)(h * 64 + cw * 16 + 2 * i + rsel);
+              if (q < 4) {
+                const float4 v = *reinterpret_cast<const float4*>(zsrc + rr * (KT * 4) + q * 16);
+                const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                const float e0 = v.x - f01.x, e1 = v.y - f01.y, e2r = v.z - f23.x, e3 = v.w - f23.y;
+                z2[h * 8 + i] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, z2[h * 8 + i]))));
+                r2[h * 8 + i] = fmaf(e0, e0, fmaf(e1, e1, fmaf(e2r, e2r, fmaf(e3, e3, r2[h * 8 + i]))));
+                const uint32_t dst = abase + rr * 32u + (((((uint32_t)q >> 1) & 1u) ^ ((rr >> 2) & 1u)) << 4) + ((uint32_t)q & 1u) * 8u;
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(*reinterpret_cast<const uint32_t*>(&h01)),
+                             "r"(*reinterpret_cast<const uint32_t*>(&h23))
+                             : "memory");
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_zempty(slot));
+          if (++slot == (uint32_t)P.nzslot) { slot = 0; zphase ^= 1u; }
+          if (c == n_chunks - 1) break;                                 // statistics first (below), then publish
+          fence_proxy_async();
+          asm volatile("bar.sync 7, 128;" ::: "memory");
+          if (threadIdx.x == CONV_WARP0 * 32) {
+            if (CG == 1 || leader) mbar_arrive(bar_afull(c));
+            else mbar_arrive_cluster(bar_afull(c), 0);
+          }
+        }
+        // row statistics of the finished tile, before its last panel is published
+        {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float a = z2[i], b = r2[i];
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) {
+              a += __shfl_xor_sync(0xffffffffu, a, o);
+              b += __shfl_xor_sync(0xffffffffu, b, o);
+            }
+            if (q == 0) rowstat[(ti % RS_RING) * TM + (i >> 3) * 64 + cw * 16 + 2 * (i & 7) + rsel] = make_float2(a, b);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_rsfull(ti % RS_RING));
+        }
+        if (P.n_tail > 0) {                                             // publish the last tail panel
+          fence_proxy_async();
+          asm volatile("bar.sync 7, 128;" ::: "memory");
+          if (threadIdx.x == CONV_WARP0 * 32) {
+            if (CG == 1 || leader) mbar_arrive(bar_afull(n_chunks - 1));
+            else mbar_arrive_cluster(bar_afull(n_chunks - 1), 0);
           }
         }
       }
@@ -818,8 +848,8 @@ __global__ void __launch_bounds__(256) row_prep_kernel(const ZT* __restrict__ z,
   }
 }
 
-// exact re-rank of two candidate codes per listed row (one warp per entry, fp64); all loads of an
-// entry are issued before the first use
+// exact re-rank of the two or three candidate codes of each listed row (one warp per entry, fp64);
+// all loads of an entry are issued before the first use.  Lowest index wins exact ties.
 template <typename ZT>
 __global__ void __launch_bounds__(256) pair_recheck_kernel(const ZT* __restrict__ z, const float* __restrict__ E,
                                                            int D, const int* __restrict__ pair_list,
@@ -831,15 +861,17 @@ __global__ void __launch_bounds__(256) pair_recheck_kernel(const ZT* __restrict_
   constexpr int U = 4;                                   // 4 x 128 columns per pass
   const bool vec = (D % 4 == 0) && sizeof(ZT) == 4;
   for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n; e += wstride) {
-    const int row = pair_list[3 * e], a = pair_list[3 * e + 1], b = pair_list[3 * e + 2];
+    const int4 ent = reinterpret_cast<const int4*>(pair_list)[e];
+    const int row = ent.x, a = ent.y, b = ent.z, c = ent.w;
     const ZT* zr = z + (size_t)row * D;
     const float* ea = E + (size_t)a * D;
     const float* eb = E + (size_t)b * D;
-    double da = 0.0, db = 0.0;
+    const float* ec = E + (size_t)(c >= 0 ? c : a) * D;
+    double da = 0.0, db = 0.0, dc = 0.0;
     if (vec) {
       const float* zf = reinterpret_cast<const float*>(zr);
       for (int j0 = lane * 4; j0 < D; j0 += 128 * U) {
-        float4 zv[U], av[U], bv[U];
+        float4 zv[U], av[U], bv[U], cv[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int j = j0 + 128 * u;
@@ -847,8 +879,9 @@ __global__ void __launch_bounds__(256) pair_recheck_kernel(const ZT* __restrict_
             zv[u] = __ldg(reinterpret_cast<const float4*>(zf + j));
             av[u] = __ldg(reinterpret_cast<const float4*>(ea + j));
             bv[u] = __ldg(reinterpret_cast<const float4*>(eb + j));
+            cv[u] = (c >= 0) ? __ldg(reinterpret_cast<const float4*>(ec + j)) : av[u];
           } else {
-            zv[u] = av[u] = bv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            zv[u] = av[u] = bv[u] = cv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
 #pragma unroll
@@ -856,28 +889,39 @@ __global__ void __launch_bounds__(256) pair_recheck_kernel(const ZT* __restrict_
           const float zz[4] = {zv[u].x, zv[u].y, zv[u].z, zv[u].w};
           const float aa[4] = {av[u].x, av[u].y, av[u].z, av[u].w};
           const float bb[4] = {bv[u].x, bv[u].y, bv[u].z, bv[u].w};
+          const float cc[4] = {cv[u].x, cv[u].y, cv[u].z, cv[u].w};
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const double xa = (double)zz[c] - (double)aa[c], xb = (double)zz[c] - (double)bb[c];
+          for (int t = 0; t < 4; ++t) {
+            const double xa = (double)zz[t] - (double)aa[t], xb = (double)zz[t] - (double)bb[t];
+            const double xc = (double)zz[t] - (double)cc[t];
             da = fma(xa, xa, da);
             db = fma(xb, xb, db);
+            dc = fma(xc, xc, dc);
           }
         }
       }
     } else {
       for (int j = lane; j < D; j += 32) {
         const double zv = (double)ld_f32(zr + j);
-        const double xa = zv - (double)__ldg(ea + j), xb = zv - (double)__ldg(eb + j);
+        const double xa = zv - (double)__ldg(ea + j), xb = zv - (double)__ldg(eb + j), xc = zv - (double)__ldg(ec + j);
         da = fma(xa, xa, da);
         db = fma(xb, xb, db);
+        dc = fma(xc, xc, dc);
       }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       da += __shfl_xor_sync(0xffffffffu, da, o);
       db += __shfl_xor_sync(0xffffffffu, db, o);
+      dc += __shfl_xor_sync(0xffffffffu, dc, o);
     }
-    if (lane == 0) idx[row] = (db < da || (db == da && b < a)) ? b : a;
+    if (lane == 0) {
+      int best = a;
+      double dbest = da;
+      if (db < dbest || (db == dbest && b < best)) { best = b; dbest = db; }
+      if (c >= 0 && (dc < dbest || (dc == dbest && c < best))) { best = c; dbest = dc; }
+      idx[row] = best;
+    }
   }
   if (stats && blockIdx.x == 0 && threadIdx.x == 0) {
     atomicAdd(stats + G2V_STAT_PAIR_RECHECK, (unsigned long long)n);
@@ -938,7 +982,7 @@ TcWs tc_ws(int64_t N, int D) {
   w.z16 = 0;
   w.rowinfo = al256((size_t)N * Dp * 2);
   w.pairs = w.rowinfo + al256((size_t)N * sizeof(RowInfo));
-  w.fulls = w.pairs + al256((size_t)N * 12);
+  w.fulls = w.pairs + al256((size_t)N * 16);
   w.counters = w.fulls + al256((size_t)N * 4);
   w.total = w.counters + 256;
   return w;
