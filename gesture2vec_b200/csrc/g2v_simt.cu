@@ -355,11 +355,12 @@ template <typename ZT, bool VEC, int FR_ROWS, int NP>
 __global__ void __launch_bounds__(FR_THREADS) full_recheck_kernel(
     const ZT* __restrict__ z, const float* __restrict__ E, const float* __restrict__ e2,
     const float* __restrict__ ntab, int K, int D, const int* __restrict__ list,
-    const int* __restrict__ count, int* __restrict__ idx_out, unsigned long long* stats) {
+    const int* __restrict__ count, int skip, int* __restrict__ idx_out, unsigned long long* stats) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* zs = reinterpret_cast<float*>(smem_raw);                 // [FR_ROWS][Dp4]
   const int Dp4 = (D + 3) & ~3;
   constexpr int NW = FR_THREADS / 32;
+  list += skip;                                                   // the first `skip` rows are handled by full64_kernel
   __shared__ double bv[NW];
   __shared__ float b1[NW][FR_ROWS], b2[NW][FR_ROWS];
   __shared__ int bi[NW][FR_ROWS];
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(FR_THREADS) full_recheck_kernel(
   __shared__ int need64[FR_ROWS];
   __shared__ float z2s[FR_ROWS], v1s[FR_ROWS], taus[FR_ROWS];
   __shared__ int n64;
-  const int n = *count;
+  const int n = *count - skip;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // rounding steps on a dot product: the FMA chain of one partial, the partial merge, e2 and the final fma
   const float nround = (VEC && NP == 4) ? (float)(D / 4 + 6) : (float)(D + 2);
@@ -740,6 +741,58 @@ int launch_codebook_prepare(const float* E, int K, int D, void* cb, cudaStream_t
   return G2V_OK;
 }
 
+// Exact re-rank of a SMALL number of listed rows: one CTA per row, warps split the codes, lanes split
+// the dimensions (coalesced), straight fp64.  Used for the first kFull64Cap listed rows (the usual
+// case: a few hundred rows per million); anything beyond goes to the batched fp32+fp64 kernel above.
+constexpr int kFull64Cap = 4096;
+
+template <typename ZT>
+__global__ void __launch_bounds__(256) full64_kernel(const ZT* __restrict__ z, const float* __restrict__ E, int K, int D,
+                                                     const int* __restrict__ list, const int* __restrict__ count,
+                                                     int* __restrict__ idx_out, unsigned long long* stats) {
+  __shared__ double bv[8];
+  __shared__ int bi[8];
+  const int n = min(*count, kFull64Cap);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int e = blockIdx.x; e < n; e += gridDim.x) {
+    const int row = list[e];
+    const ZT* zr = z + (size_t)row * D;
+    double best = INFINITY;
+    int besti = 0x7fffffff;
+    for (int k = warp; k < K; k += 8) {
+      const float* er = E + (size_t)k * D;
+      double s = 0.0;
+      for (int j0 = lane; j0 < D; j0 += 32 * 8) {
+        float zv[8], ev[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = j0 + 32 * u;
+          zv[u] = j < D ? to_f32(zr[j]) : 0.f;
+          ev[u] = j < D ? __ldg(er + j) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const double df = (double)zv[u] - (double)ev[u];
+          s = fma(df, df, s);
+        }
+      }
+      s = warp_sum(s);
+      if (s < best) { best = s; besti = k; }                 // ascending k inside a warp: first wins
+    }
+    __syncthreads();
+    if (lane == 0) { bv[warp] = best; bi[warp] = besti; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double v = bv[0];
+      int id = bi[0];
+      for (int w = 1; w < 8; ++w)
+        if (bv[w] < v || (bv[w] == v && bi[w] < id)) { v = bv[w]; id = bi[w]; }
+      idx_out[row] = id;
+    }
+  }
+  if (stats && blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(stats + G2V_STAT_FULL_RECHECK, (unsigned long long)n);
+}
+
 template <typename ZT, bool VEC, int R, int NP>
 static int launch_full_recheck_v(const ZT* z, const float* E, const void* cb, int K, int D, const int32_t* list,
                                  const int32_t* count, int64_t max_rows, int32_t* idx,
@@ -752,7 +805,7 @@ static int launch_full_recheck_v(const ZT* z, const float* E, const void* cb, in
   const float* e2 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_e2_offset());
   if (smem > 40 * 1024)
     G2V_CUDA_CHECK(cudaFuncSetAttribute(full_recheck_kernel<ZT, VEC, R, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  full_recheck_kernel<ZT, VEC, R, NP><<<grid, FR_THREADS, smem, st>>>(z, E, e2, ntab, K, D, list, count, idx, stats);
+  full_recheck_kernel<ZT, VEC, R, NP><<<grid, FR_THREADS, smem, st>>>(z, E, e2, ntab, K, D, list, count, kFull64Cap, idx, stats);
   G2V_LAUNCH_CHECK("full_recheck_kernel");
   return G2V_OK;
 }
@@ -761,6 +814,14 @@ template <typename ZT>
 static int launch_full_recheck_t(const ZT* z, const float* E, const void* cb, int K, int D, const int32_t* list,
                                  const int32_t* count, int64_t max_rows, int32_t* idx,
                                  unsigned long long* stats, cudaStream_t st) {
+  {
+    const long long cap = max_rows < kFull64Cap ? max_rows : kFull64Cap;
+    const long long lim = (long long)num_sms() * 8;
+    const int g = (int)(cap < 1 ? 1 : (cap < lim ? cap : lim));
+    full64_kernel<ZT><<<g, 256, 0, st>>>(z, E, K, D, list, count, idx, stats);
+    G2V_LAUNCH_CHECK("full64_kernel");
+    if (max_rows <= kFull64Cap) return G2V_OK;               // nothing can be left for the batched kernel
+  }
   const bool vec = (D % 4 == 0) && aligned16(E);
   // small codebooks: 8 rows per CTA (more CTAs in flight, 4 partial sums -> tight fp32 bound);
   // large codebooks: 16 rows per CTA so each codebook row fetched from L2 serves more latents

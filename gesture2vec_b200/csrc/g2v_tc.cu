@@ -78,7 +78,8 @@ struct TcParams {
   int* idx;
   int* pair_list;               // int4 per entry: row, code a, code b, code c (-1 if only two)
   int* full_list;               // 1 int per entry: row
-  int* counters;                // [0] pairs, [1] fallback rows
+  int* chain_list;              // int4 per entry: row, chain (code % 32), extra code a, extra code b (-1 = none)
+  int* counters;                // [0] candidate entries, [1] full-row fallbacks, [2] chain entries
   unsigned flags;
 };
 
@@ -647,12 +648,21 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // Exact candidates are known only if no chain hides a code: a chain's third-best is unknown,
             // so a runner-up within tau (of any of the three chains) or a fourth chain within tau means
             // the whole row must be re-ranked.  Otherwise the candidates are the chain minima within tau.
-            const bool hidden = near(c1.key2) || near(c2.key2) || (near(c3.key) && near(c3.key2)) || near(k4);
+            const bool h1 = near(c1.key2), h2 = near(c2.key2), h3 = near(c3.key2), h4 = near(k4);
             const int code2 = (int)(c2.key & 511u) * 32 + c2.j;
-            const int code3 = near(c3.key) ? (int)(c3.key & 511u) * 32 + c3.j : -1;
-            if (!hidden && code2 < P.K && code3 < P.K) {
+            const int code3 = (int)(c3.key & 511u) * 32 + c3.j;
+            const bool n2 = near(c2.key) && code2 < P.K, n3 = near(c3.key) && code3 < P.K;
+            if (!h1 && !h2 && !h3 && !h4) {
+              // every candidate is known: the chain minima within tau
               const int slot = atomicAdd(P.counters + 0, 1);
-              reinterpret_cast<int4*>(P.pair_list)[slot] = make_int4((int)row, code1, code2, code3);
+              reinterpret_cast<int4*>(P.pair_list)[slot] = make_int4((int)row, code1, n2 ? code2 : code1, n3 ? code3 : -1);
+            } else if (!h4 && ((int)h1 + (int)h2 + (int)h3) == 1) {
+              // exactly one chain may hide codes: re-rank that chain's K/32 codes plus the other chains' minima
+              const int slot = atomicAdd(P.counters + 2, 1);
+              const int cj = h1 ? c1.j : (h2 ? c2.j : c3.j);
+              const int ea = h1 ? (n2 ? code2 : -1) : code1;
+              const int eb = h3 ? (n2 ? code2 : -1) : (n3 ? code3 : -1);
+              reinterpret_cast<int4*>(P.chain_list)[slot] = make_int4((int)row, cj, ea, eb);
             } else {
               const int slot = atomicAdd(P.counters + 1, 1);
               P.full_list[slot] = (int)row;
@@ -858,7 +868,7 @@ __global__ void __launch_bounds__(256) pair_recheck_kernel(const ZT* __restrict_
   const int lane = threadIdx.x & 31;
   const int n = counters[0];
   const int wstride = (gridDim.x * blockDim.x) >> 5;
-  constexpr int U = 4;                                   // 4 x 128 columns per pass
+  constexpr int U = 2;                                   // 2 x 128 columns per pass (registers -> occupancy)
   const bool vec = (D % 4 == 0) && sizeof(ZT) == 4;
   for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n; e += wstride) {
     const int4 ent = reinterpret_cast<const int4*>(pair_list)[e];
@@ -929,6 +939,50 @@ __global__ void __launch_bounds__(256) pair_recheck_kernel(const ZT* __restrict_
   }
 }
 
+// exact re-rank over one chain (codes j, j+32, ... < K) plus up to two extra codes (one warp per
+// entry, fp64, lanes split the dimensions); lowest index wins exact ties
+template <typename ZT>
+__global__ void __launch_bounds__(256) chain_recheck_kernel(const ZT* __restrict__ z, const float* __restrict__ E,
+                                                            int K, int D, const int* __restrict__ chain_list,
+                                                            const int* __restrict__ counters, int* __restrict__ idx,
+                                                            unsigned long long* stats) {
+  const int lane = threadIdx.x & 31;
+  const int n = counters[2];
+  const int wstride = (gridDim.x * blockDim.x) >> 5;
+  for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n; e += wstride) {
+    const int4 ent = reinterpret_cast<const int4*>(chain_list)[e];
+    const ZT* zr = z + (size_t)ent.x * D;
+    double best = INFINITY;
+    int besti = 0x7fffffff;
+    const int nchain = (K - ent.y + 31) / 32;
+    for (int t = 0; t < nchain + 2; ++t) {
+      const int k = t < nchain ? ent.y + 32 * t : (t == nchain ? ent.z : ent.w);
+      if (k < 0 || k >= K) continue;                                // warp-uniform
+      const float* er = E + (size_t)k * D;
+      double s = 0.0;
+      for (int j0 = lane; j0 < D; j0 += 32 * 8) {
+        float zv[8], ev[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = j0 + 32 * u;
+          zv[u] = j < D ? ld_f32(zr + j) : 0.f;
+          ev[u] = j < D ? __ldg(er + j) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const double df = (double)zv[u] - (double)ev[u];
+          s = fma(df, df, s);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (s < best || (s == best && k < besti)) { best = s; besti = k; }
+    }
+    if (lane == 0 && besti != 0x7fffffff) idx[ent.x] = besti;
+  }
+  if (stats && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + G2V_STAT_PAIR_RECHECK, (unsigned long long)n);
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -974,7 +1028,7 @@ int make_map(CUtensorMap* tm, const void* gptr, uint64_t rows, uint64_t cols, ui
 inline size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 
 struct TcWs {
-  size_t z16, rowinfo, pairs, fulls, counters, total;
+  size_t z16, rowinfo, pairs, fulls, chains, counters, total;
 };
 TcWs tc_ws(int64_t N, int D) {
   const int Dp = round_up(D, 16);
@@ -983,7 +1037,8 @@ TcWs tc_ws(int64_t N, int D) {
   w.rowinfo = al256((size_t)N * Dp * 2);
   w.pairs = w.rowinfo + al256((size_t)N * sizeof(RowInfo));
   w.fulls = w.pairs + al256((size_t)N * 16);
-  w.counters = w.fulls + al256((size_t)N * 4);
+  w.chains = w.fulls + al256((size_t)N * 4);
+  w.counters = w.chains + al256((size_t)N * 16);
   w.total = w.counters + 256;
   return w;
 }
@@ -998,6 +1053,7 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
   RowInfo* rowinfo = reinterpret_cast<RowInfo*>(base + w.rowinfo);
   int* pairs = reinterpret_cast<int*>(base + w.pairs);
   int* fulls = reinterpret_cast<int*>(base + w.fulls);
+  int* chains = reinterpret_cast<int*>(base + w.chains);
   int* counters = reinterpret_cast<int*>(base + w.counters);
   const auto* hdr = reinterpret_cast<const CbHeader*>(cb);
   const float* e2 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_e2_offset());
@@ -1029,7 +1085,7 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
   P.n_row_tiles = (int)((N + (long long)TM * cg - 1) / ((long long)TM * cg));   // tiles of 128*cg rows
   P.rowinfo = rowinfo; P.e2 = e2; P.idx = idx;
   P.ntab = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_tab_offset());
-  P.pair_list = pairs; P.full_list = fulls; P.counters = counters; P.flags = flags;
+  P.pair_list = pairs; P.full_list = fulls; P.chain_list = chains; P.counters = counters; P.flags = flags;
   P.trace = nullptr;
   if (const char* env = getenv("G2V_TC_TRACE")) P.trace = reinterpret_cast<long long*>(strtoull(env, nullptr, 0));
   if (const char* env = getenv("G2V_TC_DEBUG")) P.flags |= ((unsigned)atoi(env) & 15u) << 8;   // results are wrong with these
@@ -1117,9 +1173,11 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
   if (pev1) G2V_CUDA_CHECK(cudaEventRecord(pev1, st));
 
   if (!(flags & G2V_NO_RECHECK)) {
-    const int pgrid = num_sms() * 2;
+    const int pgrid = num_sms() * 4;
     pair_recheck_kernel<ZT><<<pgrid, 256, 0, st>>>(z, E, D, pairs, counters, idx, stats);
     G2V_LAUNCH_CHECK("pair_recheck_kernel");
+    chain_recheck_kernel<ZT><<<pgrid, 256, 0, st>>>(z, E, K, D, chains, counters, idx, stats);
+    G2V_LAUNCH_CHECK("chain_recheck_kernel");
     rc = launch_full_recheck(z, z_dtype, E, cb, K, D, fulls, counters + 1, N, idx, stats, st);
     if (rc) return rc;
   }
