@@ -151,18 +151,18 @@ int g2v_vq_search(const void* z, int z_dtype, const float* E, const void* cb, in
 }
 
 int g2v_vq_apply(const float* x, const float* zs, const float* E, const int32_t* idx, int64_t N, int K, int D,
-                 float* out, double* sse, int32_t* counts, float* dwr, void* stream) {
-  if (bad_shape(N, K, D) || !E || (N > 0 && (!x || !idx))) return G2V_ERR_INVALID;
+                 float* out, double* sse, int32_t* counts, float* dwr, int dwr_replicas, void* stream) {
+  if (bad_shape(N, K, D) || !E || (N > 0 && (!x || !idx)) || (dwr && dwr_replicas < 1)) return G2V_ERR_INVALID;
   if (N == 0) return G2V_OK;
   int rc = check_arch();
   if (rc) return rc;
-  return launch_apply(x, zs, E, idx, N, K, D, out, sse, counts, dwr, (cudaStream_t)stream);
+  return launch_apply(x, zs, E, idx, N, K, D, out, sse, counts, dwr, dwr_replicas, (cudaStream_t)stream);
 }
 
-int g2v_vq_stats_pack(const int32_t* counts, const double* sse, int64_t N, int K, int D, float* packed,
-                      void* stream) {
-  if (K <= 0 || D <= 0 || N < 0 || !packed) return G2V_ERR_INVALID;
-  return launch_stats_pack(counts, sse, N, K, D, packed, (cudaStream_t)stream);
+int g2v_vq_stats_pack(const int32_t* counts, const double* sse, const float* dwr, int dwr_replicas, int64_t N,
+                      int K, int D, float* packed, void* stream) {
+  if (K <= 0 || D <= 0 || N < 0 || !packed || (dwr && dwr_replicas < 1)) return G2V_ERR_INVALID;
+  return launch_stats_pack(counts, sse, dwr, dwr_replicas, N, K, D, packed, (cudaStream_t)stream);
 }
 
 int g2v_vq_stats_finalize(const float* packed, int K, int D, float coef_codebook, float coef_commit,

@@ -93,9 +93,9 @@ int launch_full_recheck(const void* z, int z_dtype, const float* E, const void* 
                         const int32_t* count, int64_t max_rows, int32_t* idx, unsigned long long* stats,
                         cudaStream_t st);
 int launch_apply(const float* x, const float* zs, const float* E, const int32_t* idx, int64_t N, int K,
-                 int D, float* out, double* sse, int32_t* counts, float* dwr, cudaStream_t st);
-int launch_stats_pack(const int32_t* counts, const double* sse, int64_t N, int K, int D, float* packed,
-                      cudaStream_t st);
+                 int D, float* out, double* sse, int32_t* counts, float* dwr, int dwr_replicas, cudaStream_t st);
+int launch_stats_pack(const int32_t* counts, const double* sse, const float* dwr, int dwr_replicas, int64_t N,
+                      int K, int D, float* packed, cudaStream_t st);
 int launch_stats_finalize(const float* packed, int K, int D, float coef_codebook, float coef_commit,
                           float* loss, float* ppl, cudaStream_t st);
 int launch_ema_update(float* cs, float* ema_w, const float* E_old, float* E_new, const float* packed,

@@ -504,9 +504,10 @@ template <bool VEC>
 __global__ void __launch_bounds__(APPLY_WARPS * 32) apply_kernel(
     const float* __restrict__ x, const float* __restrict__ zs, const float* __restrict__ E,
     const int* __restrict__ idx, long long N, int K, int D, float* __restrict__ out, double* sse,
-    int* counts, float* dwr, int use_hist) {
+    int* counts, float* dwr, int dwr_replicas, int use_hist) {
   extern __shared__ int hist[];
   __shared__ double wsum[APPLY_WARPS];
+  if (dwr) dwr += (size_t)(blockIdx.x % dwr_replicas) * K * D;      // this block's private copy
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (use_hist) {
     for (int k = threadIdx.x; k < K; k += blockDim.x) hist[k] = 0;
@@ -609,13 +610,21 @@ __global__ void __launch_bounds__(256) backward_kernel(const float* __restrict__
 // ------------------------------------------------------------------------------------------
 // scalar outputs / EMA / misc
 // ------------------------------------------------------------------------------------------
-__global__ void stats_pack_kernel(const int* __restrict__ counts, const double* __restrict__ sse, long long N,
-                                  int K, int D, float* __restrict__ packed) {
-  float* tail = packed + (size_t)K * D;
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K + 2; k += gridDim.x * blockDim.x) {
-    if (k < K) tail[k] = counts ? (float)counts[k] : 0.f;
-    else if (k == K) tail[k] = sse ? (float)(*sse) : 0.f;
+__global__ void stats_pack_kernel(const int* __restrict__ counts, const double* __restrict__ sse,
+                                  const float* __restrict__ dwr, int reps, long long N, int K, int D,
+                                  float* __restrict__ packed) {
+  const size_t KD = (size_t)K * D;
+  float* tail = packed + KD;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  for (size_t k = tid; k < (size_t)K + 2; k += nth) {
+    if (k < (size_t)K) tail[k] = counts ? (float)counts[k] : 0.f;
+    else if (k == (size_t)K) tail[k] = sse ? (float)(*sse) : 0.f;
     else tail[k] = (float)N;
+  }
+  for (size_t i = tid; i < KD; i += nth) {                 // sum the replicas in a fixed order
+    float a = 0.f;
+    for (int r = 0; r < reps; ++r) a += dwr[(size_t)r * KD + i];
+    packed[i] = a;
   }
 }
 
@@ -750,36 +759,52 @@ template <typename ZT>
 __global__ void __launch_bounds__(256) full64_kernel(const ZT* __restrict__ z, const float* __restrict__ E, int K, int D,
                                                      const int* __restrict__ list, const int* __restrict__ count,
                                                      int* __restrict__ idx_out, unsigned long long* stats) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* zs = reinterpret_cast<float*>(smem_raw);            // the row, zero padded to a multiple of 32
   __shared__ double bv[8];
   __shared__ int bi[8];
   const int n = min(*count, kFull64Cap);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Dp = (D + 31) & ~31;
+  constexpr int KC4 = 4;                                     // codes in flight per warp (latency hiding)
   for (int e = blockIdx.x; e < n; e += gridDim.x) {
     const int row = list[e];
-    const ZT* zr = z + (size_t)row * D;
+    __syncthreads();
+    for (int j = threadIdx.x; j < Dp; j += blockDim.x) zs[j] = j < D ? to_f32(z[(size_t)row * D + j]) : 0.f;
+    __syncthreads();
     double best = INFINITY;
     int besti = 0x7fffffff;
-    for (int k = warp; k < K; k += 8) {
-      const float* er = E + (size_t)k * D;
-      double s = 0.0;
-      for (int j0 = lane; j0 < D; j0 += 32 * 8) {
-        float zv[8], ev[8];
+    for (int kb = warp * KC4; kb < K; kb += 8 * KC4) {
+      double s[KC4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int j = j0 + 32 * u;
-          zv[u] = j < D ? to_f32(zr[j]) : 0.f;
-          ev[u] = j < D ? __ldg(er + j) : 0.f;
+      for (int c = 0; c < KC4; ++c) s[c] = 0.0;
+      for (int j0 = lane; j0 < Dp; j0 += 32 * 4) {
+        float ev[KC4][4];
+#pragma unroll
+        for (int c = 0; c < KC4; ++c) {
+          const float* er = E + (size_t)min(kb + c, K - 1) * D;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) ev[c][u] = (j0 + 32 * u < D) ? __ldg(er + j0 + 32 * u) : 0.f;
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const double df = (double)zv[u] - (double)ev[u];
-          s = fma(df, df, s);
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + 32 * u;
+          if (j < Dp) {
+            const double zv = (double)zs[j];
+#pragma unroll
+            for (int c = 0; c < KC4; ++c) {
+              const double df = zv - (double)ev[c][u];
+              s[c] = fma(df, df, s[c]);
+            }
+          }
         }
       }
-      s = warp_sum(s);
-      if (s < best) { best = s; besti = k; }                 // ascending k inside a warp: first wins
+#pragma unroll
+      for (int c = 0; c < KC4; ++c) {
+        const double t = warp_sum(s[c]);
+        if (kb + c < K && t < best) { best = t; besti = kb + c; }     // ascending k inside a warp: first wins
+      }
     }
-    __syncthreads();
     if (lane == 0) { bv[warp] = best; bi[warp] = besti; }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -818,7 +843,7 @@ static int launch_full_recheck_t(const ZT* z, const float* E, const void* cb, in
     const long long cap = max_rows < kFull64Cap ? max_rows : kFull64Cap;
     const long long lim = (long long)num_sms() * 8;
     const int g = (int)(cap < 1 ? 1 : (cap < lim ? cap : lim));
-    full64_kernel<ZT><<<g, 256, 0, st>>>(z, E, K, D, list, count, idx, stats);
+    full64_kernel<ZT><<<g, 256, (size_t)((D + 31) / 32 * 32) * sizeof(float), st>>>(z, E, K, D, list, count, idx, stats);
     G2V_LAUNCH_CHECK("full64_kernel");
     if (max_rows <= kFull64Cap) return G2V_OK;               // nothing can be left for the batched kernel
   }
@@ -882,23 +907,24 @@ int launch_search_simt(const void* z, int z_dtype, const float* E, const void* c
 }
 
 int launch_apply(const float* x, const float* zs, const float* E, const int32_t* idx, int64_t N, int K, int D,
-                 float* out, double* sse, int32_t* counts, float* dwr, cudaStream_t st) {
+                 float* out, double* sse, int32_t* counts, float* dwr, int dwr_replicas, cudaStream_t st) {
   const bool vec = (D % 4 == 0) && aligned16(x) && aligned16(E) && (!zs || aligned16(zs)) &&
                    (!out || aligned16(out)) && (!dwr || aligned16(dwr));
   const int use_hist = (counts && K <= 8192) ? 1 : 0;
   const size_t smem = use_hist ? (size_t)K * sizeof(int) : 0;
   const int grid = grid_for(N, APPLY_WARPS, 8);
   if (vec)
-    apply_kernel<true><<<grid, APPLY_WARPS * 32, smem, st>>>(x, zs, E, idx, N, K, D, out, sse, counts, dwr, use_hist);
+    apply_kernel<true><<<grid, APPLY_WARPS * 32, smem, st>>>(x, zs, E, idx, N, K, D, out, sse, counts, dwr, dwr_replicas, use_hist);
   else
-    apply_kernel<false><<<grid, APPLY_WARPS * 32, smem, st>>>(x, zs, E, idx, N, K, D, out, sse, counts, dwr, use_hist);
+    apply_kernel<false><<<grid, APPLY_WARPS * 32, smem, st>>>(x, zs, E, idx, N, K, D, out, sse, counts, dwr, dwr_replicas, use_hist);
   G2V_LAUNCH_CHECK("apply_kernel");
   return G2V_OK;
 }
 
-int launch_stats_pack(const int32_t* counts, const double* sse, int64_t N, int K, int D, float* packed,
-                      cudaStream_t st) {
-  stats_pack_kernel<<<(K + 2 + 255) / 256, 256, 0, st>>>(counts, sse, N, K, D, packed);
+int launch_stats_pack(const int32_t* counts, const double* sse, const float* dwr, int dwr_replicas, int64_t N,
+                      int K, int D, float* packed, cudaStream_t st) {
+  stats_pack_kernel<<<grid_for((long long)K * D + K + 2, 256, 8), 256, 0, st>>>(counts, sse, dwr, dwr ? dwr_replicas : 0, N,
+                                                                                 K, D, packed);
   G2V_LAUNCH_CHECK("stats_pack_kernel");
   return G2V_OK;
 }

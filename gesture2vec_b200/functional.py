@@ -116,17 +116,22 @@ def vq_apply(x: torch.Tensor, E: torch.Tensor, idx: torch.Tensor, *, zs: Optiona
     st = _stream(dev)
     out = torch.empty_like(x) if want_out else None
     packed = None
-    counts = sse = None
+    counts = sse = dwr = None
+    reps = 0
     if want_stats:
-        packed = torch.zeros(packed_numel(K, D), dtype=torch.float32, device=dev) if want_dwr else \
-            torch.empty(packed_numel(K, D), dtype=torch.float32, device=dev)
+        packed = torch.empty(packed_numel(K, D), dtype=torch.float32, device=dev)
         acc = torch.zeros(K * 4 + 8, dtype=torch.uint8, device=dev)   # int32 counts[K] + double sse
         sse = acc[:8].view(torch.float64)
         counts = acc[8:].view(torch.int32)
+        if want_dwr:
+            # private copies of the [K, D] sums keep hot codes from serialising the fp32 atomics;
+            # large batches get up to 8 copies (bounded to 64 MB), small ones a single copy
+            reps = 1 if N < 32768 else max(1, min(8, (64 << 20) // (K * D * 4)))
+            dwr = torch.zeros(reps * K * D, dtype=torch.float32, device=dev)
     _lib.check(lib.g2v_vq_apply(_ptr(x), _ptr(zs), _ptr(E), _ptr(idx), N, K, D, _ptr(out), _ptr(sse),
-                                _ptr(counts), _ptr(packed) if want_dwr else None, st), "g2v_vq_apply")
+                                _ptr(counts), _ptr(dwr), reps, st), "g2v_vq_apply")
     if want_stats:
-        _lib.check(lib.g2v_vq_stats_pack(_ptr(counts), _ptr(sse), N, K, D, _ptr(packed), st),
+        _lib.check(lib.g2v_vq_stats_pack(_ptr(counts), _ptr(sse), _ptr(dwr), reps, N, K, D, _ptr(packed), st),
                    "g2v_vq_stats_pack")
     return out, packed
 

@@ -106,17 +106,19 @@ int g2v_vq_search(const void* z, int z_dtype, const float* E, const void* cb,
  *   out     optional [N,D]: x + (E[idx] - x)
  *   sse     optional double[1], accumulated: sum (E[idx]-x)^2
  *   counts  optional int32[K], accumulated: rows per code
- *   dwr     optional fp32 [K,D], accumulated: sum_{n: idx=k} (zs_n - e_k)  (the EMA sum
- *           encodings^T @ flat_input minus counts*E; residual form keeps grad_E accurate) */
+ *   dwr     optional fp32 [dwr_replicas, K, D], accumulated: sum_{n: idx=k} (zs_n - e_k)  (the
+ *           EMA sum encodings^T @ flat_input minus counts*E; residual form keeps grad_E accurate).
+ *           dwr_replicas >= 1 independent copies spread the atomic traffic of hot codes (thread
+ *           blocks round-robin over them); g2v_vq_stats_pack sums the copies. */
 int g2v_vq_apply(const float* x, const float* zs, const float* E, const int32_t* idx,
                  int64_t N, int K, int D, float* out, double* sse, int32_t* counts,
-                 float* dwr, void* stream);
+                 float* dwr, int dwr_replicas, void* stream);
 
 /* Pack the per-step statistics into ONE fp32 buffer for the data-parallel all-reduce:
- * packed = [ dwr (K*D) | counts (K) | sse (1) | rows (1) ], K*D+K+2 floats.  dwr is
- * expected to already live at packed[0 .. K*D) (pass that pointer to g2v_vq_apply). */
-int g2v_vq_stats_pack(const int32_t* counts, const double* sse, int64_t N, int K, int D,
-                      float* packed, void* stream);
+ * packed = [ dwr (K*D) | counts (K) | sse (1) | rows (1) ], K*D+K+2 floats.  The dwr_replicas
+ * copies written by g2v_vq_apply are summed into packed[0 .. K*D) (dwr may be NULL: zeros). */
+int g2v_vq_stats_pack(const int32_t* counts, const double* sse, const float* dwr, int dwr_replicas,
+                      int64_t N, int K, int D, float* packed, void* stream);
 
 /* mse = sse/(rows*D); loss = coef_codebook*mse + coef_commit*mse; perplexity =
  * exp(-sum p log(p+1e-10)), p = counts/rows -- from a (possibly all-reduced) packed buffer.

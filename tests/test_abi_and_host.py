@@ -56,9 +56,9 @@ def test_size_queries_and_validation_without_gpu(lib):
     assert lib.g2v_search_path(0, 40, 0) == -1
     # null / bad arguments are rejected before any CUDA call
     assert lib.g2v_vq_search(None, 0, None, None, 10, 4, 4, None, None, None, 0, 0, None) == -1
-    assert lib.g2v_vq_apply(None, None, None, None, 10, 4, 4, None, None, None, None, None) == -1
+    assert lib.g2v_vq_apply(None, None, None, None, 10, 4, 4, None, None, None, None, 0, None) == -1
     assert lib.g2v_onehot(None, 5, 0, None, None) == -1
-    assert lib.g2v_vq_stats_pack(None, None, 1, 4, 4, None, None) == -1
+    assert lib.g2v_vq_stats_pack(None, None, None, 0, 1, 4, 4, None, None) == -1
     assert lib.g2v_tokenize_host_bytes(0, 4, 4, 0, 0) == 0
 
 
