@@ -394,8 +394,10 @@ TRAFFIC_NOTE = {}
 
 def launches_estimate(a, path):
     """Kernels of ours launched per step (counted from the launch sites in csrc/)."""
-    # simt: fp32 sweep + re-rank; tc: row prep + tcgen05 sweep + pair re-rank + full-row re-rank
-    search = 2 if path.startswith("simt") else 4
+    # simt: fp32 sweep + per-row fp64 re-rank + batched re-rank (lists longer than 4096 rows)
+    # tc:   [row_prep unless fp32 rows and K <= 512] + tcgen05 sweep + candidate / chain / per-row / batched re-rank
+    fused = a.dtype == "f32" and a.codes <= 512
+    search = 3 if path.startswith("simt") else (5 if fused else 6)
     if a.workload == "tokenize":
         return search
     # train: search + apply + pack + finalize + ema(2) + codebook prep(3) + backward

@@ -44,6 +44,7 @@ def _worker(rank, world, port, out):
         b, e = g.shard_rows(N, rank, world)
         x = z[b:e].to(dev).requires_grad_(True)
         for _ in range(2):
+            x.grad = None
             loss, q, ppl, _ = layer(x)
             (loss + q.sum()).backward()
         torch.cuda.synchronize()
