@@ -477,13 +477,11 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     // =========================== B producer ===========================
     {   // whole warp walks the schedule (uniform control flow); one elected lane issues
-      uint32_t g = 0;  // global chunk counter
+      uint32_t s = 0, sph = 0;  // ring position and its phase (no division by the run-time ring depth in the loop)
       for (int tile = group; tile < P.n_row_tiles; tile += n_groups) {
         for (int nt = 0; nt < P.n_ntiles; ++nt) {
-          for (int c = 0; c < n_chunks; ++c, ++g) {
-            const int s = g % NST;
-            const uint32_t round = g / NST;
-            mbar_wait(bar_empty(s), (round & 1u) ^ 1u);
+          for (int c = 0; c < n_chunks; ++c) {
+            mbar_wait(bar_empty(s), sph ^ 1u);
             const bool full = c < n_full;
             // the last code tile only fetches the rows its MMA reads (n_last_mma <= 256); each CTA
             // of a pair fetches its 1/CG slice of the code rows
@@ -498,6 +496,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                               bar_full(s));
             }
             __syncwarp();
+            if (++s == NST) { s = 0; sph ^= 1u; }
           }
         }
       }
@@ -557,7 +556,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     if (leader) {                  // the leader CTA issues for the whole group; one elected lane per step
-      uint32_t g = 0, it = 0, ti = 0;
+      uint32_t s = 0, sph = 0, it = 0, ti = 0;
       for (int tile = group; tile < P.n_row_tiles; tile += n_groups, ++ti) {
         for (int nt = 0; nt < P.n_ntiles; ++nt, ++it) {
           const uint32_t as = it & 1u, around = it >> 1;
@@ -568,17 +567,13 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           TRACE(1, 200 + nt);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + as * TN;
-          for (int c = 0; c < n_chunks; ++c, ++g) {
-            const int s = g % NST;
-            const uint32_t round = g / NST;
+          for (int c = 0; c < n_chunks; ++c) {
             if (nt == 0) {
               if (FUSED && CG == 2) mbar_wait_cluster(bar_afull(c), ti & 1u);
               else mbar_wait(bar_afull(c), ti & 1u);
               if (FUSED) fence_proxy_async();
-              TRACE(1, 300 + c);
             }
-            mbar_wait(bar_full(s), round & 1u);
-            TRACE(1, 400 + c);
+            mbar_wait(bar_full(s), sph);
             tc_fence_after();
             const uint32_t a_addr = a_chunk_addr(c), b_addr = sB + (uint32_t)s * sp.b_stage;
             const bool fullp = c < n_full;
@@ -599,6 +594,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (c == n_chunks - 1) tc_commit<CG>(bar_accfull(as));
             }
             __syncwarp();
+            if (++s == NST) { s = 0; sph ^= 1u; }
           }
         }
       }
@@ -1304,6 +1300,410 @@ tc_resident_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------
+// "tmem" variant: fp32 rows -> fp16 A operand in tensor memory, CTA pairs, both operands streamed
+// ------------------------------------------------------------------------------------------
+// What bounds the fused shared-memory variant at K <= 512 is shared-memory bandwidth and the depth of
+// its fp32 staging ring (the fp16 A tile takes 100 KB).  Here the A operand lives in tensor memory
+// (tcgen05.st.16x256b, lane = row, 32-bit column = two K elements; tcgen05.mma reads it from there), so
+// shared memory only holds rings: >= 128 KB of fp32 row slots in flight per SM (HBM latency under load is
+// 1.5 - 3 us) and the codebook stages, of which each CTA of a pair (cta_group::2, M = 256) loads half.
+// TMEM columns: [0, Dp/2) A operand, then two accumulator stages of `ntile` codes.
+constexpr int TME_THREADS = 640;        // 4 control warps, 8 epilogue warps, 8 converter warps
+constexpr int TME_MAX_ZSLOTS = 10;
+constexpr int TME_ZCOLS = 32;           // fp32 columns per staging slot (128 bytes: one SWIZZLE_128B row)
+constexpr int TME_ZSLOT = TM * TME_ZCOLS * 4;   // 16384
+constexpr int TME_MAX_BST = 16;
+
+struct TmeParams {
+  long long N;
+  int K, D, Dp;
+  int n_full, n_tail, n_chunks;   // K panels of the A operand: 64 columns, then 16-column tails
+  int ntile, n_ntiles, n_last;    // codes per accumulator stage; code tiles; codes of the last tile (multiple of 16)
+  int acc_col0;                   // first accumulator column in TMEM
+  int n_row_tiles;                // tiles of 256 rows (128 per CTA)
+  int n_ksteps;
+  int Kpad;                       // (n_ntiles - 1) * ntile + n_last
+  int nb, nz;                     // codebook stages / fp32 row slots
+  uint32_t b_stage;               // bytes of one codebook stage in one CTA
+  const CbHeader* hdr;
+  const float* ntab;
+  const float* e2;
+  int* idx;
+  int* pair_list;
+  int* full_list;
+  int* chain_list;
+  int* counters;
+  long long* trace;
+  unsigned flags;
+};
+
+struct TmePlan {
+  uint32_t b_off, z_off, e2_off, xch_off, rs_off, bar_off, tmem_off, total;
+};
+constexpr int TME_NBARS = 2 * TME_MAX_BST + 2 * TME_MAX_ZSLOTS + 3 * MAX_CHUNKS + 4 + RS_RING;
+__host__ __device__ inline TmePlan tme_plan(int nb, uint32_t b_stage, int nz, int Kpad) {
+  TmePlan p;
+  p.b_off = 0;
+  p.z_off = (uint32_t)nb * b_stage;
+  p.e2_off = p.z_off + (uint32_t)nz * TME_ZSLOT;
+  p.xch_off = p.e2_off + (((uint32_t)Kpad * 4u + 127u) & ~127u);
+  p.rs_off = p.xch_off + TM * 12 * 4;
+  p.bar_off = p.rs_off + RS_RING * TM * 8;
+  p.tmem_off = p.bar_off + 8 * TME_NBARS;
+  p.total = p.tmem_off + 16;
+  return p;
+}
+
+__global__ void __launch_bounds__(TME_THREADS, 1)
+tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmZt,
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBt,
+               const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmBlt, const TmeParams P) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t raw = smem_u32(smem_dyn);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  unsigned char* gbase = smem_dyn + (base - raw);
+  const TmePlan sp = tme_plan(P.nb, P.b_stage, P.nz, P.Kpad);
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int n_groups = gridDim.x / 2, group = blockIdx.x / 2;
+  const uint32_t NB = (uint32_t)P.nb, NZ = (uint32_t)P.nz;
+
+  const uint32_t sB = base + sp.b_off, sZ = base + sp.z_off;
+  float* e2s = reinterpret_cast<float*>(gbase + sp.e2_off);
+  uint32_t* xch = reinterpret_cast<uint32_t*>(gbase + sp.xch_off);
+  float2* rowstat = reinterpret_cast<float2*>(gbase + sp.rs_off);
+  const uint32_t bars = base + sp.bar_off;
+  auto bar_bfull = [&](int s) { return bars + 8u * s; };
+  auto bar_bempty = [&](int s) { return bars + 8u * (TME_MAX_BST + s); };
+  auto bar_zfull = [&](int s) { return bars + 8u * (2 * TME_MAX_BST + s); };
+  auto bar_zempty = [&](int s) { return bars + 8u * (2 * TME_MAX_BST + TME_MAX_ZSLOTS + s); };
+  constexpr int A0 = 2 * TME_MAX_BST + 2 * TME_MAX_ZSLOTS;
+  auto bar_aconv = [&](int c) { return bars + 8u * (A0 + c); };                      // this CTA's converters wrote panel c
+  auto bar_apeer = [&](int c) { return bars + 8u * (A0 + MAX_CHUNKS + c); };         // leader: the peer's converters did
+  auto bar_aempty = [&](int c) { return bars + 8u * (A0 + 2 * MAX_CHUNKS + c); };    // the MMAs finished reading panel c
+  auto bar_accfull = [&](int a) { return bars + 8u * (A0 + 3 * MAX_CHUNKS + a); };
+  auto bar_accempty = [&](int a) { return bars + 8u * (A0 + 3 * MAX_CHUNKS + 2 + a); };
+  auto bar_rsfull = [&](int s) { return bars + 8u * (A0 + 3 * MAX_CHUNKS + 4 + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + sp.tmem_off);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_chunks = P.n_chunks, n_full = P.n_full;
+  const uint32_t acc_col[2] = {(uint32_t)P.acc_col0, (uint32_t)(P.acc_col0 + P.ntile)};
+  const int n_sc = (n_full + 1) >> 1;      // super-chunks (codebook stages / A hand-overs) per code tile
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TME_MAX_BST; ++s) { mbar_init(bar_bfull(s), 1); mbar_init(bar_bempty(s), 1); }
+    for (int s = 0; s < TME_MAX_ZSLOTS; ++s) { mbar_init(bar_zfull(s), 1); mbar_init(bar_zempty(s), RES_CONV_WARPS); }
+    for (int c = 0; c < MAX_CHUNKS; ++c) { mbar_init(bar_aconv(c), RES_CONV_WARPS); mbar_init(bar_apeer(c), 1); mbar_init(bar_aempty(c), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_accfull(a), 1); mbar_init(bar_accempty(a), 16); }
+    for (int s = 0; s < RS_RING; ++s) mbar_init(bar_rsfull(s), RES_CONV_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < P.Kpad; i += TME_THREADS) e2s[i] = (i < P.K) ? __ldg(P.e2 + i) : 0.f;
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  int trace_n = 0;
+  auto TRACE = [&](int role, int tag) {   // role 0 B producer, 1 MMA, 2 row producer, 3 epilogue warp 4, 4 converter warp 12
+    if (P.trace && blockIdx.x == 0 && lane == 0 && trace_n < 512) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      P.trace[(role * 512 + trace_n) * 2] = tag;
+      P.trace[(role * 512 + trace_n) * 2 + 1] = t;
+      ++trace_n;
+    }
+  };
+
+  if (warp == 0) {
+    // =========================== codebook producer (each CTA fetches its half of every stage) ===========================
+    // a stage = one "super-chunk" of a code tile: two 64-column panels, the last one also the 16-column tails
+    uint32_t s = 0, sph = 0;     // ring position and its phase
+    for (int tile = group; tile < P.n_row_tiles; tile += n_groups) {
+      for (int nt = 0; nt < P.n_ntiles; ++nt) {
+        const bool last = (nt == P.n_ntiles - 1);
+        const uint32_t rows = (uint32_t)(last ? P.n_last : P.ntile);        // codes of the tile; this CTA fetches half
+        const int row = nt * P.ntile + (int)(cta_rank * (rows / 2));
+        for (int sc = 0; sc < n_sc; ++sc) {
+          mbar_wait(bar_bempty(s), sph ^ 1u);
+          const int p0 = 2 * sc, np = min(2, n_full - p0);
+          const int nt_here = (sc == n_sc - 1) ? P.n_tail : 0;
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(bar_bfull(s), rows * (uint32_t)(np * KC + nt_here * KT) * 2u);   // bytes of both CTAs
+            uint32_t dst = sB + s * P.b_stage;
+            for (int k = 0; k < np; ++k, dst += (rows / 2) * 128u)
+              tma_load_2d<2>(dst, last ? &tmBl : &tmB, (p0 + k) * KC, row, bar_bfull(s));
+            for (int t = 0; t < nt_here; ++t, dst += (rows / 2) * 32u)
+              tma_load_2d<2>(dst, last ? &tmBlt : &tmBt, n_full * KC + t * KT, row, bar_bfull(s));
+          }
+          __syncwarp();
+          if (++s == NB) { s = 0; sph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // =========================== MMA issuer ===========================
+      uint32_t s = 0, sph = 0, it = 0, ti = 0;
+      const bool skip_mma = (P.flags & kDbgSkipMma) != 0;
+      for (int tile = group; tile < P.n_row_tiles; tile += n_groups, ++ti) {
+        for (int nt = 0; nt < P.n_ntiles; ++nt, ++it) {
+          const uint32_t as = it & 1u, around = it >> 1;
+          const bool last_nt = (nt == P.n_ntiles - 1);
+          const uint32_t idesc = umma_idesc(2 * TM, last_nt ? P.n_last : P.ntile);
+          TRACE(1, 100 + nt);
+          mbar_wait(bar_accempty(as), (around & 1u) ^ 1u);
+          TRACE(1, 200 + nt);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc_col[as];
+          const uint32_t rows_b = (uint32_t)(last_nt ? P.n_last : P.ntile) / 2u;     // code rows per CTA in a stage
+          for (int sc = 0; sc < n_sc; ++sc) {
+            if (nt == 0) {
+              mbar_wait(bar_aconv(sc), ti & 1u);
+              mbar_wait_cluster(bar_apeer(sc), ti & 1u);
+            }
+            mbar_wait(bar_bfull(s), sph);
+            tc_fence_after();
+            const int p0 = 2 * sc, np = min(2, n_full - p0);
+            const bool tails = (sc == n_sc - 1);
+            const uint32_t b_addr = sB + s * P.b_stage;
+            if (elect_one()) {
+              if (!skip_mma) {
+                for (int k = 0; k < np; ++k) {
+                  const uint64_t bd0 = umma_desc(b_addr + (uint32_t)k * rows_b * 128u, 1024, 2);
+                  const uint32_t a_tmem = tmem_base + 32u * (uint32_t)(p0 + k);
+#pragma unroll
+                  for (int kk = 0; kk < KC / KT; ++kk)
+                    tc_mma_f16_ts2(d_tmem, a_tmem + 8u * kk, bd0 + 2u * kk, idesc, (sc | k | kk) != 0);
+                }
+                if (tails)
+                  for (int t = 0; t < P.n_tail; ++t)
+                    tc_mma_f16_ts2(d_tmem, tmem_base + 32u * n_full + 8u * t,
+                                   umma_desc(b_addr + (uint32_t)np * rows_b * 128u + (uint32_t)t * rows_b * 32u, 256, 6), idesc, 1u);
+              }
+              tc_commit<2>(bar_bempty(s));
+              if (last_nt) tc_commit<2>(bar_aempty(sc));
+              if (tails) tc_commit<2>(bar_accfull(as));
+            }
+            __syncwarp();
+            if (++s == NB) { s = 0; sph ^= 1u; }
+          }
+        }
+      }
+    } else {
+      // =========================== peer: forward "panel written" to the leader ===========================
+      uint32_t ti = 0;
+      for (int tile = group; tile < P.n_row_tiles; tile += n_groups, ++ti) {
+        for (int sc = 0; sc < n_sc; ++sc) {
+          mbar_wait(bar_aconv(sc), ti & 1u);
+          if (elect_one()) mbar_arrive_cluster(bar_apeer(sc), 0);
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // =========================== row producer: fp32 slots of 128 rows x 32 columns ===========================
+    uint32_t slot = 0, ph = 0;
+    for (int tile = group; tile < P.n_row_tiles; tile += n_groups) {
+      const long long r0 = ((long long)tile * 2 + cta_rank) * TM;
+      const int row0 = (int)(r0 < P.N ? r0 : P.N - 1);       // a tile past the end reads (and ignores) the last row
+      const int n_slots = 2 * n_full + P.n_tail;
+      for (int u = 0; u < n_slots; ++u) {
+        mbar_wait(bar_zempty(slot), ph ^ 1u);
+        TRACE(2, u);
+        if (P.flags & kDbgNoZ) {
+          if (elect_one()) mbar_arrive(bar_zfull(slot));
+        } else if (elect_one()) {
+          if (u < 2 * n_full) {
+            mbar_expect_tx(bar_zfull(slot), TME_ZSLOT);
+            tma_load_2d<1>(sZ + slot * TME_ZSLOT, &tmZ, u * TME_ZCOLS, row0, bar_zfull(slot));
+          } else {
+            mbar_expect_tx(bar_zfull(slot), TM * KT * 4);
+            tma_load_2d<1>(sZ + slot * TME_ZSLOT, &tmZt, n_full * KC + (u - 2 * n_full) * KT, row0, bar_zfull(slot));
+          }
+        }
+        __syncwarp();
+        if (++slot == NZ) { slot = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp >= EPI_WARP0 && warp < RES_CONV_WARP0) {
+    // =========================== epilogue ===========================
+    // as in tc_search_kernel; a warp's 16-column pieces are the codes [32 g + 16 eh, +16) inside the tile
+    const int q = warp & 3;
+    const int eh = (warp - EPI_WARP0) >> 2;
+    const int r = q * 32 + lane;
+    uint32_t* xrow = xch + (size_t)r * 12;
+    uint32_t it = 0, ti = 0;
+    const float h_sfrac = P.hdr->sfrac, h_e2min = P.hdr->e2min, h_scale_e = P.hdr->scale_e;
+    for (int tile = group; tile < P.n_row_tiles; tile += n_groups, ++ti) {
+      const long long row = ((long long)tile * 2 + cta_rank) * TM + r;
+      const bool valid = row < P.N;
+      mbar_wait(bar_rsfull(ti % RS_RING), (ti / RS_RING) & 1u);
+      const float2 st = rowstat[(ti % RS_RING) * TM + r];
+      const RowInfo ri = make_rowinfo(st.x, st.y, 1.f, h_sfrac, h_e2min, h_scale_e, P.n_ksteps);
+      uint32_t m1[16], m2[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { m1[j] = 0xFFFFFFFFu; m2[j] = 0xFFFFFFFFu; }
+
+      for (int nt = 0; nt < P.n_ntiles; ++nt, ++it) {
+        const uint32_t as = it & 1u, around = it >> 1;
+        const int s0 = nt * P.ntile;
+        const int e_valid = min(s0 + ((nt == P.n_ntiles - 1) ? P.n_last : P.ntile), P.K);
+        const int g0 = (s0 - 16 * eh + 31) >> 5, g1 = (e_valid - 16 * eh + 31) >> 5;     // pieces g0 .. g1-1
+        if (warp == EPI_WARP0) TRACE(3, 100 + nt);
+        mbar_wait(bar_accfull(as), around & 1u);
+        if (warp == EPI_WARP0) TRACE(3, 200 + nt);
+        tc_fence_after();
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col[as] + (uint32_t)(16 * eh - s0);
+        uint32_t va[16], vb[16];
+        if (g0 < g1) tc_ld16(taddr0 + 32u * g0, va);
+        for (int g = g0; g < g1; g += 2) {
+          tc_wait_ld();
+          if (g + 1 < g1) tc_ld16(taddr0 + 32u * (g + 1), vb);
+          if (!(P.flags & kDbgSkipEpi)) {
+            const int cb0 = 32 * g + 16 * eh, nv = e_valid - cb0;
+            if (nv >= 16) epi_chunk<false>(va, e2s + cb0, ri.cS, ri.S, (uint32_t)g, 16, m1, m2);
+            else epi_chunk<true>(va, e2s + cb0, ri.cS, ri.S, (uint32_t)g, nv, m1, m2);
+          }
+          if (g + 1 < g1) {
+            tc_wait_ld();
+            if (g + 2 < g1) tc_ld16(taddr0 + 32u * (g + 2), va);
+            if (!(P.flags & kDbgSkipEpi)) {
+              const int cb0 = 32 * (g + 1) + 16 * eh, nv = e_valid - cb0;
+              if (nv >= 16) epi_chunk<false>(vb, e2s + cb0, ri.cS, ri.S, (uint32_t)(g + 1), 16, m1, m2);
+              else epi_chunk<true>(vb, e2s + cb0, ri.cS, ri.S, (uint32_t)(g + 1), nv, m1, m2);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (warp == EPI_WARP0) TRACE(3, 300 + nt);
+        if (lane == 0) {
+          if (leader) mbar_arrive(bar_accempty(as));
+          else mbar_arrive_cluster(bar_accempty(as), 0);
+        }
+      }
+
+      const Cand none{0xFFFFFFFFu, 0xFFFFFFFFu, 0};
+      Cand c1 = none, c2 = none, c3 = none;
+      uint32_t k4 = 0xFFFFFFFFu;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) cand_insert(c1, c2, c3, k4, Cand{m1[j], m2[j], eh * 16 + j});
+      if (eh == 1) {
+        xrow[0] = c1.key; xrow[1] = c1.key2; xrow[2] = (uint32_t)c1.j;
+        xrow[3] = c2.key; xrow[4] = c2.key2; xrow[5] = (uint32_t)c2.j;
+        xrow[6] = c3.key; xrow[7] = c3.key2; xrow[8] = (uint32_t)c3.j;
+        xrow[9] = k4;
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+      if (eh == 0) {
+        cand_insert(c1, c2, c3, k4, Cand{xrow[0], xrow[1], (int)xrow[2]});
+        cand_insert(c1, c2, c3, k4, Cand{xrow[3], xrow[4], (int)xrow[5]});
+        cand_insert(c1, c2, c3, k4, Cand{xrow[6], xrow[7], (int)xrow[8]});
+        k4 = min(k4, xrow[9]);
+        finish_row(c1, c2, c3, k4, ri, row, valid, P.K, P.ntab, P.flags, P.idx, P.pair_list, P.chain_list, P.full_list, P.counters);
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+    }
+  } else if (warp >= RES_CONV_WARP0) {
+    // =========================== converters ===========================
+    // warp cw owns the 16 TMEM lanes (rows) 32 (cw % 4) + 16 (cw / 4) ...; in the 16x256b store pattern
+    // lane i holds, per K step of 16, the elements 4 (i % 4) .. +3 of the rows i / 4 and i / 4 + 8.
+    // A slot row is 128 bytes (32 fp32) with the 16-byte chunks XOR-swizzled by row % 8, so the eight rows
+    // a quarter-warp reads hit all banks.
+    const int cw = warp - RES_CONV_WARP0;
+    const int lane0_row = 32 * (cw & 3) + 16 * (cw >> 2);
+    const int ra_l = lane0_row + (lane >> 2), rb_l = ra_l + 8;
+    const uint32_t t_lane = tmem_base + ((uint32_t)lane0_row << 16);
+    const uint32_t kq = (uint32_t)(lane & 3), sw = (uint32_t)(ra_l & 7);            // (rb_l & 7) == (ra_l & 7)
+    const uint32_t off_a0 = (uint32_t)ra_l * 128u + ((kq ^ sw) << 4), off_a1 = (uint32_t)ra_l * 128u + (((4u + kq) ^ sw) << 4);
+    const uint32_t off_t = (uint32_t)ra_l * 64u + kq * 16u;                        // tail slot: 64-byte rows, no swizzle
+    float z2a = 0.f, r2a = 0.f, z2b = 0.f, r2b = 0.f;
+    auto cvt = [&](const float4 v, float& z2, float& r2, uint32_t& w0, uint32_t& w1) {
+      const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+      const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+      const float e0 = v.x - f01.x, e1 = v.y - f01.y, e2r = v.z - f23.x, e3 = v.w - f23.y;
+      z2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, z2))));
+      r2 = fmaf(e0, e0, fmaf(e1, e1, fmaf(e2r, e2r, fmaf(e3, e3, r2))));
+      w0 = *reinterpret_cast<const uint32_t*>(&h01);
+      w1 = *reinterpret_cast<const uint32_t*>(&h23);
+    };
+    uint32_t slot = 0, ph = 0, ti = 0;
+    for (int tile = group; tile < P.n_row_tiles; tile += n_groups, ++ti) {
+      for (int c = 0; c < n_chunks; ++c) {
+        // barriers work on super-chunks: panels 2 sc and 2 sc + 1, the tails belong to the last one
+        const int sc = min(c >> 1, n_sc - 1);
+        const bool sc_first = (c < n_full) && ((c & 1) == 0);
+        const bool sc_last = (c == n_chunks - 1) || (c < n_full - 1 && (c & 1) == 1) || (c == n_full - 1 && sc < n_sc - 1);
+        if (sc_first) {
+          if (cw == 0) TRACE(4, 100 + sc);
+          mbar_wait(bar_aempty(sc), (ti & 1u) ^ 1u);       // the MMAs of the previous row tile have read these panels
+          if (cw == 0) TRACE(4, 200 + sc);
+          tc_fence_after();
+        }
+        if (c < n_full) {
+          uint32_t w[16];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(bar_zfull(slot), ph);
+            const unsigned char* zs = gbase + sp.z_off + slot * TME_ZSLOT;
+            const float4 a0 = *reinterpret_cast<const float4*>(zs + off_a0), b0 = *reinterpret_cast<const float4*>(zs + off_a0 + 8 * 128);
+            const float4 a1 = *reinterpret_cast<const float4*>(zs + off_a1), b1 = *reinterpret_cast<const float4*>(zs + off_a1 + 8 * 128);
+            cvt(a0, z2a, r2a, w[8 * h + 0], w[8 * h + 1]);
+            cvt(b0, z2b, r2b, w[8 * h + 2], w[8 * h + 3]);
+            cvt(a1, z2a, r2a, w[8 * h + 4], w[8 * h + 5]);
+            cvt(b1, z2b, r2b, w[8 * h + 6], w[8 * h + 7]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_zempty(slot));
+            if (++slot == NZ) { slot = 0; ph ^= 1u; }
+          }
+          tc_st_16x256b_x4(t_lane + 32u * c, w);
+        } else {
+          mbar_wait(bar_zfull(slot), ph);
+          const unsigned char* zs = gbase + sp.z_off + slot * TME_ZSLOT;
+          const float4 a0 = *reinterpret_cast<const float4*>(zs + off_t), b0 = *reinterpret_cast<const float4*>(zs + off_t + 8 * 64);
+          uint32_t w0, w1, w2, w3;
+          cvt(a0, z2a, r2a, w0, w1);
+          cvt(b0, z2b, r2b, w2, w3);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_zempty(slot));
+          if (++slot == NZ) { slot = 0; ph ^= 1u; }
+          tc_st_16x256b_x1(t_lane + 32u * n_full + 8u * (c - n_full), w0, w1, w2, w3);
+        }
+        if (sc_last) {
+          if (cw == 0) TRACE(4, 300 + sc);
+          tc_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_aconv(sc));
+        }
+      }
+      // row statistics of the finished tile: sum over the four lanes that share a row
+      z2a += __shfl_xor_sync(0xffffffffu, z2a, 1); r2a += __shfl_xor_sync(0xffffffffu, r2a, 1);
+      z2b += __shfl_xor_sync(0xffffffffu, z2b, 1); r2b += __shfl_xor_sync(0xffffffffu, r2b, 1);
+      z2a += __shfl_xor_sync(0xffffffffu, z2a, 2); r2a += __shfl_xor_sync(0xffffffffu, r2a, 2);
+      z2b += __shfl_xor_sync(0xffffffffu, z2b, 2); r2b += __shfl_xor_sync(0xffffffffu, r2b, 2);
+      if ((lane & 3) == 0) {
+        rowstat[(ti % RS_RING) * TM + ra_l] = make_float2(z2a, r2a);
+        rowstat[(ti % RS_RING) * TM + rb_l] = make_float2(z2b, r2b);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_rsfull(ti % RS_RING));
+      z2a = r2a = z2b = r2b = 0.f;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
 // row preparation: fp16 operand rows + per-row constants
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float ld_f32(const float* p) { return __ldg(p); }
@@ -1620,6 +2020,72 @@ int launch_resident(ResParams& R, const __half* e16, int Kp, cudaStream_t st) {
   return G2V_OK;
 }
 
+// "tmem" variant: geometry, or false if the shape does not qualify (fp32 rows read through TMA: D % 4 == 0
+// and a 16-byte aligned base; more than one 128-row tile so that a CTA pair has work).
+bool plan_tmem(const void* z, int z_dtype, int64_t N, int K, int D, TmeParams* R) {
+  const int Dp = round_up(D, 16);
+  if (z_dtype != G2V_F32 || D % 4 != 0 || (reinterpret_cast<uintptr_t>(z) & 15) != 0) return false;
+  if (N <= TM || Dp > kMaxDp || Dp < KC) return false;
+  const int acc_col0 = round_up(Dp / 2, 16);
+  const int nt_max = std::min(256, ((512 - acc_col0) / 2) & ~15);
+  int best_nt = 0, best_n = 1 << 30, best_pad = 1 << 30, best_last = 0;
+  for (int nt = nt_max; nt >= 32 && nt >= nt_max - 64; nt -= 16) {
+    const int n = (K + nt - 1) / nt;
+    const int last = round_up(K - (n - 1) * nt, 16);
+    if (last > nt) continue;
+    const int pad = (n - 1) * nt + last;
+    if (n < best_n || (n == best_n && pad < best_pad)) { best_nt = nt; best_n = n; best_pad = pad; best_last = last; }
+  }
+  if (best_nt == 0) return false;
+  R->N = N; R->K = K; R->D = D; R->Dp = Dp;
+  R->n_full = Dp / KC; R->n_tail = (Dp % KC) / KT; R->n_chunks = R->n_full + R->n_tail;
+  if (R->n_chunks > MAX_CHUNKS) return false;
+  R->ntile = best_nt; R->n_ntiles = best_n; R->n_last = best_last; R->Kpad = best_pad;
+  R->acc_col0 = acc_col0;
+  R->n_ksteps = Dp / KT;
+  R->b_stage = (uint32_t)round_up((best_nt / 2) * (std::min(2, R->n_full) * KC + R->n_tail * KT) * 2, 1024);
+  R->n_row_tiles = (int)((N + 2 * TM - 1) / (2 * TM));
+  // codebook ring: ~1.5 us of L2 latency at 288 MMA cycles per full panel; the rest goes to the row slots
+  int nb = 5;
+  if (const char* env = getenv("G2V_TC_BSTAGES")) nb = std::max(2, std::min(TME_MAX_BST, atoi(env)));
+  int nz = TME_MAX_ZSLOTS;
+  if (const char* env = getenv("G2V_TC_ZSLOTS")) nz = std::max(2, std::min(TME_MAX_ZSLOTS, atoi(env)));
+  while (nz > 2 && tme_plan(nb, R->b_stage, nz, R->Kpad).total + 1024 > 227 * 1024) --nz;
+  R->nb = nb; R->nz = nz;
+  return tme_plan(nb, R->b_stage, nz, R->Kpad).total + 1024 <= 227 * 1024;
+}
+
+int launch_tmem(TmeParams& R, const float* z, const __half* e16, int Kp, cudaStream_t st) {
+  alignas(64) CUtensorMap tmZ, tmZt, tmB, tmBt, tmBl, tmBlt;
+  int rc;
+  if ((rc = make_map(&tmZ, z, (uint64_t)R.N, (uint64_t)R.D, TME_ZCOLS, TM, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
+  if ((rc = make_map(&tmZt, z, (uint64_t)R.N, (uint64_t)R.D, KT, TM, CU_TENSOR_MAP_SWIZZLE_NONE, true))) return rc;
+  const uint32_t brow = (uint32_t)R.ntile / 2, blast = (uint32_t)R.n_last / 2;
+  if ((rc = make_map(&tmB, e16, (uint64_t)Kp, (uint64_t)R.Dp, KC, brow, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map(&tmBt, e16, (uint64_t)Kp, (uint64_t)R.Dp, KT, brow, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  if ((rc = make_map(&tmBl, e16, (uint64_t)Kp, (uint64_t)R.Dp, KC, blast, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map(&tmBlt, e16, (uint64_t)Kp, (uint64_t)R.Dp, KT, blast, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  const size_t smem = tme_plan(R.nb, R.b_stage, R.nz, R.Kpad).total + 1024;
+  G2V_CUDA_CHECK(cudaFuncSetAttribute(tc_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int max_groups = num_sms() / 2;
+  const int groups = R.n_row_tiles < max_groups ? R.n_row_tiles : max_groups;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(groups * 2);
+  cfg.blockDim = dim3(TME_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  G2V_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_tmem_kernel, tmZ, tmZt, tmB, tmBt, tmBl, tmBlt, R));
+  G2V_LAUNCH_CHECK("tc_tmem_kernel");
+  return G2V_OK;
+}
+
 template <typename ZT>
 int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, int K, int D, int32_t* idx,
            unsigned long long* stats, void* ws, unsigned flags, cudaStream_t st) {
@@ -1636,6 +2102,28 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
   const float* e2 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_e2_offset());
   const __half* e16 = reinterpret_cast<const __half*>(reinterpret_cast<const char*>(cb) + cb_e16_offset(K));
 
+  {   // fp32 rows, few code tiles: A operand in tensor memory, CTA pairs (G2V_TC_TMEM=0 switches the variant off,
+      // =2 forces it for any K)
+    TmeParams R;
+    const char* env = getenv("G2V_TC_TMEM");
+    const int mode = env ? atoi(env) : 1;
+    if (mode != 0 && plan_tmem(z, z_dtype, N, K, D, &R) && (mode == 2 || R.n_ntiles <= 4)) {
+      R.hdr = hdr; R.e2 = e2; R.idx = idx;
+      R.ntab = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_tab_offset());
+      R.pair_list = pairs; R.full_list = fulls; R.chain_list = chains; R.counters = counters; R.flags = flags;
+      if (const char* dbg = getenv("G2V_TC_DEBUG")) R.flags |= ((unsigned)atoi(dbg) & 63u) << 8;
+      R.trace = nullptr;
+      if (const char* tr = getenv("G2V_TC_TRACE")) R.trace = reinterpret_cast<long long*>(strtoull(tr, nullptr, 0));
+      G2V_CUDA_CHECK(cudaMemsetAsync(counters, 0, 16, st));
+      cudaEvent_t pev0, pev1;
+      profile_take(&pev0, &pev1);
+      if (pev0) G2V_CUDA_CHECK(cudaEventRecord(pev0, st));
+      const int rc = launch_tmem(R, reinterpret_cast<const float*>(z), e16, Kp, st);
+      if (rc) return rc;
+      if (pev1) G2V_CUDA_CHECK(cudaEventRecord(pev1, st));
+      return run_recheck(z, z_dtype, E, cb, N, K, D, pairs, chains, fulls, counters, idx, stats, flags, st);
+    }
+  }
   {   // K * D small: codebook-resident CTA pairs.  Experimental (G2V_TC_RES=1): correct, but slower than the
       // fused streaming variant until its row stream is staged through shared memory
     ResParams R;
