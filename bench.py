@@ -368,7 +368,9 @@ def main():
         roof["peak_source"] = pk["src"] + (" (sustained bf16)" if roof["bound"] == "tensor" else " (copy)")
         roof["algorithmic_per_chunk"] = {"search_bytes": search_bytes_per_row, "step_bytes": bytes_per_row,
                                          "flops": flops_per_row}
-        roof["kernel"] = ("tc_search_kernel (tcgen05 sweep)" if not path.startswith("simt") else "search_simt_kernel")
+        roof["kernel"] = "search_simt_kernel" if path.startswith("simt") else (
+            "tc_tmem_kernel (tcgen05 sweep, fp32 rows -> TMEM operand)" if tmem_variant(a.dtype, N, K, D)
+            else "tc_search_kernel (tcgen05 sweep)")
         roof["kernel_ms_per_launch"] = kernel_ms
         roof["kernel_share_of_step"] = kernel_ms / ms_step
         out = {
@@ -392,11 +394,21 @@ def main():
 TRAFFIC_NOTE = {}
 
 
+def tmem_variant(dtype, N, K, D):
+    """Mirror of plan_tmem() in csrc/g2v_tc.cu: fp32 rows and at most four code tiles."""
+    if dtype != "f32" or D % 4 or N <= 128 or D < 64:
+        return False
+    dp = (D + 15) // 16 * 16
+    acc0 = (dp // 2 + 15) // 16 * 16
+    nt_max = min(256, ((512 - acc0) // 2) & ~15)
+    return nt_max >= 32 and -(-K // nt_max) <= 4
+
+
 def launches_estimate(a, path):
     """Kernels of ours launched per step (counted from the launch sites in csrc/)."""
     # simt: fp32 sweep + per-row fp64 re-rank + batched re-rank (lists longer than 4096 rows)
     # tc:   [row_prep unless fp32 rows and K <= 512] + tcgen05 sweep + candidate / chain / per-row / batched re-rank
-    fused = a.dtype == "f32" and a.codes <= 512
+    fused = a.dtype == "f32" and (a.codes <= 512 or tmem_variant(a.dtype, a.rows, a.codes, 400))
     search = 3 if path.startswith("simt") else (5 if fused else 6)
     if a.workload == "tokenize":
         return search

@@ -88,10 +88,13 @@ int launch_codebook_prepare(const float* E, int K, int D, void* cb, cudaStream_t
 int launch_search_simt(const void* z, int z_dtype, const float* E, const void* cb, int64_t N, int K, int D,
                        int32_t* full_list, int32_t* full_count, int32_t* idx,
                        unsigned long long* stats, cudaStream_t st);
-// exact fp64 argmin of the rows in list[0 .. *count) (count <= max_rows)
+// exact fp64 argmin of the rows in list[0 .. *count) (count <= max_rows).  The first kFull64Cap listed rows
+// take a per-row fp64 kernel, the rest a batched fp32+fp64 kernel; overflow_only = the caller has already
+// handled the first kFull64Cap rows itself.
+constexpr int kFull64Cap = 4096;
 int launch_full_recheck(const void* z, int z_dtype, const float* E, const void* cb, int K, int D, const int32_t* list,
                         const int32_t* count, int64_t max_rows, int32_t* idx, unsigned long long* stats,
-                        cudaStream_t st);
+                        bool overflow_only, cudaStream_t st);
 int launch_apply(const float* x, const float* zs, const float* E, const int32_t* idx, int64_t N, int K,
                  int D, float* out, double* sse, int32_t* counts, float* dwr, int dwr_replicas, cudaStream_t st);
 int launch_stats_pack(const int32_t* counts, const double* sse, const float* dwr, int dwr_replicas, int64_t N,

@@ -753,7 +753,6 @@ int launch_codebook_prepare(const float* E, int K, int D, void* cb, cudaStream_t
 // Exact re-rank of a SMALL number of listed rows: one CTA per row, warps split the codes, lanes split
 // the dimensions (coalesced), straight fp64.  Used for the first kFull64Cap listed rows (the usual
 // case: a few hundred rows per million); anything beyond goes to the batched fp32+fp64 kernel above.
-constexpr int kFull64Cap = 4096;
 
 template <typename ZT>
 __global__ void __launch_bounds__(256) full64_kernel(const ZT* __restrict__ z, const float* __restrict__ E, int K, int D,
@@ -838,8 +837,10 @@ static int launch_full_recheck_v(const ZT* z, const float* E, const void* cb, in
 template <typename ZT>
 static int launch_full_recheck_t(const ZT* z, const float* E, const void* cb, int K, int D, const int32_t* list,
                                  const int32_t* count, int64_t max_rows, int32_t* idx,
-                                 unsigned long long* stats, cudaStream_t st) {
-  {
+                                 unsigned long long* stats, bool overflow_only, cudaStream_t st) {
+  if (overflow_only) {
+    if (max_rows <= kFull64Cap) return G2V_OK;
+  } else {
     const long long cap = max_rows < kFull64Cap ? max_rows : kFull64Cap;
     const long long lim = (long long)num_sms() * 8;
     const int g = (int)(cap < 1 ? 1 : (cap < lim ? cap : lim));
@@ -857,11 +858,11 @@ static int launch_full_recheck_t(const ZT* z, const float* E, const void* cb, in
 
 int launch_full_recheck(const void* z, int z_dtype, const float* E, const void* cb, int K, int D, const int32_t* list,
                         const int32_t* count, int64_t max_rows, int32_t* idx, unsigned long long* stats,
-                        cudaStream_t st) {
+                        bool overflow_only, cudaStream_t st) {
   switch (z_dtype) {
-    case G2V_F32: return launch_full_recheck_t(reinterpret_cast<const float*>(z), E, cb, K, D, list, count, max_rows, idx, stats, st);
-    case G2V_F16: return launch_full_recheck_t(reinterpret_cast<const __half*>(z), E, cb, K, D, list, count, max_rows, idx, stats, st);
-    case G2V_BF16: return launch_full_recheck_t(reinterpret_cast<const __nv_bfloat16*>(z), E, cb, K, D, list, count, max_rows, idx, stats, st);
+    case G2V_F32: return launch_full_recheck_t(reinterpret_cast<const float*>(z), E, cb, K, D, list, count, max_rows, idx, stats, overflow_only, st);
+    case G2V_F16: return launch_full_recheck_t(reinterpret_cast<const __half*>(z), E, cb, K, D, list, count, max_rows, idx, stats, overflow_only, st);
+    case G2V_BF16: return launch_full_recheck_t(reinterpret_cast<const __nv_bfloat16*>(z), E, cb, K, D, list, count, max_rows, idx, stats, overflow_only, st);
     default: return G2V_ERR_DTYPE;
   }
 }
@@ -891,7 +892,7 @@ static int launch_search_simt_t(const ZT* z, int z_dtype, const float* E, const 
   }
   G2V_LAUNCH_CHECK("search_simt_kernel");
   if (pev1) G2V_CUDA_CHECK(cudaEventRecord(pev1, st));
-  return launch_full_recheck_t(z, E, cb, K, D, full_list, full_count, N, idx, stats, st);
+  return launch_full_recheck_t(z, E, cb, K, D, full_list, full_count, N, idx, stats, false, st);
 }
 
 // fp32 search of all rows; `full_list` (N ints) and `full_count` (1 int) are scratch

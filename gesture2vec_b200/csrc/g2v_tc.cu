@@ -1757,12 +1757,9 @@ __global__ void __launch_bounds__(256) row_prep_kernel(const ZT* __restrict__ z,
 // exact re-rank of the two or three candidate codes of each listed row (one warp per entry, fp64);
 // all loads of an entry are issued before the first use.  Lowest index wins exact ties.
 template <typename ZT>
-__global__ void __launch_bounds__(256) pair_recheck_kernel(const ZT* __restrict__ z, const float* __restrict__ E,
-                                                           int D, const int* __restrict__ pair_list,
-                                                           const int* __restrict__ counters, int* __restrict__ idx,
-                                                           unsigned long long* stats) {
+__device__ __forceinline__ void pair_entries(const ZT* __restrict__ z, const float* __restrict__ E, int D,
+                                             const int* __restrict__ pair_list, int n, int* __restrict__ idx) {
   const int lane = threadIdx.x & 31;
-  const int n = counters[0];
   const int wstride = (gridDim.x * blockDim.x) >> 5;
   constexpr int U = 2;                                   // 2 x 128 columns per pass (registers -> occupancy)
   const bool vec = (D % 4 == 0) && sizeof(ZT) == 4;
@@ -1829,29 +1826,25 @@ __global__ void __launch_bounds__(256) pair_recheck_kernel(const ZT* __restrict_
       idx[row] = best;
     }
   }
-  if (stats && blockIdx.x == 0 && threadIdx.x == 0) {
-    atomicAdd(stats + G2V_STAT_PAIR_RECHECK, (unsigned long long)n);
-    atomicAdd(stats + G2V_STAT_FALLBACK_ROWS, (unsigned long long)counters[1]);
-  }
 }
 
 // exact re-rank over one chain (codes j, j+32, ... < K) plus up to two extra codes (one warp per
 // entry, fp64, lanes split the dimensions); lowest index wins exact ties
-template <typename ZT>
-__global__ void __launch_bounds__(256) chain_recheck_kernel(const ZT* __restrict__ z, const float* __restrict__ E,
-                                                            int K, int D, const int* __restrict__ chain_list,
-                                                            const int* __restrict__ counters, int* __restrict__ idx,
-                                                            unsigned long long* stats) {
-  const int lane = threadIdx.x & 31;
-  const int n = counters[2];
-  const int wstride = (gridDim.x * blockDim.x) >> 5;
-  for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n; e += wstride) {
+// BLOCK = false: one warp per entry.  BLOCK = true (large K: a chain is K / 32 codes): one CTA per entry, the
+// warps split the chain and combine through shared memory.
+template <typename ZT, bool BLOCK>
+__device__ __forceinline__ void chain_entries(const ZT* __restrict__ z, const float* __restrict__ E, int K, int D,
+                                              const int* __restrict__ chain_list, int n, int* __restrict__ idx,
+                                              double* sh_v, int* sh_i) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wstride = BLOCK ? (int)gridDim.x : (int)((gridDim.x * blockDim.x) >> 5);
+  for (int e = BLOCK ? (int)blockIdx.x : (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); e < n; e += wstride) {
     const int4 ent = reinterpret_cast<const int4*>(chain_list)[e];
     const ZT* zr = z + (size_t)ent.x * D;
     double best = INFINITY;
     int besti = 0x7fffffff;
     const int nchain = (K - ent.y + 31) / 32;
-    for (int t = 0; t < nchain + 2; ++t) {
+    for (int t = BLOCK ? warp : 0; t < nchain + 2; t += BLOCK ? 8 : 1) {
       const int k = t < nchain ? ent.y + 32 * t : (t == nchain ? ent.z : ent.w);
       if (k < 0 || k >= K) continue;                                // warp-uniform
       const float* er = E + (size_t)k * D;
@@ -1874,9 +1867,131 @@ __global__ void __launch_bounds__(256) chain_recheck_kernel(const ZT* __restrict
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if (s < best || (s == best && k < besti)) { best = s; besti = k; }
     }
-    if (lane == 0 && besti != 0x7fffffff) idx[ent.x] = besti;
+    if constexpr (BLOCK) {
+      __syncthreads();
+      if (lane == 0) { sh_v[warp] = best; sh_i[warp] = besti; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w)
+          if (sh_v[w] < best || (sh_v[w] == best && sh_i[w] < besti)) { best = sh_v[w]; besti = sh_i[w]; }
+        if (besti != 0x7fffffff) idx[ent.x] = besti;
+      }
+    } else {
+      if (lane == 0 && besti != 0x7fffffff) idx[ent.x] = besti;
+    }
   }
-  if (stats && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + G2V_STAT_PAIR_RECHECK, (unsigned long long)n);
+}
+
+// One launch for every exact re-rank of the tensor-core pass: the listed whole rows first (fp64 over all K
+// codes; each row split into `slices` CTAs that combine through `scratch`, the last one to arrive writes the
+// index), then the chain entries, then the two/three-candidate entries.  All CTAs walk all three lists, so
+// the short long-latency lists overlap with the long cheap one instead of running as three serial kernels.
+struct RerankSlot {
+  double v;
+  int i;
+  int pad;
+};
+constexpr int kRerankMaxSlices = 32;
+constexpr size_t kRerankScratchBytes = (size_t)kFull64Cap * kRerankMaxSlices * sizeof(RerankSlot);
+constexpr size_t kRerankArriveBytes = (size_t)kFull64Cap * sizeof(int);
+
+template <typename ZT>
+__global__ void __launch_bounds__(256) rerank_kernel(const ZT* __restrict__ z, const float* __restrict__ E, int K, int D,
+                                                     const int* __restrict__ pair_list, const int* __restrict__ chain_list,
+                                                     const int* __restrict__ full_list, const int* __restrict__ counters,
+                                                     int slices, RerankSlot* scratch, int* arrive, int* __restrict__ idx,
+                                                     unsigned long long* stats) {
+  extern __shared__ __align__(16) unsigned char rr_smem[];
+  float* zs = reinterpret_cast<float*>(rr_smem);            // one row, zero padded to a multiple of 32
+  __shared__ double bv[8];
+  __shared__ int bi[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_pair = counters[0], n_full = min(counters[1], kFull64Cap), n_chain = counters[2];
+
+  // ---- whole rows ----
+  const int Dp = (D + 31) & ~31;
+  const int per = ((K + slices - 1) / slices + 3) & ~3;     // codes per slice
+  constexpr int KC4 = 4;                                     // codes in flight per warp (latency hiding)
+  for (int item = blockIdx.x; item < n_full * slices; item += gridDim.x) {
+    const int e = item / slices, sl = item - e * slices;
+    const int row = full_list[e];
+    const int k0 = sl * per, k1 = min(K, k0 + per);
+    __syncthreads();
+    for (int j = threadIdx.x; j < Dp; j += blockDim.x) zs[j] = j < D ? ld_f32(z + (size_t)row * D + j) : 0.f;
+    __syncthreads();
+    double best = INFINITY;
+    int besti = 0x7fffffff;
+    for (int kb = k0 + warp * KC4; kb < k1; kb += 8 * KC4) {
+      double acc[KC4];
+#pragma unroll
+      for (int c = 0; c < KC4; ++c) acc[c] = 0.0;
+      for (int j0 = lane; j0 < Dp; j0 += 32 * 4) {
+        float ev[KC4][4];
+#pragma unroll
+        for (int c = 0; c < KC4; ++c) {
+          const float* er = E + (size_t)min(kb + c, K - 1) * D;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) ev[c][u] = (j0 + 32 * u < D) ? __ldg(er + j0 + 32 * u) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + 32 * u;
+          if (j < Dp) {
+            const double zv = (double)zs[j];
+#pragma unroll
+            for (int c = 0; c < KC4; ++c) {
+              const double df = zv - (double)ev[c][u];
+              acc[c] = fma(df, df, acc[c]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < KC4; ++c) {
+        double t = acc[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (kb + c < k1 && t < best) { best = t; besti = kb + c; }     // ascending k inside a warp: first wins
+      }
+    }
+    if (lane == 0) { bv[warp] = best; bi[warp] = besti; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double v = bv[0];
+      int id = bi[0];
+      for (int w = 1; w < 8; ++w)
+        if (bv[w] < v || (bv[w] == v && bi[w] < id)) { v = bv[w]; id = bi[w]; }
+      if (slices == 1) {
+        idx[row] = id;
+      } else {
+        RerankSlot* slot = scratch + (size_t)e * slices;
+        slot[sl].v = v;
+        slot[sl].i = id;
+        __threadfence();
+        if (atomicAdd(arrive + e, 1) == slices - 1) {       // the last slice of this row: combine
+          __threadfence();
+          const volatile RerankSlot* vs = slot;
+          v = vs[0].v; id = vs[0].i;
+          for (int q = 1; q < slices; ++q) {
+            const double qv = vs[q].v;
+            const int qi = vs[q].i;
+            if (qv < v || (qv == v && qi < id)) { v = qv; id = qi; }
+          }
+          idx[row] = id;
+          arrive[e] = 0;                                     // ready for the next search on this workspace
+        }
+      }
+    }
+  }
+  // ---- chains, then candidate pairs / triples ----
+  if (K >= 2048) chain_entries<ZT, true>(z, E, K, D, chain_list, n_chain, idx, bv, bi);
+  else chain_entries<ZT, false>(z, E, K, D, chain_list, n_chain, idx, bv, bi);
+  pair_entries<ZT>(z, E, D, pair_list, n_pair, idx);
+  if (stats && blockIdx.x == 0 && threadIdx.x == 0) {
+    atomicAdd(stats + G2V_STAT_PAIR_RECHECK, (unsigned long long)(n_pair + n_chain));
+    atomicAdd(stats + G2V_STAT_FALLBACK_ROWS, (unsigned long long)counters[1]);
+    if (n_full > 0) atomicAdd(stats + G2V_STAT_FULL_RECHECK, (unsigned long long)n_full);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1924,7 +2039,7 @@ int make_map(CUtensorMap* tm, const void* gptr, uint64_t rows, uint64_t cols, ui
 inline size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 
 struct TcWs {
-  size_t z16, rowinfo, pairs, fulls, chains, counters, total;
+  size_t z16, rowinfo, pairs, fulls, chains, counters, scratch, total;
 };
 TcWs tc_ws(int64_t N, int D) {
   const int Dp = round_up(D, 16);
@@ -1934,22 +2049,30 @@ TcWs tc_ws(int64_t N, int D) {
   w.pairs = w.rowinfo + al256((size_t)N * sizeof(RowInfo));
   w.fulls = w.pairs + al256((size_t)N * 16);
   w.chains = w.fulls + al256((size_t)N * 4);
-  w.counters = w.chains + al256((size_t)N * 16);
-  w.total = w.counters + 256;
+  w.counters = w.chains + al256((size_t)N * 16);       // 256 bytes of list counters, then the re-rank arrive counters
+  w.scratch = w.counters + 256 + al256(kRerankArriveBytes);
+  w.total = w.scratch + al256(kRerankScratchBytes);
   return w;
 }
 
-// exact re-rank of the rows the fast pass could not certify (candidate list, chain list, whole rows)
+// exact re-rank of the rows the fast pass could not certify (candidate list, chain list, whole rows).
+// `counters` is followed by the arrive counters (zero on entry, left zero) and `scratch` by tc_ws().
 template <typename ZT>
 int run_recheck(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, int K, int D, int* pairs, int* chains,
-                int* fulls, int* counters, int32_t* idx, unsigned long long* stats, unsigned flags, cudaStream_t st) {
+                int* fulls, int* counters, void* scratch, int32_t* idx, unsigned long long* stats, unsigned flags,
+                cudaStream_t st) {
   if (flags & G2V_NO_RECHECK) return G2V_OK;
-  const int pgrid = num_sms() * 4;
-  pair_recheck_kernel<ZT><<<pgrid, 256, 0, st>>>(z, E, D, pairs, counters, idx, stats);
-  G2V_LAUNCH_CHECK("pair_recheck_kernel");
-  chain_recheck_kernel<ZT><<<pgrid, 256, 0, st>>>(z, E, K, D, chains, counters, idx, stats);
-  G2V_LAUNCH_CHECK("chain_recheck_kernel");
-  return launch_full_recheck(z, z_dtype, E, cb, K, D, fulls, counters + 1, N, idx, stats, st);
+  // a whole row costs K x D fp64 operations on one CTA: split it so that a handful of rows does not become
+  // the latency of the step (~64 codes per warp pass)
+  int slices = K / 256;
+  slices = slices < 1 ? 1 : (slices > kRerankMaxSlices ? kRerankMaxSlices : slices);
+  if (K >= 96 && slices < 4) slices = 4;
+  int* arrive = counters + 64;
+  const size_t smem = (size_t)((D + 31) / 32 * 32) * sizeof(float);
+  rerank_kernel<ZT><<<num_sms() * 4, 256, smem, st>>>(z, E, K, D, pairs, chains, fulls, counters, slices,
+                                                     reinterpret_cast<RerankSlot*>(scratch), arrive, idx, stats);
+  G2V_LAUNCH_CHECK("rerank_kernel");
+  return launch_full_recheck(z, z_dtype, E, cb, K, D, fulls, counters + 1, N, idx, stats, true, st);
 }
 
 // Codebook-resident variant: geometry, or false if the shape does not qualify.
@@ -2114,14 +2237,14 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
       if (const char* dbg = getenv("G2V_TC_DEBUG")) R.flags |= ((unsigned)atoi(dbg) & 63u) << 8;
       R.trace = nullptr;
       if (const char* tr = getenv("G2V_TC_TRACE")) R.trace = reinterpret_cast<long long*>(strtoull(tr, nullptr, 0));
-      G2V_CUDA_CHECK(cudaMemsetAsync(counters, 0, 16, st));
+      G2V_CUDA_CHECK(cudaMemsetAsync(counters, 0, 256 + kRerankArriveBytes, st));
       cudaEvent_t pev0, pev1;
       profile_take(&pev0, &pev1);
       if (pev0) G2V_CUDA_CHECK(cudaEventRecord(pev0, st));
       const int rc = launch_tmem(R, reinterpret_cast<const float*>(z), e16, Kp, st);
       if (rc) return rc;
       if (pev1) G2V_CUDA_CHECK(cudaEventRecord(pev1, st));
-      return run_recheck(z, z_dtype, E, cb, N, K, D, pairs, chains, fulls, counters, idx, stats, flags, st);
+      return run_recheck(z, z_dtype, E, cb, N, K, D, pairs, chains, fulls, counters, base + w.scratch, idx, stats, flags, st);
     }
   }
   {   // K * D small: codebook-resident CTA pairs.  Experimental (G2V_TC_RES=1): correct, but slower than the
@@ -2135,14 +2258,14 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
       if (const char* dbg = getenv("G2V_TC_DEBUG")) R.flags |= ((unsigned)atoi(dbg) & 63u) << 8;
       R.trace = nullptr;
       if (const char* tr = getenv("G2V_TC_TRACE")) R.trace = reinterpret_cast<long long*>(strtoull(tr, nullptr, 0));
-      G2V_CUDA_CHECK(cudaMemsetAsync(counters, 0, 16, st));
+      G2V_CUDA_CHECK(cudaMemsetAsync(counters, 0, 256 + kRerankArriveBytes, st));
       cudaEvent_t pev0, pev1;
       profile_take(&pev0, &pev1);
       if (pev0) G2V_CUDA_CHECK(cudaEventRecord(pev0, st));
       const int rc = launch_resident<ZT>(R, e16, Kp, st);
       if (rc) return rc;
       if (pev1) G2V_CUDA_CHECK(cudaEventRecord(pev1, st));
-      return run_recheck(z, z_dtype, E, cb, N, K, D, pairs, chains, fulls, counters, idx, stats, flags, st);
+      return run_recheck(z, z_dtype, E, cb, N, K, D, pairs, chains, fulls, counters, base + w.scratch, idx, stats, flags, st);
     }
   }
   TcParams P;
@@ -2180,8 +2303,9 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
   P.n_ksteps = n_ksteps;
   P.hdr = hdr;
   if (fused) {
-    G2V_CUDA_CHECK(cudaMemsetAsync(counters, 0, 16, st));
+    G2V_CUDA_CHECK(cudaMemsetAsync(counters, 0, 256 + kRerankArriveBytes, st));
   } else {
+    G2V_CUDA_CHECK(cudaMemsetAsync(counters, 0, 256 + kRerankArriveBytes, st));
     const long long threads = N * 32;
     const int grid = (int)((threads + 255) / 256);
     row_prep_kernel<ZT><<<grid, 256, 0, st>>>(z, N, D, Dp, hdr, z16, rowinfo, counters, n_ksteps);
@@ -2259,7 +2383,7 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
   G2V_LAUNCH_CHECK("tc_search_kernel");
   if (pev1) G2V_CUDA_CHECK(cudaEventRecord(pev1, st));
 
-  return run_recheck(z, z_dtype, E, cb, N, K, D, pairs, chains, fulls, counters, idx, stats, flags, st);
+  return run_recheck(z, z_dtype, E, cb, N, K, D, pairs, chains, fulls, counters, base + w.scratch, idx, stats, flags, st);
 }
 
 }  // namespace
