@@ -39,17 +39,21 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defines=(), suffix: str = "") -> str:
+    """Compile csrc/*.cu and link csrc/libg2v_vq<suffix>.so.  `defines` / `suffix` build an experiment
+    variant next to the product library (selected at run time with G2V_LIB_PATH)."""
     nvcc = nvcc_path()
+    lib = LIB.replace(".so", f"{suffix}.so")
+    dflags = [f"-D{d}" for d in defines]
     extra_headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     objs = []
     procs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(CSRC, src.replace(".cu", ".o"))
+        o = os.path.join(CSRC, src.replace(".cu", f"{suffix}.o"))
         objs.append(o)
         if force or _stale(o, [s] + HEADERS + extra_headers):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-c", s, "-o", o]
+            cmd = [nvcc] + NVCC_FLAGS + dflags + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-c", s, "-o", o]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
         out, _ = p.communicate()
@@ -57,14 +61,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stdout.write(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
-    if force or procs or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    if force or procs or _stale(lib, objs):
+        cmd = [nvcc, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode:
             sys.stdout.write(r.stdout)
             raise RuntimeError("link failed")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    sfx = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--suffix=")), "")
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs, suffix=sfx))

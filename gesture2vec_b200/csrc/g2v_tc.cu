@@ -50,6 +50,11 @@ constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23: float bits = 0x4B400000 +
 constexpr float kKeyCap = 16777215.0f;  // kMagic + 2^22 - 1: largest key value
 constexpr int kMaxDp = 496;
 constexpr int kMaxK = 16384;            // 9-bit column-group field of the key
+// role-level timeline (tools/tc_trace.py): compiled in only with -DG2V_TRACE=1, the trace state costs registers
+#ifndef G2V_TRACE
+#define G2V_TRACE 0
+#endif
+constexpr bool kTraceBuild = G2V_TRACE != 0;
 constexpr unsigned kDbgSkipMma = 0x100u, kDbgSkipEpi = 0x200u, kDbgSkipConv = 0x400u, kDbgPrefetch = 0x800u,
                    kDbgNoB = 0x1000u, kDbgNoZ = 0x2000u;   // G2V_TC_DEBUG bring-up switches (timing only)
 
@@ -98,7 +103,24 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// G2V_WAIT_HINT: suspend-time hint (ns) of try_wait -- the warp sleeps in hardware until the phase completes
+// or the hint expires, instead of re-polling (each poll costs three issue slots: SYNCS, YIELD, BRA)
+#ifndef G2V_WAIT_HINT
+#define G2V_WAIT_HINT 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#if G2V_WAIT_HINT
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity), "r"((uint32_t)G2V_WAIT_HINT)
+      : "memory");
+#else
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -109,11 +131,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "WAIT_DONE:\n\t"
       "}" ::"r"(bar), "r"(parity)
       : "memory");
+#endif
 }
 // TMA tile load.  CG == 2: the .cta_group::2 form, whose completion bytes are credited to the
 // mbarrier at the same offset in the LEADER CTA (peer bit of the shared::cluster address cleared).
 // wait with cluster-scope acquire (pairs with a peer CTA's release.cluster arrive)
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+#if G2V_WAIT_HINT
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP_C:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra.uni WAIT_DONE_C;\n\t"
+      "bra.uni WAIT_LOOP_C;\n\t"
+      "WAIT_DONE_C:\n\t"
+      "}" ::"r"(bar), "r"(parity), "r"((uint32_t)G2V_WAIT_HINT)
+      : "memory");
+#else
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -124,6 +159,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
       "WAIT_DONE_C:\n\t"
       "}" ::"r"(bar), "r"(parity)
       : "memory");
+#endif
 }
 // make generic-proxy shared-memory writes visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -274,6 +310,26 @@ __host__ __device__ inline SmemPlan smem_plan(int n_full, int n_tail, int cg, in
 // ------------------------------------------------------------------------------------------
 // epilogue helpers
 // ------------------------------------------------------------------------------------------
+// two fp32 FMAs in one instruction (FFMA2): halves the issue slots of the fp32 work in the epilogue and the
+// converters, which share the four schedulers with everything else (-DG2V_PACKED_F32=0 keeps scalar FFMA)
+#ifndef G2V_PACKED_F32
+#define G2V_PACKED_F32 1
+#endif
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
+#if G2V_PACKED_F32
+  uint64_t ra, rb, rc, rd;
+  float2 d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+#else
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+
 // 16 columns of a chunk: key = fixed-point(e2 - 2 z.e) << 9 | column group; one running top-2 chain
 // per column position
 template <bool PARTIAL>
@@ -282,16 +338,97 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[16], const float* 
 #pragma unroll
   for (int j4 = 0; j4 < 4; ++j4) {
     const float4 e = *reinterpret_cast<const float4*>(e2c + 4 * j4);
-    const float ee[4] = {e.x, e.y, e.z, e.w};
+    const float2 cS2 = make_float2(cS, cS), S2 = make_float2(S, S), M2 = make_float2(kMagic, kMagic);
+    const float2 x01 = ffma2(make_float2(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1])), cS2,
+                             ffma2(make_float2(e.x, e.y), S2, M2));
+    const float2 x23 = ffma2(make_float2(__uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])), cS2,
+                             ffma2(make_float2(e.z, e.w), S2, M2));
+    const float xx[4] = {x01.x, x01.y, x23.x, x23.y};
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int j = 4 * j4 + u;
-      float x = fmaf(__uint_as_float(v[j]), cS, fmaf(ee[u], S, kMagic));
-      x = fminf(x, kKeyCap);                         // far codes saturate instead of wrapping
+      float x = fminf(xx[u], kKeyCap);               // far codes saturate instead of wrapping
       uint32_t key = __float_as_uint(x) * 512u + group;
       if (PARTIAL && j >= nvalid) key = 0xFFFFFFFFu;
       m2[j] = max(m1[j], min(m2[j], key));
       m1[j] = min(m1[j], key);
+    }
+  }
+}
+
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+// volatile: the load stays where it is written (half a piece ahead of its use) instead of being sunk to it
+__device__ __forceinline__ float4 lds4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+// 8 columns (chains OFF .. OFF+7 of this thread): keys as in epi_chunk.  Written stage by stage over the eight
+// independent columns: ptxas keeps that order, and every stage then has eight instructions in flight instead
+// of one dependent chain per column (which left the epilogue warps latency-bound at ~0.17 IPC).
+template <int OFF, bool PARTIAL>
+__device__ __forceinline__ void epi8(const uint32_t (&v)[8], const float4 e0, const float4 e1, float cS, float S, uint32_t group,
+                                     int nvalid, uint32_t (&m1)[16], uint32_t (&m2)[16]) {
+  const float2 cS2 = make_float2(cS, cS), S2 = make_float2(S, S), M2 = make_float2(kMagic, kMagic);
+  const float2 ee[4] = {make_float2(e0.x, e0.y), make_float2(e0.z, e0.w), make_float2(e1.x, e1.y), make_float2(e1.z, e1.w)};
+  float2 t[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) t[p] = ffma2(ee[p], S2, M2);
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+    t[p] = ffma2(make_float2(__uint_as_float(v[2 * p]), __uint_as_float(v[2 * p + 1])), cS2, t[p]);
+  float f[8];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    f[2 * p] = fminf(t[p].x, kKeyCap);                  // far codes saturate instead of wrapping
+    f[2 * p + 1] = fminf(t[p].y, kKeyCap);
+  }
+  uint32_t key[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    key[j] = __float_as_uint(f[j]) * 512u + group;
+    if (PARTIAL && j >= nvalid) key[j] = 0xFFFFFFFFu;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) lo[j] = min(m2[OFF + j], key[j]);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m2[OFF + j] = max(m1[OFF + j], lo[j]);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m1[OFF + j] = min(m1[OFF + j], key[j]);
+}
+// One code tile of one epilogue warp: its 16-column pieces g0 .. g1-1 (codes [32 g + 16 eh, +16)), software-pipelined
+// in halves of 8 columns -- while one half is turned into keys, the tensor-memory load and the ||e||^2 loads
+// of the next half are in flight.  tcol0 / e2addr0 address code 16 eh (tensor-memory column, shared-memory byte).
+__device__ __forceinline__ void epi_sweep(uint32_t tcol0, uint32_t e2addr0, int g0, int g1, int e_valid, int eh, float cS, float S,
+                                          bool skip, uint32_t (&m1)[16], uint32_t (&m2)[16]) {
+  if (g0 >= g1) return;
+  uint32_t va[8], vb[8];
+  tc_ld8(tcol0 + 32u * g0, va);
+  float4 ea0 = lds4(e2addr0 + 128u * g0), ea1 = lds4(e2addr0 + 128u * g0 + 16u), eb0, eb1;
+  for (int g = g0; g < g1; ++g) {
+    const int nv = e_valid - (32 * g + 16 * eh);          // valid codes of this piece (>= 1)
+    tc_wait_ld();
+    tc_ld8(tcol0 + 32u * g + 8u, vb);
+    eb0 = lds4(e2addr0 + 128u * g + 32u);
+    eb1 = lds4(e2addr0 + 128u * g + 48u);
+    if (!skip) {
+      if (nv >= 8) epi8<0, false>(va, ea0, ea1, cS, S, (uint32_t)g, 8, m1, m2);
+      else epi8<0, true>(va, ea0, ea1, cS, S, (uint32_t)g, nv, m1, m2);
+    }
+    tc_wait_ld();
+    if (g + 1 < g1) {
+      tc_ld8(tcol0 + 32u * (g + 1), va);
+      ea0 = lds4(e2addr0 + 128u * (g + 1));
+      ea1 = lds4(e2addr0 + 128u * (g + 1) + 16u);
+    }
+    if (!skip) {
+      if (nv >= 16) epi8<8, false>(vb, eb0, eb1, cS, S, (uint32_t)g, 8, m1, m2);
+      else epi8<8, true>(vb, eb0, eb1, cS, S, (uint32_t)g, nv - 8, m1, m2);
     }
   }
 }
@@ -302,16 +439,19 @@ struct Cand {
   int j;           // chain id = column % 32
 };
 // keep the three smallest chain minima (c1 <= c2 <= c3) and the fourth smallest key (k4)
+// (branch-free: rows of a warp take different paths, and the selects of successive insertions overlap)
 __device__ __forceinline__ void cand_insert(Cand& c1, Cand& c2, Cand& c3, uint32_t& k4, const Cand n) {
-  if (n.key < c1.key) {
-    k4 = c3.key; c3 = c2; c2 = c1; c1 = n;
-  } else if (n.key < c2.key) {
-    k4 = c3.key; c3 = c2; c2 = n;
-  } else if (n.key < c3.key) {
-    k4 = c3.key; c3 = n;
-  } else {
-    k4 = min(k4, n.key);
-  }
+  const bool l1 = n.key < c1.key, l2 = n.key < c2.key, l3 = n.key < c3.key;
+  k4 = min(k4, max(n.key, c3.key));      // whichever of the new key and the old third does not stay among the three
+  c3.key = l3 ? (l2 ? c2.key : n.key) : c3.key;
+  c3.key2 = l3 ? (l2 ? c2.key2 : n.key2) : c3.key2;
+  c3.j = l3 ? (l2 ? c2.j : n.j) : c3.j;
+  c2.key = l2 ? (l1 ? c1.key : n.key) : c2.key;
+  c2.key2 = l2 ? (l1 ? c1.key2 : n.key2) : c2.key2;
+  c2.j = l2 ? (l1 ? c1.j : n.j) : c2.j;
+  c1.key = l1 ? n.key : c1.key;
+  c1.key2 = l1 ? n.key2 : c1.key2;
+  c1.j = l1 ? n.j : c1.j;
 }
 
 // Per-row decision from the three best chain minima (each with the runner-up of its own chain) and the
@@ -462,7 +602,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // bring-up trace: role r (0 B-prod, 1 MMA, 2 A-prod, 3 epilogue warp 4, 4 converter warp 12), up to 512 events each
   int trace_n = 0;
   auto TRACE = [&](int role, int tag) {
-    if (P.trace && blockIdx.x == 0 && lane == 0 && trace_n < 512) {
+    if (kTraceBuild && P.trace && blockIdx.x == 0 && lane == 0 && trace_n < 512) {
       long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       P.trace[(role * 512 + trace_n) * 2] = tag;
@@ -968,7 +1108,7 @@ tc_resident_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_chunks = P.n_chunks, n_full = P.n_full;
-  const uint32_t acc_col[2] = {(uint32_t)P.acc_col0, (uint32_t)(P.acc_col0 + P.ntile)};
+  auto acc_col_of = [&](uint32_t a) { return (uint32_t)P.acc_col0 + a * (uint32_t)P.ntile; };   // accumulator stage a
   const uint32_t a_cols = (uint32_t)P.Dp / 2, abm = (uint32_t)P.a_bufs - 1u, absh = (uint32_t)P.a_bufs >> 1;   // buffer = ti & abm, use = ti >> absh
 
   if (threadIdx.x == 0) {
@@ -992,7 +1132,7 @@ tc_resident_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   int trace_n = 0;
   auto TRACE = [&](int role, int tag) {   // role 1 MMA, 2 signaller (CTA 1 only), 3 epilogue warp 4, 4 converter warp 12
-    if (P.trace && blockIdx.x == (role == 2 ? 1 : 0) && lane == 0 && trace_n < 512) {
+    if (kTraceBuild && P.trace && blockIdx.x == (role == 2 ? 1 : 0) && lane == 0 && trace_n < 512) {
       long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       P.trace[(role * 512 + trace_n) * 2] = tag;
@@ -1064,7 +1204,7 @@ tc_resident_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
           mbar_wait(bar_accempty(as), (around & 1u) ^ 1u);
           TRACE(1, 200 + nt);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc_col[as];
+          const uint32_t d_tmem = tmem_base + acc_col_of(as);
           for (int c = 0; c < n_chunks; ++c) {
             if (nt == 0) {
               mbar_wait(bar_aconv(ab, c), apar);
@@ -1135,7 +1275,7 @@ tc_resident_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constan
         mbar_wait(bar_accfull(as), around & 1u);
         if (warp == EPI_WARP0) TRACE(3, 200 + nt);
         tc_fence_after();
-        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col[as] + (uint32_t)(16 * eh - s0);
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col_of(as) + (uint32_t)(16 * eh - s0);
         uint32_t va[16], vb[16];
         if (g0 < g1) tc_ld16(taddr0 + 32u * g0, va);
         for (int g = g0; g < g1; g += 2) {
@@ -1313,13 +1453,14 @@ constexpr int TME_MAX_ZSLOTS = 10;
 constexpr int TME_ZCOLS = 32;           // fp32 columns per staging slot (128 bytes: one SWIZZLE_128B row)
 constexpr int TME_ZSLOT = TM * TME_ZCOLS * 4;   // 16384
 constexpr int TME_MAX_BST = 16;
+constexpr int kTmeDefaultABufs = 1;   // see plan_tmem()
 
 struct TmeParams {
   long long N;
   int K, D, Dp;
   int n_full, n_tail, n_chunks;   // K panels of the A operand: 64 columns, then 16-column tails
   int ntile, n_ntiles, n_last;    // codes per accumulator stage; code tiles; codes of the last tile (multiple of 16)
-  int acc_col0;                   // first accumulator column in TMEM
+  int a_bufs, acc_col0;           // A operand buffers in TMEM (1 or 2); first accumulator column in TMEM
   int n_row_tiles;                // tiles of 256 rows (128 per CTA)
   int n_ksteps;
   int Kpad;                       // (n_ntiles - 1) * ntile + n_last
@@ -1340,7 +1481,7 @@ struct TmeParams {
 struct TmePlan {
   uint32_t b_off, z_off, e2_off, xch_off, rs_off, bar_off, tmem_off, total;
 };
-constexpr int TME_NBARS = 2 * TME_MAX_BST + 2 * TME_MAX_ZSLOTS + 3 * MAX_CHUNKS + 4 + RS_RING;
+constexpr int TME_NBARS = 2 * TME_MAX_BST + 2 * TME_MAX_ZSLOTS + 6 * MAX_CHUNKS + 4 + RS_RING;
 __host__ __device__ inline TmePlan tme_plan(int nb, uint32_t b_stage, int nz, int Kpad) {
   TmePlan p;
   p.b_off = 0;
@@ -1378,23 +1519,26 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
   auto bar_zfull = [&](int s) { return bars + 8u * (2 * TME_MAX_BST + s); };
   auto bar_zempty = [&](int s) { return bars + 8u * (2 * TME_MAX_BST + TME_MAX_ZSLOTS + s); };
   constexpr int A0 = 2 * TME_MAX_BST + 2 * TME_MAX_ZSLOTS;
-  auto bar_aconv = [&](int c) { return bars + 8u * (A0 + c); };                      // this CTA's converters wrote panel c
-  auto bar_apeer = [&](int c) { return bars + 8u * (A0 + MAX_CHUNKS + c); };         // leader: the peer's converters did
-  auto bar_aempty = [&](int c) { return bars + 8u * (A0 + 2 * MAX_CHUNKS + c); };    // the MMAs finished reading panel c
-  auto bar_accfull = [&](int a) { return bars + 8u * (A0 + 3 * MAX_CHUNKS + a); };
-  auto bar_accempty = [&](int a) { return bars + 8u * (A0 + 3 * MAX_CHUNKS + 2 + a); };
-  auto bar_rsfull = [&](int s) { return bars + 8u * (A0 + 3 * MAX_CHUNKS + 4 + s); };
+  // per A buffer b and super-chunk c
+  auto bar_aconv = [&](int b, int c) { return bars + 8u * (A0 + b * MAX_CHUNKS + c); };              // this CTA's converters wrote it
+  auto bar_apeer = [&](int b, int c) { return bars + 8u * (A0 + (2 + b) * MAX_CHUNKS + c); };        // leader: the peer's converters did
+  auto bar_aempty = [&](int b, int c) { return bars + 8u * (A0 + (4 + b) * MAX_CHUNKS + c); };       // the MMAs finished reading it
+  auto bar_accfull = [&](int a) { return bars + 8u * (A0 + 6 * MAX_CHUNKS + a); };
+  auto bar_accempty = [&](int a) { return bars + 8u * (A0 + 6 * MAX_CHUNKS + 2 + a); };
+  auto bar_rsfull = [&](int s) { return bars + 8u * (A0 + 6 * MAX_CHUNKS + 4 + s); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + sp.tmem_off);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_chunks = P.n_chunks, n_full = P.n_full;
-  const uint32_t acc_col[2] = {(uint32_t)P.acc_col0, (uint32_t)(P.acc_col0 + P.ntile)};
+  auto acc_col_of = [&](uint32_t a) { return (uint32_t)P.acc_col0 + a * (uint32_t)P.ntile; };   // accumulator stage a
+  const uint32_t a_cols = (uint32_t)P.Dp / 2, abm = (uint32_t)P.a_bufs - 1u, absh = (uint32_t)P.a_bufs >> 1;   // buffer = ti & abm, use = ti >> absh
   const int n_sc = (n_full + 1) >> 1;      // super-chunks (codebook stages / A hand-overs) per code tile
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TME_MAX_BST; ++s) { mbar_init(bar_bfull(s), 1); mbar_init(bar_bempty(s), 1); }
     for (int s = 0; s < TME_MAX_ZSLOTS; ++s) { mbar_init(bar_zfull(s), 1); mbar_init(bar_zempty(s), RES_CONV_WARPS); }
-    for (int c = 0; c < MAX_CHUNKS; ++c) { mbar_init(bar_aconv(c), RES_CONV_WARPS); mbar_init(bar_apeer(c), 1); mbar_init(bar_aempty(c), 1); }
+    for (int b = 0; b < 2; ++b)
+      for (int c = 0; c < MAX_CHUNKS; ++c) { mbar_init(bar_aconv(b, c), RES_CONV_WARPS); mbar_init(bar_apeer(b, c), 1); mbar_init(bar_aempty(b, c), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(bar_accfull(a), 1); mbar_init(bar_accempty(a), 16); }
     for (int s = 0; s < RS_RING; ++s) mbar_init(bar_rsfull(s), RES_CONV_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1411,7 +1555,7 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   int trace_n = 0;
   auto TRACE = [&](int role, int tag) {   // role 0 B producer, 1 MMA, 2 row producer, 3 epilogue warp 4, 4 converter warp 12
-    if (P.trace && blockIdx.x == 0 && lane == 0 && trace_n < 512) {
+    if (kTraceBuild && P.trace && blockIdx.x == 0 && lane == 0 && trace_n < 512) {
       long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       P.trace[(role * 512 + trace_n) * 2] = tag;
@@ -1452,6 +1596,9 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
       uint32_t s = 0, sph = 0, it = 0, ti = 0;
       const bool skip_mma = (P.flags & kDbgSkipMma) != 0;
       for (int tile = group; tile < P.n_row_tiles; tile += n_groups, ++ti) {
+        const int ab = (int)(ti & abm);
+        const uint32_t apar = (ti >> absh) & 1u;
+        const uint32_t a_base = tmem_base + (uint32_t)ab * a_cols;
         for (int nt = 0; nt < P.n_ntiles; ++nt, ++it) {
           const uint32_t as = it & 1u, around = it >> 1;
           const bool last_nt = (nt == P.n_ntiles - 1);
@@ -1460,14 +1607,17 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
           mbar_wait(bar_accempty(as), (around & 1u) ^ 1u);
           TRACE(1, 200 + nt);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc_col[as];
+          const uint32_t d_tmem = tmem_base + acc_col_of(as);
           const uint32_t rows_b = (uint32_t)(last_nt ? P.n_last : P.ntile) / 2u;     // code rows per CTA in a stage
           for (int sc = 0; sc < n_sc; ++sc) {
             if (nt == 0) {
-              mbar_wait(bar_aconv(sc), ti & 1u);
-              mbar_wait_cluster(bar_apeer(sc), ti & 1u);
+              mbar_wait(bar_aconv(ab, sc), apar);
+              TRACE(1, 300 + sc);
+              mbar_wait_cluster(bar_apeer(ab, sc), apar);
+              TRACE(1, 400 + sc);
             }
             mbar_wait(bar_bfull(s), sph);
+            if (nt == 0) TRACE(1, 500 + sc);
             tc_fence_after();
             const int p0 = 2 * sc, np = min(2, n_full - p0);
             const bool tails = (sc == n_sc - 1);
@@ -1476,18 +1626,18 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
               if (!skip_mma) {
                 for (int k = 0; k < np; ++k) {
                   const uint64_t bd0 = umma_desc(b_addr + (uint32_t)k * rows_b * 128u, 1024, 2);
-                  const uint32_t a_tmem = tmem_base + 32u * (uint32_t)(p0 + k);
+                  const uint32_t a_tmem = a_base + 32u * (uint32_t)(p0 + k);
 #pragma unroll
                   for (int kk = 0; kk < KC / KT; ++kk)
                     tc_mma_f16_ts2(d_tmem, a_tmem + 8u * kk, bd0 + 2u * kk, idesc, (sc | k | kk) != 0);
                 }
                 if (tails)
                   for (int t = 0; t < P.n_tail; ++t)
-                    tc_mma_f16_ts2(d_tmem, tmem_base + 32u * n_full + 8u * t,
+                    tc_mma_f16_ts2(d_tmem, a_base + 32u * n_full + 8u * t,
                                    umma_desc(b_addr + (uint32_t)np * rows_b * 128u + (uint32_t)t * rows_b * 32u, 256, 6), idesc, 1u);
               }
               tc_commit<2>(bar_bempty(s));
-              if (last_nt) tc_commit<2>(bar_aempty(sc));
+              if (last_nt) tc_commit<2>(bar_aempty(ab, sc));
               if (tails) tc_commit<2>(bar_accfull(as));
             }
             __syncwarp();
@@ -1500,8 +1650,8 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
       uint32_t ti = 0;
       for (int tile = group; tile < P.n_row_tiles; tile += n_groups, ++ti) {
         for (int sc = 0; sc < n_sc; ++sc) {
-          mbar_wait(bar_aconv(sc), ti & 1u);
-          if (elect_one()) mbar_arrive_cluster(bar_apeer(sc), 0);
+          mbar_wait(bar_aconv((int)(ti & abm), sc), (ti >> absh) & 1u);
+          if (elect_one()) mbar_arrive_cluster(bar_apeer((int)(ti & abm), sc), 0);
           __syncwarp();
         }
       }
@@ -1539,13 +1689,16 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
     const int r = q * 32 + lane;
     uint32_t* xrow = xch + (size_t)r * 12;
     uint32_t it = 0, ti = 0;
-    const float h_sfrac = P.hdr->sfrac, h_e2min = P.hdr->e2min, h_scale_e = P.hdr->scale_e;
+    const uint32_t e2_saddr = smem_u32(e2s) + 64u * (uint32_t)eh;      // ||e||^2 of code 16 eh
     for (int tile = group; tile < P.n_row_tiles; tile += n_groups, ++ti) {
-      const long long row = ((long long)tile * 2 + cta_rank) * TM + r;
-      const bool valid = row < P.N;
+      // Only the two key constants of the row stay in registers across the sweep (the key/top-2 chains need
+      // every register they can get); the full per-row constants are rebuilt from the statistics afterwards.
       mbar_wait(bar_rsfull(ti % RS_RING), (ti / RS_RING) & 1u);
-      const float2 st = rowstat[(ti % RS_RING) * TM + r];
-      const RowInfo ri = make_rowinfo(st.x, st.y, 1.f, h_sfrac, h_e2min, h_scale_e, P.n_ksteps);
+      float key_cS, key_S;
+      {
+        const RowInfo r0 = make_rowinfo(rowstat[(ti % RS_RING) * TM + r].x, 0.f, 1.f, 0.f, P.hdr->e2min, P.hdr->scale_e, P.n_ksteps);
+        key_cS = r0.cS; key_S = r0.S;
+      }
       uint32_t m1[16], m2[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) { m1[j] = 0xFFFFFFFFu; m2[j] = 0xFFFFFFFFu; }
@@ -1559,27 +1712,8 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
         mbar_wait(bar_accfull(as), around & 1u);
         if (warp == EPI_WARP0) TRACE(3, 200 + nt);
         tc_fence_after();
-        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col[as] + (uint32_t)(16 * eh - s0);
-        uint32_t va[16], vb[16];
-        if (g0 < g1) tc_ld16(taddr0 + 32u * g0, va);
-        for (int g = g0; g < g1; g += 2) {
-          tc_wait_ld();
-          if (g + 1 < g1) tc_ld16(taddr0 + 32u * (g + 1), vb);
-          if (!(P.flags & kDbgSkipEpi)) {
-            const int cb0 = 32 * g + 16 * eh, nv = e_valid - cb0;
-            if (nv >= 16) epi_chunk<false>(va, e2s + cb0, ri.cS, ri.S, (uint32_t)g, 16, m1, m2);
-            else epi_chunk<true>(va, e2s + cb0, ri.cS, ri.S, (uint32_t)g, nv, m1, m2);
-          }
-          if (g + 1 < g1) {
-            tc_wait_ld();
-            if (g + 2 < g1) tc_ld16(taddr0 + 32u * (g + 2), va);
-            if (!(P.flags & kDbgSkipEpi)) {
-              const int cb0 = 32 * (g + 1) + 16 * eh, nv = e_valid - cb0;
-              if (nv >= 16) epi_chunk<false>(vb, e2s + cb0, ri.cS, ri.S, (uint32_t)(g + 1), 16, m1, m2);
-              else epi_chunk<true>(vb, e2s + cb0, ri.cS, ri.S, (uint32_t)(g + 1), nv, m1, m2);
-            }
-          }
-        }
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col_of(as) + (uint32_t)(16 * eh - s0);
+        epi_sweep(taddr0, e2_saddr, g0, g1, e_valid, eh, key_cS, key_S, (P.flags & kDbgSkipEpi) != 0, m1, m2);
         tc_fence_before();
         __syncwarp();
         if (warp == EPI_WARP0) TRACE(3, 300 + nt);
@@ -1606,6 +1740,10 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
         cand_insert(c1, c2, c3, k4, Cand{xrow[3], xrow[4], (int)xrow[5]});
         cand_insert(c1, c2, c3, k4, Cand{xrow[6], xrow[7], (int)xrow[8]});
         k4 = min(k4, xrow[9]);
+        const long long row = ((long long)tile * 2 + cta_rank) * TM + r;
+        const bool valid = row < P.N;
+        const float2 st = rowstat[(ti % RS_RING) * TM + r];
+        const RowInfo ri = make_rowinfo(st.x, st.y, 1.f, P.hdr->sfrac, P.hdr->e2min, P.hdr->scale_e, P.n_ksteps);
         finish_row(c1, c2, c3, k4, ri, row, valid, P.K, P.ntab, P.flags, P.idx, P.pair_list, P.chain_list, P.full_list, P.counters);
       }
       asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
@@ -1622,19 +1760,26 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
     const uint32_t t_lane = tmem_base + ((uint32_t)lane0_row << 16);
     const uint32_t kq = (uint32_t)(lane & 3), sw = (uint32_t)(ra_l & 7);            // (rb_l & 7) == (ra_l & 7)
     const uint32_t off_a0 = (uint32_t)ra_l * 128u + ((kq ^ sw) << 4), off_a1 = (uint32_t)ra_l * 128u + (((4u + kq) ^ sw) << 4);
+    const bool odd = (ra_l & 1) != 0;
+    const uint32_t off_f = odd ? off_a1 : off_a0, off_s = odd ? off_a0 : off_a1;
     const uint32_t off_t = (uint32_t)ra_l * 64u + kq * 16u;                        // tail slot: 64-byte rows, no swizzle
-    float z2a = 0.f, r2a = 0.f, z2b = 0.f, r2b = 0.f;
-    auto cvt = [&](const float4 v, float& z2, float& r2, uint32_t& w0, uint32_t& w1) {
+    // per-row sums as two partial sums each (even / odd elements), so that the squares and the rounding
+    // residuals v - fp16(v) (exact in fp32) take packed FMAs
+    float2 z2a = make_float2(0.f, 0.f), r2a = z2a, z2b = z2a, r2b = z2a;
+    const float2 neg1 = make_float2(-1.f, -1.f);
+    auto cvt = [&](const float4 v, float2& z2, float2& r2, uint32_t& w0, uint32_t& w1) {
       const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
-      const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-      const float e0 = v.x - f01.x, e1 = v.y - f01.y, e2r = v.z - f23.x, e3 = v.w - f23.y;
-      z2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, z2))));
-      r2 = fmaf(e0, e0, fmaf(e1, e1, fmaf(e2r, e2r, fmaf(e3, e3, r2))));
+      const float2 v01 = make_float2(v.x, v.y), v23 = make_float2(v.z, v.w);
+      const float2 e01 = ffma2(__half22float2(h01), neg1, v01), e23 = ffma2(__half22float2(h23), neg1, v23);
+      z2 = ffma2(v23, v23, ffma2(v01, v01, z2));
+      r2 = ffma2(e23, e23, ffma2(e01, e01, r2));
       w0 = *reinterpret_cast<const uint32_t*>(&h01);
       w1 = *reinterpret_cast<const uint32_t*>(&h23);
     };
     uint32_t slot = 0, ph = 0, ti = 0;
     for (int tile = group; tile < P.n_row_tiles; tile += n_groups, ++ti) {
+      const int ab = (int)(ti & abm);
+      const uint32_t t_buf = t_lane + (uint32_t)ab * a_cols;
       for (int c = 0; c < n_chunks; ++c) {
         // barriers work on super-chunks: panels 2 sc and 2 sc + 1, the tails belong to the last one
         const int sc = min(c >> 1, n_sc - 1);
@@ -1642,7 +1787,7 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
         const bool sc_last = (c == n_chunks - 1) || (c < n_full - 1 && (c & 1) == 1) || (c == n_full - 1 && sc < n_sc - 1);
         if (sc_first) {
           if (cw == 0) TRACE(4, 100 + sc);
-          mbar_wait(bar_aempty(sc), (ti & 1u) ^ 1u);       // the MMAs of the previous row tile have read these panels
+          mbar_wait(bar_aempty(ab, sc), ((ti >> absh) & 1u) ^ 1u);   // the MMAs of the buffer's previous row tile have read these panels
           if (cw == 0) TRACE(4, 200 + sc);
           tc_fence_after();
         }
@@ -1652,17 +1797,24 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
           for (int h = 0; h < 2; ++h) {
             mbar_wait(bar_zfull(slot), ph);
             const unsigned char* zs = gbase + sp.z_off + slot * TME_ZSLOT;
-            const float4 a0 = *reinterpret_cast<const float4*>(zs + off_a0), b0 = *reinterpret_cast<const float4*>(zs + off_a0 + 8 * 128);
-            const float4 a1 = *reinterpret_cast<const float4*>(zs + off_a1), b1 = *reinterpret_cast<const float4*>(zs + off_a1 + 8 * 128);
-            cvt(a0, z2a, r2a, w[8 * h + 0], w[8 * h + 1]);
-            cvt(b0, z2b, r2b, w[8 * h + 2], w[8 * h + 3]);
-            cvt(a1, z2a, r2a, w[8 * h + 4], w[8 * h + 5]);
-            cvt(b1, z2b, r2b, w[8 * h + 6], w[8 * h + 7]);
+            // odd rows fetch their second K step first: the two rows of a quarter-warp then sit in different
+            // halves of the swizzled 128-byte line (no bank conflict); the words are put back in order below
+            const float4 af = *reinterpret_cast<const float4*>(zs + off_f), bf = *reinterpret_cast<const float4*>(zs + off_f + 8 * 128);
+            const float4 as = *reinterpret_cast<const float4*>(zs + off_s), bs = *reinterpret_cast<const float4*>(zs + off_s + 8 * 128);
+            uint32_t f0, f1, f2, f3, s0, s1, s2, s3;
+            cvt(af, z2a, r2a, f0, f1);
+            cvt(bf, z2b, r2b, f2, f3);
+            cvt(as, z2a, r2a, s0, s1);
+            cvt(bs, z2b, r2b, s2, s3);
+            w[8 * h + 0] = odd ? s0 : f0; w[8 * h + 1] = odd ? s1 : f1;
+            w[8 * h + 2] = odd ? s2 : f2; w[8 * h + 3] = odd ? s3 : f3;
+            w[8 * h + 4] = odd ? f0 : s0; w[8 * h + 5] = odd ? f1 : s1;
+            w[8 * h + 6] = odd ? f2 : s2; w[8 * h + 7] = odd ? f3 : s3;
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_zempty(slot));
             if (++slot == NZ) { slot = 0; ph ^= 1u; }
           }
-          tc_st_16x256b_x4(t_lane + 32u * c, w);
+          tc_st_16x256b_x4(t_buf + 32u * c, w);
         } else {
           mbar_wait(bar_zfull(slot), ph);
           const unsigned char* zs = gbase + sp.z_off + slot * TME_ZSLOT;
@@ -1673,28 +1825,30 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_zempty(slot));
           if (++slot == NZ) { slot = 0; ph ^= 1u; }
-          tc_st_16x256b_x1(t_lane + 32u * n_full + 8u * (c - n_full), w0, w1, w2, w3);
+          tc_st_16x256b_x1(t_buf + 32u * n_full + 8u * (c - n_full), w0, w1, w2, w3);
         }
         if (sc_last) {
           if (cw == 0) TRACE(4, 300 + sc);
           tc_wait_st();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_aconv(sc));
+          if (lane == 0) mbar_arrive(bar_aconv(ab, sc));
+          if (cw == 0) TRACE(4, 400 + sc);
         }
       }
       // row statistics of the finished tile: sum over the four lanes that share a row
-      z2a += __shfl_xor_sync(0xffffffffu, z2a, 1); r2a += __shfl_xor_sync(0xffffffffu, r2a, 1);
-      z2b += __shfl_xor_sync(0xffffffffu, z2b, 1); r2b += __shfl_xor_sync(0xffffffffu, r2b, 1);
-      z2a += __shfl_xor_sync(0xffffffffu, z2a, 2); r2a += __shfl_xor_sync(0xffffffffu, r2a, 2);
-      z2b += __shfl_xor_sync(0xffffffffu, z2b, 2); r2b += __shfl_xor_sync(0xffffffffu, r2b, 2);
+      float sza = z2a.x + z2a.y, sra = r2a.x + r2a.y, szb = z2b.x + z2b.y, srb = r2b.x + r2b.y;
+      sza += __shfl_xor_sync(0xffffffffu, sza, 1); sra += __shfl_xor_sync(0xffffffffu, sra, 1);
+      szb += __shfl_xor_sync(0xffffffffu, szb, 1); srb += __shfl_xor_sync(0xffffffffu, srb, 1);
+      sza += __shfl_xor_sync(0xffffffffu, sza, 2); sra += __shfl_xor_sync(0xffffffffu, sra, 2);
+      szb += __shfl_xor_sync(0xffffffffu, szb, 2); srb += __shfl_xor_sync(0xffffffffu, srb, 2);
       if ((lane & 3) == 0) {
-        rowstat[(ti % RS_RING) * TM + ra_l] = make_float2(z2a, r2a);
-        rowstat[(ti % RS_RING) * TM + rb_l] = make_float2(z2b, r2b);
+        rowstat[(ti % RS_RING) * TM + ra_l] = make_float2(sza, sra);
+        rowstat[(ti % RS_RING) * TM + rb_l] = make_float2(szb, srb);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_rsfull(ti % RS_RING));
-      z2a = r2a = z2b = r2b = 0.f;
+      z2a = r2a = z2b = r2b = make_float2(0.f, 0.f);
     }
   }
 
@@ -2145,11 +2299,14 @@ int launch_resident(ResParams& R, const __half* e16, int Kp, cudaStream_t st) {
 
 // "tmem" variant: geometry, or false if the shape does not qualify (fp32 rows read through TMA: D % 4 == 0
 // and a 16-byte aligned base; more than one 128-row tile so that a CTA pair has work).
-bool plan_tmem(const void* z, int z_dtype, int64_t N, int K, int D, TmeParams* R) {
+bool plan_tmem(const void* z, int z_dtype, int64_t N, int K, int D, int a_bufs, TmeParams* R) {
   const int Dp = round_up(D, 16);
   if (z_dtype != G2V_F32 || D % 4 != 0 || (reinterpret_cast<uintptr_t>(z) & 15) != 0) return false;
   if (N <= TM || Dp > kMaxDp || Dp < KC) return false;
-  const int acc_col0 = round_up(Dp / 2, 16);
+  // a_bufs == 2: the fp16 rows of the next tile are converted while the MMAs still read this one's; what is
+  // left of tensor memory holds two (then much narrower) accumulator stages
+  const int acc_col0 = round_up(a_bufs * (Dp / 2), 16);
+  if (512 - acc_col0 < 2 * 32) return false;
   const int nt_max = std::min(256, ((512 - acc_col0) / 2) & ~15);
   int best_nt = 0, best_n = 1 << 30, best_pad = 1 << 30, best_last = 0;
   for (int nt = nt_max; nt >= 32 && nt >= nt_max - 64; nt -= 16) {
@@ -2164,12 +2321,13 @@ bool plan_tmem(const void* z, int z_dtype, int64_t N, int K, int D, TmeParams* R
   R->n_full = Dp / KC; R->n_tail = (Dp % KC) / KT; R->n_chunks = R->n_full + R->n_tail;
   if (R->n_chunks > MAX_CHUNKS) return false;
   R->ntile = best_nt; R->n_ntiles = best_n; R->n_last = best_last; R->Kpad = best_pad;
-  R->acc_col0 = acc_col0;
+  R->a_bufs = a_bufs; R->acc_col0 = acc_col0;
   R->n_ksteps = Dp / KT;
   R->b_stage = (uint32_t)round_up((best_nt / 2) * (std::min(2, R->n_full) * KC + R->n_tail * KT) * 2, 1024);
   R->n_row_tiles = (int)((N + 2 * TM - 1) / (2 * TM));
-  // codebook ring: ~1.5 us of L2 latency at 288 MMA cycles per full panel; the rest goes to the row slots
-  int nb = 5;
+  // codebook ring: ~1.5 us of L2 latency at 288 MMA cycles per full panel of 144 codes (~105 KB in flight,
+  // whatever the stage size); the rest goes to the row slots
+  int nb = std::max(5, std::min(TME_MAX_BST, (int)((5u * 21504u + R->b_stage - 1) / R->b_stage)));
   if (const char* env = getenv("G2V_TC_BSTAGES")) nb = std::max(2, std::min(TME_MAX_BST, atoi(env)));
   int nz = TME_MAX_ZSLOTS;
   if (const char* env = getenv("G2V_TC_ZSLOTS")) nz = std::max(2, std::min(TME_MAX_ZSLOTS, atoi(env)));
@@ -2230,7 +2388,14 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
     TmeParams R;
     const char* env = getenv("G2V_TC_TMEM");
     const int mode = env ? atoi(env) : 1;
-    if (mode != 0 && plan_tmem(z, z_dtype, N, K, D, &R) && (mode == 2 || R.n_ntiles <= 4)) {
+    bool use = mode != 0 && plan_tmem(z, z_dtype, N, K, D, 1, &R) && (mode == 2 || R.n_ntiles <= 4);
+    if (use) {      // G2V_TC_ABUFS=1|2: single / double A operand buffer
+      int a_bufs = kTmeDefaultABufs;
+      if (const char* ab = getenv("G2V_TC_ABUFS")) a_bufs = atoi(ab) == 2 ? 2 : 1;
+      TmeParams R2;
+      if (a_bufs == 2 && plan_tmem(z, z_dtype, N, K, D, 2, &R2)) R = R2;
+    }
+    if (use) {
       R.hdr = hdr; R.e2 = e2; R.idx = idx;
       R.ntab = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_tab_offset());
       R.pair_list = pairs; R.full_list = fulls; R.chain_list = chains; R.counters = counters; R.flags = flags;
