@@ -13,6 +13,8 @@
 // g2v_tc.cu.
 #include "g2v_common.cuh"
 
+#include <stdlib.h>
+
 #include <float.h>
 #include <math.h>
 
@@ -574,6 +576,128 @@ __global__ void __launch_bounds__(APPLY_WARPS * 32) apply_kernel(
   }
 }
 
+// Same pass with the EMA sums aggregated before they reach memory.  A warp takes 32 consecutive rows, sorts
+// their (code, row) pairs with a shuffle network and walks the rows code by code: the residuals of a run of
+// rows with the same code are summed in registers and leave as ONE vector reduction per run (and the code
+// is fetched once per run).  Usage is Zipf-like in practice, so the hot codes -- the ones whose per-row
+// atomics serialise in L2 -- collapse the most.  Lane l owns the float4 columns l, l+32, l+64, l+96 of a row
+// (D % 4 == 0, D <= 512).
+constexpr int RUNS_MAX_D = 512;
+
+__device__ __forceinline__ unsigned warp_sort_u32(unsigned v, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const unsigned o = __shfl_xor_sync(0xffffffffu, v, j);
+      const bool up = ((lane & k) == 0) == ((lane & j) == 0);     // keep the smaller of the pair?
+      v = up ? min(v, o) : max(v, o);
+    }
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(APPLY_WARPS * 32) apply_runs_kernel(
+    const float* __restrict__ x, const float* __restrict__ zs, const float* __restrict__ E,
+    const int* __restrict__ idx, long long N, int K, int D, float* __restrict__ out, double* sse,
+    int* counts, float* dwr, int dwr_replicas, int use_hist) {
+  extern __shared__ int hist[];
+  __shared__ double wsum[APPLY_WARPS];
+  dwr += (size_t)(blockIdx.x % dwr_replicas) * K * D;               // this block's private copy
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (use_hist) {
+    for (int k = threadIdx.x; k < K; k += blockDim.x) hist[k] = 0;
+    __syncthreads();
+  }
+  const int nq = D >> 2;                                            // float4 columns per row
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float acc = 0.f;
+  const long long stride = (long long)gridDim.x * APPLY_WARPS * 32;
+  for (long long base = ((long long)blockIdx.x * APPLY_WARPS + warp) * 32; base < N; base += stride) {
+    const int nvalid = (int)min((long long)32, N - base);
+    int k = K;                                                      // rows past the end sort last
+    if (lane < nvalid) {
+      k = min(max(__ldg(idx + base + lane), 0), K - 1);
+      if (counts) {
+        if (use_hist) atomicAdd(&hist[k], 1);
+        else atomicAdd(counts + k, 1);
+      }
+    }
+    const unsigned key = warp_sort_u32(((unsigned)k << 5) | (unsigned)lane, lane);
+    float4 a[4], ev[4], xn[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = ev[u] = zero4;
+    int cur = -1;
+    auto load_row = [&](const float* src, int i, float4 (&v)[4]) {
+      const unsigned ki = __shfl_sync(0xffffffffu, key, i);
+      const float* r = src + (size_t)(base + (ki & 31u)) * D;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (lane + 32 * u < nq) ? ldg4(r + 4 * (lane + 32 * u)) : zero4;
+    };
+    auto flush = [&]() {
+      float* drow = dwr + (size_t)cur * D;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (lane + 32 * u < nq) red_add_v4(drow + 4 * (lane + 32 * u), a[u].x, a[u].y, a[u].z, a[u].w);
+    };
+    load_row(x, 0, xn);
+    for (int i = 0; i < nvalid; ++i) {
+      const unsigned ki = __shfl_sync(0xffffffffu, key, i);
+      const int code = (int)(ki >> 5);
+      const long long row = base + (ki & 31u);
+      float4 xv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) xv[u] = xn[u];
+      if (i + 1 < nvalid) load_row(x, i + 1, xn);                   // next row in flight while this one is summed
+      if (code != cur) {                                            // warp-uniform
+        if (cur >= 0) flush();
+        cur = code;
+        const float* er = E + (size_t)code * D;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          ev[u] = (lane + 32 * u < nq) ? ldg4(er + 4 * (lane + 32 * u)) : zero4;
+          a[u] = zero4;
+        }
+      }
+      float4 zv[4];
+      if (zs) load_row(zs, i, zv);
+      float* orow = out ? out + (size_t)row * D : nullptr;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 d = make_float4(ev[u].x - xv[u].x, ev[u].y - xv[u].y, ev[u].z - xv[u].z, ev[u].w - xv[u].w);
+        acc = fmaf(d.x, d.x, acc); acc = fmaf(d.y, d.y, acc);
+        acc = fmaf(d.z, d.z, acc); acc = fmaf(d.w, d.w, acc);
+        if (orow && lane + 32 * u < nq)
+          __stcs(reinterpret_cast<float4*>(orow + 4 * (lane + 32 * u)),
+                 make_float4(xv[u].x + d.x, xv[u].y + d.y, xv[u].z + d.z, xv[u].w + d.w));
+        if (zs) {
+          a[u].x += zv[u].x - ev[u].x; a[u].y += zv[u].y - ev[u].y;
+          a[u].z += zv[u].z - ev[u].z; a[u].w += zv[u].w - ev[u].w;
+        } else {
+          a[u].x -= d.x; a[u].y -= d.y; a[u].z -= d.z; a[u].w -= d.w;
+        }
+      }
+    }
+    if (cur >= 0) flush();
+  }
+  if (sse) {
+    double s = warp_sum((double)acc);
+    if (lane == 0) wsum[warp] = s;
+  }
+  __syncthreads();
+  if (sse && threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < APPLY_WARPS; ++w) s += wsum[w];
+    atomicAdd(sse, s);
+  }
+  if (use_hist && counts) {
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      int v = hist[k];
+      if (v) atomicAdd(counts + k, v);
+    }
+  }
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(256) backward_kernel(const float* __restrict__ x, const float* __restrict__ E,
                                                        const int* __restrict__ idx,
@@ -914,6 +1038,15 @@ int launch_apply(const float* x, const float* zs, const float* E, const int32_t*
   const int use_hist = (counts && K <= 8192) ? 1 : 0;
   const size_t smem = use_hist ? (size_t)K * sizeof(int) : 0;
   const int grid = grid_for(N, APPLY_WARPS, 8);
+  // EMA / codebook-gradient sums wanted: aggregate runs of equal codes in registers first (G2V_APPLY_RUNS=0:
+  // one reduction per row, the older kernel)
+  static const bool runs_on = [] { const char* e = getenv("G2V_APPLY_RUNS"); return !(e && atoi(e) == 0); }();
+  if (vec && dwr && D <= RUNS_MAX_D && runs_on) {
+    const int g = grid_for((N + 31) / 32, APPLY_WARPS, 8);
+    apply_runs_kernel<<<g, APPLY_WARPS * 32, smem, st>>>(x, zs, E, idx, N, K, D, out, sse, counts, dwr, dwr_replicas, use_hist);
+    G2V_LAUNCH_CHECK("apply_runs_kernel");
+    return G2V_OK;
+  }
   if (vec)
     apply_kernel<true><<<grid, APPLY_WARPS * 32, smem, st>>>(x, zs, E, idx, N, K, D, out, sse, counts, dwr, dwr_replicas, use_hist);
   else
