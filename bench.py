@@ -364,7 +364,11 @@ def main():
                     "whole_step_achieved": flops_per_row / sec_per_row_step / 1e12}
         roof["frac"] = roof["achieved"] / roof["peak"]
         roof["whole_step_frac"] = roof["whole_step_achieved"] / roof["peak"]
-        roof["traffic"] = TRAFFIC_NOTE.get((a.workload, K))
+        tn = TRAFFIC_NOTE.get((a.workload, K))
+        # valid only for the captured configuration (same rows / dtype / kernel); scaled to this launch's rows
+        roof["traffic"] = (tn["dram_bytes_per_launch"] * N / tn["rows"]
+                           if tn and tn["dtype"] == a.dtype and tmem_variant(a.dtype, N, K, D) else None)
+        roof["traffic_source"] = tn["source"] if roof["traffic"] is not None else None
         roof["peak_source"] = pk["src"] + (" (sustained bf16)" if roof["bound"] == "tensor" else " (copy)")
         roof["algorithmic_per_chunk"] = {"search_bytes": search_bytes_per_row, "step_bytes": bytes_per_row,
                                          "flops": flops_per_row}
@@ -391,7 +395,12 @@ def main():
 
 # dram__bytes_read+write per launch of the dominant kernel from the committed `ncu --set full`
 # captures under profiles/ (None where no capture exists for that workload)
-TRAFFIC_NOTE = {}
+TRAFFIC_NOTE = {
+    # tc_tmem_kernel, 1M fp32 rows, K=400: 1.6006 GB read + 0.0093 GB written (profiles/r1_ncu_full_tc_tmem_k400.csv)
+    # against 1.604 GB algorithmic -- every row is read from DRAM exactly once, the codebook stays in L2
+    ("tokenize", 400): {"dram_bytes_per_launch": 1.6099e9, "rows": 1_000_000, "dtype": "f32",
+                        "source": "profiles/r1_ncu_full_tc_tmem_k400.csv"},
+}
 
 
 def tmem_variant(dtype, N, K, D):
@@ -406,10 +415,12 @@ def tmem_variant(dtype, N, K, D):
 
 def launches_estimate(a, path):
     """Kernels of ours launched per step (counted from the launch sites in csrc/)."""
+    # (checked against the ncu launch lists under profiles/)
     # simt: fp32 sweep + per-row fp64 re-rank + batched re-rank (lists longer than 4096 rows)
-    # tc:   [row_prep unless fp32 rows and K <= 512] + tcgen05 sweep + candidate / chain / per-row / batched re-rank
+    # tc:   [row_prep unless the fp32 rows are converted inside the sweep] + tcgen05 sweep + rerank_kernel
+    #       (candidate / chain / whole-row lists) + batched re-rank of an overflowing whole-row list
     fused = a.dtype == "f32" and (a.codes <= 512 or tmem_variant(a.dtype, a.rows, a.codes, 400))
-    search = 3 if path.startswith("simt") else (5 if fused else 6)
+    search = 3 if (path.startswith("simt") or fused) else 4
     if a.workload == "tokenize":
         return search
     # train: search + apply + pack + finalize + ema(2) + codebook prep(3) + backward

@@ -11,4 +11,7 @@ from .quantizers import (DAE_VQ_Payam, DAE_VQ_Payam_EMA, VQVAE_VQ_Payam, VQVAE_V
 from .reference_patch import patch_reference, unpatch_reference, swap_vq_layer  # noqa: F401
 from .distributed import shard_rows, StatsAllReduce, enable_data_parallel_ema, packed_layout  # noqa: F401
 
+from .kmeans import KMeans, kmeans_update  # noqa: F401
+from .tokenizer import GestureTokenizer, chunk_rows_from_hidden  # noqa: F401
+
 __version__ = "0.1.0"

@@ -37,6 +37,7 @@ SIGNATURES = {
     "g2v_vq_ema_update": (_i, [_p, _p, _p, _p, _p, _f, _f, _i, _i, _p, _sz, _p]),
     "g2v_vq_backward": (_i, [_p, _p, _p, _p, _p, _f, _i64, _i, _i, _p, _p]),
     "g2v_vq_grad_codebook": (_i, [_p, _p, _f, _i, _i, _p, _p]),
+    "g2v_kmeans_update": (_i, [_p, _p, _i, _i, _p, _p, _p, _sz, _p]),
     "g2v_onehot": (_i, [_p, _i64, _i, _p, _p]),
     "g2v_tokenize_host_bytes": (_sz, [_i64, _i, _i, _i, _u]),
     "g2v_tokenize_host": (_i, [_p, _i, _i64, _p, _p, _i, _i, _p, _i64, _p, _p, _sz, _u]),

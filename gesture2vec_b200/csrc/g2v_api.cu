@@ -196,6 +196,16 @@ int g2v_vq_grad_codebook(const float* packed_dwr, const float* g_loss, float coe
   return launch_grad_codebook(packed_dwr, g_loss, coef_e, K, D, g_E, (cudaStream_t)stream);
 }
 
+int g2v_kmeans_update(const float* E_old, const float* packed, int K, int D, float* E_new, double* shift2,
+                      void* cb, size_t cb_bytes, void* stream) {
+  if (K <= 0 || D <= 0 || !E_old || !packed || !E_new) return G2V_ERR_INVALID;
+  if (cb && cb_bytes < cb_total_bytes(K, D)) return G2V_ERR_WORKSPACE;
+  int rc = launch_kmeans_update(E_old, packed, K, D, E_new, shift2, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (cb) rc = launch_codebook_prepare(E_new, K, D, cb, (cudaStream_t)stream);
+  return rc;
+}
+
 int g2v_onehot(const int32_t* idx, int64_t N, int K, float* enc, void* stream) {
   if (N < 0 || K <= 0 || (N > 0 && (!idx || !enc))) return G2V_ERR_INVALID;
   if (N == 0) return G2V_OK;

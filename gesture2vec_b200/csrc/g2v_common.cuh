@@ -103,6 +103,8 @@ int launch_stats_finalize(const float* packed, int K, int D, float coef_codebook
                           float* loss, float* ppl, cudaStream_t st);
 int launch_ema_update(float* cs, float* ema_w, const float* E_old, float* E_new, const float* packed,
                       float decay, float eps, int K, int D, cudaStream_t st);
+int launch_kmeans_update(const float* E_old, const float* packed, int K, int D, float* E_new, double* shift2,
+                         cudaStream_t st);
 int launch_backward(const float* x, const float* E, const int32_t* idx, const float* g_out,
                     const float* g_loss, float coef_x, int64_t N, int K, int D, float* g_x,
                     cudaStream_t st);

@@ -816,6 +816,31 @@ __global__ void ema_w_kernel(const float* __restrict__ cs, float* __restrict__ e
   }
 }
 
+// Lloyd M-step from the packed statistics of an assignment pass: centre k moves to the mean of its rows,
+// E[k] + dwr[k] / counts[k] (residual form: no cancellation); an empty cluster keeps its centre.
+// shift2 accumulates sum_k ||E_new[k] - E_old[k]||^2 (the convergence test of sklearn's Lloyd loop).
+__global__ void __launch_bounds__(256) kmeans_update_kernel(const float* __restrict__ E_old, const float* __restrict__ packed,
+                                                            int K, int D, float* __restrict__ E_new, double* shift2) {
+  __shared__ double sh[8];
+  const float* counts = packed + (size_t)K * D;
+  const size_t total = (size_t)K * D;
+  double part = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const float c = counts[i / D];
+    const float step = c > 0.f ? __fdiv_rn(packed[i], c) : 0.f;
+    E_new[i] = __fadd_rn(E_old[i], step);
+    part += (double)step * (double)step;
+  }
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0 && shift2) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    atomicAdd(shift2, t);
+  }
+}
+
 __global__ void grad_codebook_kernel(const float* __restrict__ dwr, const float* __restrict__ g_loss,
                                      float coef_e, size_t total, float* __restrict__ g_E) {
   const float c = -__ldg(g_loss) * coef_e;
@@ -1071,6 +1096,13 @@ int launch_ema_update(float* cs, float* ema_w, const float* E_old, float* E_new,
   G2V_LAUNCH_CHECK("ema_cs_kernel");
   ema_w_kernel<<<grid_for((long long)K * D, 256, 8), 256, 0, st>>>(cs, ema_w, E_old, E_new, packed, decay, one_m, K, D);
   G2V_LAUNCH_CHECK("ema_w_kernel");
+  return G2V_OK;
+}
+
+int launch_kmeans_update(const float* E_old, const float* packed, int K, int D, float* E_new, double* shift2,
+                         cudaStream_t st) {
+  kmeans_update_kernel<<<grid_for((long long)K * D, 256, 8), 256, 0, st>>>(E_old, packed, K, D, E_new, shift2);
+  G2V_LAUNCH_CHECK("kmeans_update_kernel");
   return G2V_OK;
 }
 

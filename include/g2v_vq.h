@@ -150,6 +150,15 @@ int g2v_vq_backward(const float* x, const float* E, const int32_t* idx, const fl
 int g2v_vq_grad_codebook(const float* packed_dwr, const float* g_loss, float coef_e,
                          int K, int D, float* g_E, void* stream);
 
+/* Lloyd M-step of k-means on the statistics of an assignment pass (g2v_vq_search + g2v_vq_apply with dwr +
+ * g2v_vq_stats_pack, all-reduced across ranks if the rows are sharded): E_new[k] = E_old[k] + dwr[k]/counts[k],
+ * a cluster without rows keeps its centre; *shift2 (optional, double, accumulated) += ||E_new - E_old||_F^2.
+ * Replaces the centre update inside sklearn.cluster.KMeans(...).fit as the reference calls it on gesture
+ * latents (Clustering.py:718-720, train_DAE.py:257-263; sklearn is a third-party dependency of the
+ * reference, requirements.txt).  E_new == E_old is allowed; if cb != NULL the aux buffer is re-prepared. */
+int g2v_kmeans_update(const float* E_old, const float* packed, int K, int D, float* E_new, double* shift2,
+                      void* cb, size_t cb_bytes, void* stream);
+
 /* encodings = one_hot(idx) as a dense fp32 [N,K] (DAE_model.py:328-331); the reference
  * returns it and callers argmax it (Clustering.py:156, lmdb_data_loader.py:1281). */
 int g2v_onehot(const int32_t* idx, int64_t N, int K, float* enc, void* stream);
