@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="tokenize", choices=["tokenize", "train"])
+    ap.add_argument("--workload", default="tokenize", choices=["tokenize", "train", "kmeans"])
     ap.add_argument("--rows", type=int, default=1_000_000, help="rows (chunks) per GPU per step")
     ap.add_argument("--codes", type=int, default=400, help="codebook size K (GENEA 400, Trinity 512)")
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
@@ -122,7 +122,15 @@ def cpu_reference_rate(workload: str, K: int, D: int, budget_s: float, block: in
     g = torch.Generator().manual_seed(1234)
     z = torch.randn(block, D, generator=g)
     torch.manual_seed(0)
-    if workload == "tokenize":
+    if workload == "kmeans":
+        # the reference's k-means IS sklearn (Clustering.py:718): one Lloyd iteration = max_iter=1 from a fixed init
+        from sklearn.cluster import KMeans as SkKMeans
+        zn = z.numpy()
+        init = zn[:K].copy()
+
+        def step():
+            return SkKMeans(n_clusters=K, init=init, n_init=1, max_iter=1, tol=0.0, algorithm="lloyd").fit(zn)
+    elif workload == "tokenize":
         mod = P.PortVQ(K, D, 0.25).eval()
         with torch.no_grad():
             mod._embedding.weight.normal_()
@@ -152,6 +160,10 @@ def cpu_reference_rate(workload: str, K: int, D: int, budget_s: float, block: in
             break
     times.sort()
     med = times[len(times) // 2]
+    if workload == "kmeans":      # fit(max_iter=1) = one Lloyd iteration + the final assignment pass: two passes over the rows
+        return dict(value=2 * block / med, unit=UNIT, cores=cores, kind="reference",
+                    sample=f"{len(times)} x sklearn KMeans(max_iter=1).fit on one {block}-row block (K={K}, D={D}, fp32): "
+                           f"2 passes over the rows per fit, median; sklearn {__import__('sklearn').__version__}")
     return dict(value=block / med, unit=UNIT, cores=cores, kind="port",
                 sample=f"{len(times)} passes over one {block}-row block of the same synthetic workload "
                        f"(K={K}, D={D}, fp32), median; torch {torch.__version__} CPU, {torch.get_num_threads()} threads")
@@ -168,7 +180,13 @@ def run_reference_arm(a):
     torch.set_num_threads(cores)
     g = torch.Generator().manual_seed(1234)
     z = torch.randn(block, D, generator=g)
-    if a.workload == "tokenize":
+    passes = 1
+    if a.workload == "kmeans":
+        from sklearn.cluster import KMeans as SkKMeans
+        zn, passes = z.numpy(), 2
+        init = zn[:K].copy()
+        fn = lambda: SkKMeans(n_clusters=K, init=init, n_init=1, max_iter=1, tol=0.0, algorithm="lloyd").fit(zn)   # noqa: E731
+    elif a.workload == "tokenize":
         mod = P.PortVQ(K, D, 0.25).eval()
         with torch.no_grad():
             mod._embedding.weight.normal_()
@@ -187,7 +205,7 @@ def run_reference_arm(a):
     for _ in range(a.steps):
         fn()
     dt = time.perf_counter() - t0
-    val = block * a.steps / dt
+    val = passes * block * a.steps / dt
     sample = (f"each step = one {block}-row block (bounded sample of the {a.rows}-row workload), "
               f"reference quantizer ops on CPU via oracle/torch_port.py (the Python reference cannot travel)")
     print(json.dumps({
@@ -202,12 +220,13 @@ def run_reference_arm(a):
 
 def workload_config(a, world, path):
     name = ("config/VQ-VAE_GENEA.yml full-dataset tokenization" if a.codes == 400 else
-            f"tokenization K={a.codes}") if a.workload == "tokenize" else \
-        f"VQ-VAE EMA training step (fwd+bwd+EMA) K={a.codes}"
+            f"tokenization K={a.codes}") if a.workload == "tokenize" else (
+        f"k-means Lloyd iteration (assign + centre update) K={a.codes}" if a.workload == "kmeans" else
+        f"VQ-VAE EMA training step (fwd+bwd+EMA) K={a.codes}")
     return {"workload": name, "codes_K": a.codes, "latent_dim_D": D_LATENT, "rows_per_gpu": a.rows,
             "rows_total": a.rows * world, "latent_dtype": a.dtype, "sharding": f"rows x{world}, codebook replicated",
             "search_path": path, "l2_policy": "inputs larger than L2 (rows*D*bytes >> 126 MB)",
-            "latents": "iid N(0,1) (worst case for near-ties)" if a.workload == "tokenize" else
+            "latents": "iid N(0,1) (worst case for near-ties)" if a.workload in ("tokenize", "kmeans") else
                        "clustered: E[c] + 0.1*N(0,1), c ~ Zipf(1.1)"}
 
 
@@ -250,6 +269,28 @@ def main():
         def step():
             g2v.vq_search(z, E, cb, flags=flags, stats=stats, out=idx)
         bytes_per_row = D * z.element_size() + 4
+        launches_per_step = None
+    elif a.workload == "kmeans":
+        # one Lloyd iteration per step: assignment (search), residual sums + counts (apply, no output rows),
+        # all-reduce of the packed statistics when sharded, centre update + codebook aux refresh
+        from gesture2vec_b200.kmeans import kmeans_update
+        zf = z.float()
+        Ek = zf[:K].clone()
+        Ek2 = torch.empty_like(Ek)
+        cbk = g2v.prepare_codebook(Ek)
+        kidx = torch.empty(N, dtype=torch.int32, device=dev)
+        red = g2v.StatsAllReduce() if world > 1 else None
+        state = {"E": Ek, "E2": Ek2}
+
+        def step():
+            E0, E1 = state["E"], state["E2"]
+            g2v.vq_search(z, E0, cbk, flags=flags, stats=stats, out=kidx)
+            _, packed = g2v.vq_apply(zf, E0, kidx, want_out=False, want_stats=True, want_dwr=True)
+            if red is not None:
+                red(packed)
+            kmeans_update(E0, packed, E1, None, cbk)
+            state["E"], state["E2"] = E1, E0
+        bytes_per_row = D * z.element_size() + 4 + D * 4 + 4      # search pass + statistics pass
         launches_per_step = None
     else:
         layer = g2v.DAE_VQ_Payam_EMA(K, D, 0.25, 0.85).to(dev).train()
@@ -328,6 +369,24 @@ def main():
                "h2d_bytes_per_step": N * D * z.element_size(), "d2h_bytes_per_step": N * 4,
                "steps": e_steps, "api": "g2v_tokenize_host (pinned host rows -> host int32 ids)"}
         assert torch.equal(ih, idx.cpu()), "host path and device path disagree"
+    elif a.workload == "kmeans" and not a.no_e2e:
+        zh = torch.empty(N, D, dtype=torch.float32, pin_memory=True).copy_(z.float())
+        init = zh[:K].numpy().copy()
+        iters = 4
+        kw = dict(n_clusters=K, init=init, max_iter=iters, tol=0.0, device=dev,
+                  stats_reduce=g2v.StatsAllReduce() if world > 1 else None,
+                  count_reduce=(lambda t: dist.all_reduce(t)) if world > 1 else None)
+        g2v.KMeans(**kw).fit(zh)                 # untimed: first-use allocations
+        barrier()
+        t0 = time.perf_counter()
+        km = g2v.KMeans(**kw).fit(zh)            # labels_ come back to the host
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": N * world * (km.n_iter_ + 1) / float(dt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": N * D * 4, "d2h_bytes_per_step": N * 4 + K * D * 4, "steps": 1,
+               "api": f"KMeans.fit(host rows), {km.n_iter_} Lloyd iterations + final assignment; rows copied once"}
     elif a.workload == "train" and not a.no_e2e:
         zh = torch.empty(N, D, dtype=torch.float32, pin_memory=True).copy_(z.float())
         e_steps = 3
@@ -423,6 +482,8 @@ def launches_estimate(a, path):
     search = 3 if (path.startswith("simt") or fused) else 4
     if a.workload == "tokenize":
         return search
+    if a.workload == "kmeans":      # search + apply + pack + centre update + codebook prep(3)
+        return search + 1 + 1 + 1 + 3
     # train: search + apply + pack + finalize + ema(2) + codebook prep(3) + backward
     return search + 1 + 1 + 1 + 2 + 3 + 1
 

@@ -1,4 +1,1 @@
-timeout 200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 60 python bench.py --workload train --codes 512 --no-cpu-baseline --no-e2e --steps 10 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('runs=1 train512 ms/step', d['ms_per_step'], 'value', d['value'])"
-G2V_APPLY_RUNS=0 timeout 60 python bench.py --workload train --codes 512 --no-cpu-baseline --no-e2e --steps 10 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('runs=0 train512 ms/step', d['ms_per_step'], 'value', d['value'])"
-timeout 100 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches_train512.csv python bench.py --workload train --codes 512 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > /dev/null 2>&1; echo ncu rc=$?
+timeout 200 python -m pytest tests/test_gpu_dist.py -q 2>&1 | grep -v "^$" | tail -45
