@@ -432,7 +432,7 @@ def main():
         roof["algorithmic_per_chunk"] = {"search_bytes": search_bytes_per_row, "step_bytes": bytes_per_row,
                                          "flops": flops_per_row}
         roof["kernel"] = "search_simt_kernel" if path.startswith("simt") else (
-            "tc_tmem_kernel (tcgen05 sweep, fp32 rows -> TMEM operand)" if tmem_variant(a.dtype, N, K, D)
+            f"tc_tmem_kernel (tcgen05 sweep, {a.dtype} rows -> fp16 operand in TMEM)" if tmem_variant(a.dtype, N, K, D)
             else "tc_search_kernel (tcgen05 sweep)")
         roof["kernel_ms_per_launch"] = kernel_ms
         roof["kernel_share_of_step"] = kernel_ms / ms_step
@@ -463,8 +463,8 @@ TRAFFIC_NOTE = {
 
 
 def tmem_variant(dtype, N, K, D):
-    """Mirror of plan_tmem() in csrc/g2v_tc.cu: fp32 rows and at most four code tiles."""
-    if dtype != "f32" or D % 4 or N <= 128 or D < 64:
+    """Mirror of plan_tmem() in csrc/g2v_tc.cu: rows readable by TMA and at most four code tiles."""
+    if D % (4 if dtype == "f32" else 8) or N <= 128 or D < 64:
         return False
     dp = (D + 15) // 16 * 16
     acc0 = (dp // 2 + 15) // 16 * 16
@@ -478,7 +478,7 @@ def launches_estimate(a, path):
     # simt: fp32 sweep + per-row fp64 re-rank + batched re-rank (lists longer than 4096 rows)
     # tc:   [row_prep unless the fp32 rows are converted inside the sweep] + tcgen05 sweep + rerank_kernel
     #       (candidate / chain / whole-row lists) + batched re-rank of an overflowing whole-row list
-    fused = a.dtype == "f32" and (a.codes <= 512 or tmem_variant(a.dtype, a.rows, a.codes, 400))
+    fused = tmem_variant(a.dtype, a.rows, a.codes, 400) or (a.dtype == "f32" and a.codes <= 512)
     search = 3 if (path.startswith("simt") or fused) else 4
     if a.workload == "tokenize":
         return search

@@ -23,6 +23,7 @@
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace g2v {
 namespace {
@@ -404,8 +405,9 @@ __device__ __forceinline__ void epi8(const uint32_t (&v)[8], const float4 e0, co
 // One code tile of one epilogue warp: its 16-column pieces g0 .. g1-1 (codes [32 g + 16 eh, +16)), software-pipelined
 // in halves of 8 columns -- while one half is turned into keys, the tensor-memory load and the ||e||^2 loads
 // of the next half are in flight.  tcol0 / e2addr0 address code 16 eh (tensor-memory column, shared-memory byte).
+// The key's column-group field is group0 + g.
 __device__ __forceinline__ void epi_sweep(uint32_t tcol0, uint32_t e2addr0, int g0, int g1, int e_valid, int eh, float cS, float S,
-                                          bool skip, uint32_t (&m1)[16], uint32_t (&m2)[16]) {
+                                          uint32_t group0, bool skip, uint32_t (&m1)[16], uint32_t (&m2)[16]) {
   if (g0 >= g1) return;
   uint32_t va[8], vb[8];
   tc_ld8(tcol0 + 32u * g0, va);
@@ -417,8 +419,8 @@ __device__ __forceinline__ void epi_sweep(uint32_t tcol0, uint32_t e2addr0, int 
     eb0 = lds4(e2addr0 + 128u * g + 32u);
     eb1 = lds4(e2addr0 + 128u * g + 48u);
     if (!skip) {
-      if (nv >= 8) epi8<0, false>(va, ea0, ea1, cS, S, (uint32_t)g, 8, m1, m2);
-      else epi8<0, true>(va, ea0, ea1, cS, S, (uint32_t)g, nv, m1, m2);
+      if (nv >= 8) epi8<0, false>(va, ea0, ea1, cS, S, group0 + (uint32_t)g, 8, m1, m2);
+      else epi8<0, true>(va, ea0, ea1, cS, S, group0 + (uint32_t)g, nv, m1, m2);
     }
     tc_wait_ld();
     if (g + 1 < g1) {
@@ -427,8 +429,8 @@ __device__ __forceinline__ void epi_sweep(uint32_t tcol0, uint32_t e2addr0, int 
       ea1 = lds4(e2addr0 + 128u * (g + 1) + 16u);
     }
     if (!skip) {
-      if (nv >= 16) epi8<8, false>(vb, eb0, eb1, cS, S, (uint32_t)g, 8, m1, m2);
-      else epi8<8, true>(vb, eb0, eb1, cS, S, (uint32_t)g, nv - 8, m1, m2);
+      if (nv >= 16) epi8<8, false>(vb, eb0, eb1, cS, S, group0 + (uint32_t)g, 8, m1, m2);
+      else epi8<8, true>(vb, eb0, eb1, cS, S, group0 + (uint32_t)g, nv - 8, m1, m2);
     }
   }
 }
@@ -780,26 +782,10 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (warp == EPI_WARP0) TRACE(3, 200 + nt);
         tc_fence_after();
         const int ncols = min(TN, P.K - nt * TN);
-        const int nch = (ncols + 31) >> 5;
+        // pieces of 16 columns at code 32 ch + 16 eh of this tile; ||e||^2 of the tile staged in e2c
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * TN + eh * 16;
-        uint32_t va[16], vb[16];
-        tc_ld16(taddr, va);
-        for (int ch = 0; ch < nch; ch += 2) {
-          tc_wait_ld();
-          if (ch + 1 < nch) tc_ld16(taddr + (ch + 1) * 32, vb);
-          if (!(P.flags & kDbgSkipEpi)) {
-            const int nv = ncols - ch * 32 - eh * 16;
-            if (nv >= 16) epi_chunk<false>(va, e2c + ch * 32 + eh * 16, ri.cS, ri.S, (uint32_t)(nt * 8 + ch), 16, m1, m2);
-            else epi_chunk<true>(va, e2c + ch * 32 + eh * 16, ri.cS, ri.S, (uint32_t)(nt * 8 + ch), nv, m1, m2);
-          }
-          if (ch + 1 < nch) {
-            tc_wait_ld();
-            if (ch + 2 < nch) tc_ld16(taddr + (ch + 2) * 32, va);
-            const int nv = (P.flags & kDbgSkipEpi) ? -1000 : ncols - (ch + 1) * 32 - eh * 16;
-            if (nv >= 16) epi_chunk<false>(vb, e2c + (ch + 1) * 32 + eh * 16, ri.cS, ri.S, (uint32_t)(nt * 8 + ch + 1), 16, m1, m2);
-            else epi_chunk<true>(vb, e2c + (ch + 1) * 32 + eh * 16, ri.cS, ri.S, (uint32_t)(nt * 8 + ch + 1), nv, m1, m2);
-          }
-        }
+        epi_sweep(taddr, smem_u32(e2c) + 64u * (uint32_t)eh, 0, (ncols - 16 * eh + 31) >> 5, ncols, eh, ri.cS, ri.S,
+                  (uint32_t)(nt * 8), (P.flags & kDbgSkipEpi) != 0, m1, m2);
         // all TMEM reads of this stage are complete (last wait::ld above): hand it back
         tc_fence_before();
         __syncwarp();
@@ -1495,6 +1481,21 @@ __host__ __device__ inline TmePlan tme_plan(int nb, uint32_t b_stage, int nz, in
   return p;
 }
 
+// four consecutive 16-bit row elements (8 bytes of a staging slot) as fp32
+template <typename ZT>
+__device__ __forceinline__ float4 unpack16(const uint2 u) {
+  if constexpr (sizeof(ZT) == 4) {
+    return make_float4(0.f, 0.f, 0.f, 0.f);      // not used for fp32 rows
+  } else if constexpr (std::is_same<ZT, __half>::value) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  } else {
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16),
+                       __uint_as_float(u.y & 0xFFFF0000u));
+  }
+}
+
+template <typename ZT>
 __global__ void __launch_bounds__(TME_THREADS, 1)
 tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmZt,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBt,
@@ -1528,6 +1529,7 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
   auto bar_rsfull = [&](int s) { return bars + 8u * (A0 + 6 * MAX_CHUNKS + 4 + s); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + sp.tmem_off);
 
+  constexpr bool Z32 = sizeof(ZT) == 4;     // fp32 rows; otherwise bf16 / fp16 rows
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_chunks = P.n_chunks, n_full = P.n_full;
   auto acc_col_of = [&](uint32_t a) { return (uint32_t)P.acc_col0 + a * (uint32_t)P.ntile; };   // accumulator stage a
@@ -1662,19 +1664,20 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
     for (int tile = group; tile < P.n_row_tiles; tile += n_groups) {
       const long long r0 = ((long long)tile * 2 + cta_rank) * TM;
       const int row0 = (int)(r0 < P.N ? r0 : P.N - 1);       // a tile past the end reads (and ignores) the last row
-      const int n_slots = 2 * n_full + P.n_tail;
+      // a slot = 128 rows x 128 bytes: 32 fp32 columns (two slots per 64-column panel) or 64 16-bit columns (one)
+      const int n_main = (Z32 ? 2 : 1) * n_full, n_slots = n_main + P.n_tail;
       for (int u = 0; u < n_slots; ++u) {
         mbar_wait(bar_zempty(slot), ph ^ 1u);
         TRACE(2, u);
         if (P.flags & kDbgNoZ) {
           if (elect_one()) mbar_arrive(bar_zfull(slot));
         } else if (elect_one()) {
-          if (u < 2 * n_full) {
+          if (u < n_main) {
             mbar_expect_tx(bar_zfull(slot), TME_ZSLOT);
-            tma_load_2d<1>(sZ + slot * TME_ZSLOT, &tmZ, u * TME_ZCOLS, row0, bar_zfull(slot));
+            tma_load_2d<1>(sZ + slot * TME_ZSLOT, &tmZ, u * (Z32 ? TME_ZCOLS : KC), row0, bar_zfull(slot));
           } else {
-            mbar_expect_tx(bar_zfull(slot), TM * KT * 4);
-            tma_load_2d<1>(sZ + slot * TME_ZSLOT, &tmZt, n_full * KC + (u - 2 * n_full) * KT, row0, bar_zfull(slot));
+            mbar_expect_tx(bar_zfull(slot), TM * KT * (uint32_t)sizeof(ZT));
+            tma_load_2d<1>(sZ + slot * TME_ZSLOT, &tmZt, n_full * KC + (u - n_main) * KT, row0, bar_zfull(slot));
           }
         }
         __syncwarp();
@@ -1713,7 +1716,7 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
         if (warp == EPI_WARP0) TRACE(3, 200 + nt);
         tc_fence_after();
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col_of(as) + (uint32_t)(16 * eh - s0);
-        epi_sweep(taddr0, e2_saddr, g0, g1, e_valid, eh, key_cS, key_S, (P.flags & kDbgSkipEpi) != 0, m1, m2);
+        epi_sweep(taddr0, e2_saddr, g0, g1, e_valid, eh, key_cS, key_S, 0u, (P.flags & kDbgSkipEpi) != 0, m1, m2);
         tc_fence_before();
         __syncwarp();
         if (warp == EPI_WARP0) TRACE(3, 300 + nt);
@@ -1791,7 +1794,46 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
           if (cw == 0) TRACE(4, 200 + sc);
           tc_fence_after();
         }
-        if (c < n_full) {
+        if (!Z32 && c < n_full) {
+          // 16-bit rows: one slot per panel, a row is 64 elements = 128 bytes (SWIZZLE_128B); K step s of row r is
+          // the 16-byte chunks 2s, 2s+1 (xor r % 8); this lane takes 8 bytes (4 elements) of it
+          uint32_t w[16];
+          mbar_wait(bar_zfull(slot), ph);
+          const unsigned char* zs = gbase + sp.z_off + slot * TME_ZSLOT;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t sf = 2u * h + (odd ? 1u : 0u), ss = 2u * h + (odd ? 0u : 1u);   // odd rows: second K step first
+            const uint32_t of = (uint32_t)ra_l * 128u + (((2u * sf + (kq >> 1)) ^ sw) << 4) + 8u * (kq & 1u);
+            const uint32_t os = (uint32_t)ra_l * 128u + (((2u * ss + (kq >> 1)) ^ sw) << 4) + 8u * (kq & 1u);
+            const uint2 af = *reinterpret_cast<const uint2*>(zs + of), bf = *reinterpret_cast<const uint2*>(zs + of + 8 * 128);
+            const uint2 as = *reinterpret_cast<const uint2*>(zs + os), bs = *reinterpret_cast<const uint2*>(zs + os + 8 * 128);
+            uint32_t f0, f1, f2, f3, s0, s1, s2, s3;
+            cvt(unpack16<ZT>(af), z2a, r2a, f0, f1);
+            cvt(unpack16<ZT>(bf), z2b, r2b, f2, f3);
+            cvt(unpack16<ZT>(as), z2a, r2a, s0, s1);
+            cvt(unpack16<ZT>(bs), z2b, r2b, s2, s3);
+            w[8 * h + 0] = odd ? s0 : f0; w[8 * h + 1] = odd ? s1 : f1;
+            w[8 * h + 2] = odd ? s2 : f2; w[8 * h + 3] = odd ? s3 : f3;
+            w[8 * h + 4] = odd ? f0 : s0; w[8 * h + 5] = odd ? f1 : s1;
+            w[8 * h + 6] = odd ? f2 : s2; w[8 * h + 7] = odd ? f3 : s3;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_zempty(slot));
+          if (++slot == NZ) { slot = 0; ph ^= 1u; }
+          tc_st_16x256b_x4(t_buf + 32u * c, w);
+        } else if (!Z32) {
+          mbar_wait(bar_zfull(slot), ph);
+          const unsigned char* zs = gbase + sp.z_off + slot * TME_ZSLOT;                 // tail slot: 32-byte rows, no swizzle
+          const uint32_t ot = (uint32_t)ra_l * 32u + kq * 8u;
+          const uint2 a0 = *reinterpret_cast<const uint2*>(zs + ot), b0 = *reinterpret_cast<const uint2*>(zs + ot + 8 * 32);
+          uint32_t w0, w1, w2, w3;
+          cvt(unpack16<ZT>(a0), z2a, r2a, w0, w1);
+          cvt(unpack16<ZT>(b0), z2b, r2b, w2, w3);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_zempty(slot));
+          if (++slot == NZ) { slot = 0; ph ^= 1u; }
+          tc_st_16x256b_x1(t_buf + 32u * n_full + 8u * (c - n_full), w0, w1, w2, w3);
+        } else if (c < n_full) {
           uint32_t w[16];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -2301,7 +2343,11 @@ int launch_resident(ResParams& R, const __half* e16, int Kp, cudaStream_t st) {
 // and a 16-byte aligned base; more than one 128-row tile so that a CTA pair has work).
 bool plan_tmem(const void* z, int z_dtype, int64_t N, int K, int D, int a_bufs, TmeParams* R) {
   const int Dp = round_up(D, 16);
-  if (z_dtype != G2V_F32 || D % 4 != 0 || (reinterpret_cast<uintptr_t>(z) & 15) != 0) return false;
+  // rows are read through TMA: 16-byte aligned base and row pitch (G2V_TC_TMEM16=0 keeps 16-bit rows on the
+  // row_prep + shared-memory-operand path)
+  static const bool tmem16 = [] { const char* e = getenv("G2V_TC_TMEM16"); return !(e && atoi(e) == 0); }();
+  if (z_dtype != G2V_F32 && !tmem16) return false;
+  if (D % (z_dtype == G2V_F32 ? 4 : 8) != 0 || (reinterpret_cast<uintptr_t>(z) & 15) != 0) return false;
   if (N <= TM || Dp > kMaxDp || Dp < KC) return false;
   // a_bufs == 2: the fp16 rows of the next tile are converted while the MMAs still read this one's; what is
   // left of tensor memory holds two (then much narrower) accumulator stages
@@ -2336,18 +2382,20 @@ bool plan_tmem(const void* z, int z_dtype, int64_t N, int K, int D, int a_bufs, 
   return tme_plan(nb, R->b_stage, nz, R->Kpad).total + 1024 <= 227 * 1024;
 }
 
-int launch_tmem(TmeParams& R, const float* z, const __half* e16, int Kp, cudaStream_t st) {
+template <typename ZT>
+int launch_tmem(TmeParams& R, const ZT* z, const __half* e16, int Kp, cudaStream_t st) {
   alignas(64) CUtensorMap tmZ, tmZt, tmB, tmBt, tmBl, tmBlt;
   int rc;
-  if ((rc = make_map(&tmZ, z, (uint64_t)R.N, (uint64_t)R.D, TME_ZCOLS, TM, CU_TENSOR_MAP_SWIZZLE_128B, true))) return rc;
-  if ((rc = make_map(&tmZt, z, (uint64_t)R.N, (uint64_t)R.D, KT, TM, CU_TENSOR_MAP_SWIZZLE_NONE, true))) return rc;
+  constexpr bool z32 = sizeof(ZT) == 4;
+  if ((rc = make_map(&tmZ, z, (uint64_t)R.N, (uint64_t)R.D, z32 ? TME_ZCOLS : KC, TM, CU_TENSOR_MAP_SWIZZLE_128B, z32))) return rc;
+  if ((rc = make_map(&tmZt, z, (uint64_t)R.N, (uint64_t)R.D, KT, TM, CU_TENSOR_MAP_SWIZZLE_NONE, z32))) return rc;
   const uint32_t brow = (uint32_t)R.ntile / 2, blast = (uint32_t)R.n_last / 2;
   if ((rc = make_map(&tmB, e16, (uint64_t)Kp, (uint64_t)R.Dp, KC, brow, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map(&tmBt, e16, (uint64_t)Kp, (uint64_t)R.Dp, KT, brow, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
   if ((rc = make_map(&tmBl, e16, (uint64_t)Kp, (uint64_t)R.Dp, KC, blast, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map(&tmBlt, e16, (uint64_t)Kp, (uint64_t)R.Dp, KT, blast, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
   const size_t smem = tme_plan(R.nb, R.b_stage, R.nz, R.Kpad).total + 1024;
-  G2V_CUDA_CHECK(cudaFuncSetAttribute(tc_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  G2V_CUDA_CHECK(cudaFuncSetAttribute(tc_tmem_kernel<ZT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int max_groups = num_sms() / 2;
   const int groups = R.n_row_tiles < max_groups ? R.n_row_tiles : max_groups;
   cudaLaunchConfig_t cfg = {};
@@ -2362,7 +2410,7 @@ int launch_tmem(TmeParams& R, const float* z, const __half* e16, int Kp, cudaStr
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  G2V_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_tmem_kernel, tmZ, tmZt, tmB, tmBt, tmBl, tmBlt, R));
+  G2V_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_tmem_kernel<ZT>, tmZ, tmZt, tmB, tmBt, tmBl, tmBlt, R));
   G2V_LAUNCH_CHECK("tc_tmem_kernel");
   return G2V_OK;
 }
@@ -2406,7 +2454,7 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
       cudaEvent_t pev0, pev1;
       profile_take(&pev0, &pev1);
       if (pev0) G2V_CUDA_CHECK(cudaEventRecord(pev0, st));
-      const int rc = launch_tmem(R, reinterpret_cast<const float*>(z), e16, Kp, st);
+      const int rc = launch_tmem<ZT>(R, z, e16, Kp, st);
       if (rc) return rc;
       if (pev1) G2V_CUDA_CHECK(cudaEventRecord(pev1, st));
       return run_recheck(z, z_dtype, E, cb, N, K, D, pairs, chains, fulls, counters, base + w.scratch, idx, stats, flags, st);
