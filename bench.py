@@ -455,9 +455,9 @@ def main():
 # dram__bytes_read+write per launch of the dominant kernel from the committed `ncu --set full`
 # captures under profiles/ (None where no capture exists for that workload)
 TRAFFIC_NOTE = {
-    # tc_tmem_kernel, 1M fp32 rows, K=400: 1.6006 GB read + 0.0093 GB written (profiles/r1_ncu_full_tc_tmem_k400.csv)
+    # tc_tmem_kernel<float>, 1M fp32 rows, K=400: 1.6005 GB read + 0.0089 GB written (profiles/r1_ncu_full_tc_tmem_k400.csv)
     # against 1.604 GB algorithmic -- every row is read from DRAM exactly once, the codebook stays in L2
-    ("tokenize", 400): {"dram_bytes_per_launch": 1.6099e9, "rows": 1_000_000, "dtype": "f32",
+    ("tokenize", 400): {"dram_bytes_per_launch": 1.6094e9, "rows": 1_000_000, "dtype": "f32",
                         "source": "profiles/r1_ncu_full_tc_tmem_k400.csv"},
 }
 
