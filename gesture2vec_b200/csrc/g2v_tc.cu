@@ -2092,7 +2092,7 @@ constexpr size_t kRerankScratchBytes = (size_t)kFull64Cap * kRerankMaxSlices * s
 constexpr size_t kRerankArriveBytes = (size_t)kFull64Cap * sizeof(int);
 
 template <typename ZT>
-__global__ void __launch_bounds__(256) rerank_kernel(const ZT* __restrict__ z, const float* __restrict__ E, int K, int D,
+__global__ void __launch_bounds__(256, 4) rerank_kernel(const ZT* __restrict__ z, const float* __restrict__ E, int K, int D,
                                                      const int* __restrict__ pair_list, const int* __restrict__ chain_list,
                                                      const int* __restrict__ full_list, const int* __restrict__ counters,
                                                      int slices, RerankSlot* scratch, int* arrive, int* __restrict__ idx,
