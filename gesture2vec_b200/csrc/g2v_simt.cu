@@ -1066,7 +1066,7 @@ int launch_apply(const float* x, const float* zs, const float* E, const int32_t*
   // EMA / codebook-gradient sums wanted: aggregate runs of equal codes in registers first (G2V_APPLY_RUNS=0:
   // one reduction per row, the older kernel)
   static const bool runs_on = [] { const char* e = getenv("G2V_APPLY_RUNS"); return !(e && atoi(e) == 0); }();
-  if (vec && dwr && D <= RUNS_MAX_D && runs_on) {
+  if (vec && dwr && D <= RUNS_MAX_D && K < (1 << 26) && runs_on) {      // sort key = code << 5 | lane
     const int g = grid_for((N + 31) / 32, APPLY_WARPS, 8);
     apply_runs_kernel<<<g, APPLY_WARPS * 32, smem, st>>>(x, zs, E, idx, N, K, D, out, sse, counts, dwr, dwr_replicas, use_hist);
     G2V_LAUNCH_CHECK("apply_runs_kernel");

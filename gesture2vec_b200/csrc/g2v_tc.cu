@@ -1,20 +1,22 @@
 // Tensor-core nearest-code search for sm_100a: tcgen05.mma (fp16 operands, fp32 accumulators in
 // TMEM) fed by TMA, fused with an argmin epilogue, so the [N,K] distance matrix never exists.
 //
-// Pipeline of one search (all on the caller's stream):
-//   1. row_prep_kernel   z (fp32/bf16/fp16) -> z16 [N,Dp] fp16, each row scaled by a power of two,
-//                        plus per-row constants (fixed-point scale, rigorous error bound tau).
-//   2. tc_search_kernel  persistent, one CTA per SM, 128-row tiles.  Warp roles:
-//                          w0  TMA producer of codebook (B) K-panels, 3-stage mbarrier ring
-//                          w1  tcgen05.mma issuer (one lane); 2 x 256-column accumulators in TMEM
-//                          w2  TMA producer of the row tile (A), per-K-panel barriers so the next
-//                              tile streams in while the last code tile is still being multiplied
-//                          w4-7 epilogue: tcgen05.ld -> d = e2 - 2 z.e as a 23-bit fixed-point key
-//                              (2 FFMA + 1 IMAD) -> 32 independent running top-2 chains (3 VIMNMX)
-//                        Rows whose best two codes are closer than tau go to a pair list (exact
-//                        fp64 re-rank of two candidates) or, if a third code may be involved, to
-//                        a fallback list (whole row re-ranked: fp32, then fp64 where needed).
-//   3. pair_recheck_kernel, full_recheck_kernel (g2v_simt.cu)
+// run_tc() picks one of three sweep kernels, all on the caller's stream:
+//   tc_tmem_kernel<ZT>        few code tiles (K <= 576 at D = 400), fp32 / bf16 / fp16 rows.  CTA pairs
+//                             (cta_group::2, UMMA M = 256).  Rows stream by TMA into a ring of staging slots;
+//                             8 converter warps round them to fp16 in registers, keep ||z||^2 and the exact
+//                             rounding residual per row, and write the A operand straight into tensor memory
+//                             (tcgen05.st); the codebook streams from L2, half of every stage per CTA.
+//   tc_search_kernel<CG,FUSED> everything else.  The A operand is an fp16 row tile in shared memory: written by
+//                             row_prep_kernel beforehand (with per-row constants; CTA pairs, deep codebook
+//                             ring -- the large-K path) or converted in-kernel from an fp32 staging ring (FUSED).
+//   tc_resident_kernel<ZT>    experimental (G2V_TC_RES=1): fp16 codebook resident in the pair's shared memory.
+// Warp roles in every variant: TMA producers (codebook stages / rows), one MMA-issuing warp (one elected lane;
+// two accumulator stages in TMEM), 8 epilogue warps: tcgen05.ld -> d = e2 - 2 z.e as a 23-bit fixed-point
+// key (packed FFMA2, FMNMX, IMAD) -> 32 running top-2 chains per row (3 VIMNMX per key).
+// A row whose best codes are closer than its error bound tau goes to a candidate list (row + up to three
+// codes), a chain list (one chain of K/32 codes may hide the winner) or the whole-row list; rerank_kernel
+// re-ranks all three exactly in fp64, full_recheck_kernel (g2v_simt.cu) takes an overflowing whole-row list.
 //
 // Operand layouts: K-major, SWIZZLE_128B panels of 64 fp16 (TMA box 64 x rows) and, for the
 // D % 64 remainder, SWIZZLE_32B panels of 16 fp16 (one UMMA_K step each).
