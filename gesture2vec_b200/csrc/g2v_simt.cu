@@ -698,6 +698,134 @@ __global__ void __launch_bounds__(APPLY_WARPS * 32) apply_runs_kernel(
   }
 }
 
+// Block-wide variant: the 256 threads sort the codes of a tile of TILE_ROWS rows (bitonic network in shared
+// memory, ~2 % of the tile's time) and every warp walks a contiguous eighth of the sorted tile.  Runs are
+// 16x longer than with the warp-wide grouping, so even near-uniform code usage (k-means on iid rows: ~1.7 rows
+// per code and tile) merges its reductions.
+constexpr int TILE_BITS = 9;
+constexpr int TILE_ROWS = 1 << TILE_BITS;
+
+__global__ void __launch_bounds__(APPLY_WARPS * 32) apply_tile_kernel(
+    const float* __restrict__ x, const float* __restrict__ zs, const float* __restrict__ E,
+    const int* __restrict__ idx, long long N, int K, int D, float* __restrict__ out, double* sse,
+    int* counts, float* dwr, int dwr_replicas, int use_hist) {
+  extern __shared__ int hist[];
+  __shared__ double wsum[APPLY_WARPS];
+  __shared__ unsigned skey[TILE_ROWS];
+  dwr += (size_t)(blockIdx.x % dwr_replicas) * K * D;               // this block's private copy
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (use_hist) {
+    for (int k = threadIdx.x; k < K; k += blockDim.x) hist[k] = 0;
+    __syncthreads();
+  }
+  const int nq = D >> 2;                                            // float4 columns per row
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float acc = 0.f;
+  const long long stride = (long long)gridDim.x * TILE_ROWS;
+  for (long long base = (long long)blockIdx.x * TILE_ROWS; base < N; base += stride) {
+    const int tvalid = (int)min((long long)TILE_ROWS, N - base);
+    // (code, row) keys of the tile, sorted by the whole block (bitonic network in shared memory)
+    __syncthreads();                                                // previous tile's keys are no longer read
+    for (int t = threadIdx.x; t < TILE_ROWS; t += blockDim.x) {
+      int k = K;                                                    // rows past the end sort last
+      if (t < tvalid) {
+        k = min(max(__ldg(idx + base + t), 0), K - 1);
+        if (counts) {
+          if (use_hist) atomicAdd(&hist[k], 1);
+          else atomicAdd(counts + k, 1);
+        }
+      }
+      skey[t] = ((unsigned)k << TILE_BITS) | (unsigned)t;
+    }
+    for (int k2 = 2; k2 <= TILE_ROWS; k2 <<= 1) {
+      for (int j = k2 >> 1; j > 0; j >>= 1) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < TILE_ROWS / 2; t += blockDim.x) {
+          const unsigned ia = (((unsigned)t & ~((unsigned)j - 1u)) << 1) | ((unsigned)t & ((unsigned)j - 1u)), ib = ia | (unsigned)j;
+          const unsigned xa = skey[ia], xb = skey[ib];
+          if ((xa > xb) == ((ia & (unsigned)k2) == 0u)) { skey[ia] = xb; skey[ib] = xa; }
+        }
+      }
+    }
+    __syncthreads();
+    // this warp walks its share of the sorted tile
+    constexpr int PER_WARP = TILE_ROWS / APPLY_WARPS;
+    const unsigned* wkey = skey + warp * PER_WARP;
+    const int nvalid = max(0, min(PER_WARP, tvalid - warp * PER_WARP));
+    float4 a[4], ev[4], xn[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = ev[u] = zero4;
+    int cur = -1;
+    auto load_row = [&](const float* src, int i, float4 (&v)[4]) {
+      const unsigned ki = wkey[i];
+      const float* r = src + (size_t)(base + (ki & (TILE_ROWS - 1u))) * D;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (lane + 32 * u < nq) ? ldg4(r + 4 * (lane + 32 * u)) : zero4;
+    };
+    auto flush = [&]() {
+      float* drow = dwr + (size_t)cur * D;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (lane + 32 * u < nq) red_add_v4(drow + 4 * (lane + 32 * u), a[u].x, a[u].y, a[u].z, a[u].w);
+    };
+    if (nvalid > 0) load_row(x, 0, xn);
+    for (int i = 0; i < nvalid; ++i) {
+      const unsigned ki = wkey[i];
+      const int code = (int)(ki >> TILE_BITS);
+      const long long row = base + (ki & (TILE_ROWS - 1u));
+      float4 xv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) xv[u] = xn[u];
+      if (i + 1 < nvalid) load_row(x, i + 1, xn);                   // next row in flight while this one is summed
+      if (code != cur) {                                            // warp-uniform
+        if (cur >= 0) flush();
+        cur = code;
+        const float* er = E + (size_t)code * D;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          ev[u] = (lane + 32 * u < nq) ? ldg4(er + 4 * (lane + 32 * u)) : zero4;
+          a[u] = zero4;
+        }
+      }
+      float4 zv[4];
+      if (zs) load_row(zs, i, zv);
+      float* orow = out ? out + (size_t)row * D : nullptr;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 d = make_float4(ev[u].x - xv[u].x, ev[u].y - xv[u].y, ev[u].z - xv[u].z, ev[u].w - xv[u].w);
+        acc = fmaf(d.x, d.x, acc); acc = fmaf(d.y, d.y, acc);
+        acc = fmaf(d.z, d.z, acc); acc = fmaf(d.w, d.w, acc);
+        if (orow && lane + 32 * u < nq)
+          __stcs(reinterpret_cast<float4*>(orow + 4 * (lane + 32 * u)),
+                 make_float4(xv[u].x + d.x, xv[u].y + d.y, xv[u].z + d.z, xv[u].w + d.w));
+        if (zs) {
+          a[u].x += zv[u].x - ev[u].x; a[u].y += zv[u].y - ev[u].y;
+          a[u].z += zv[u].z - ev[u].z; a[u].w += zv[u].w - ev[u].w;
+        } else {
+          a[u].x -= d.x; a[u].y -= d.y; a[u].z -= d.z; a[u].w -= d.w;
+        }
+      }
+    }
+    if (cur >= 0) flush();
+  }
+  if (sse) {
+    double s = warp_sum((double)acc);
+    if (lane == 0) wsum[warp] = s;
+  }
+  __syncthreads();
+  if (sse && threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < APPLY_WARPS; ++w) s += wsum[w];
+    atomicAdd(sse, s);
+  }
+  if (use_hist && counts) {
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      int v = hist[k];
+      if (v) atomicAdd(counts + k, v);
+    }
+  }
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(256) backward_kernel(const float* __restrict__ x, const float* __restrict__ E,
                                                        const int* __restrict__ idx,
@@ -1066,6 +1194,13 @@ int launch_apply(const float* x, const float* zs, const float* E, const int32_t*
   // EMA / codebook-gradient sums wanted: aggregate runs of equal codes in registers first (G2V_APPLY_RUNS=0:
   // one reduction per row, the older kernel)
   static const bool runs_on = [] { const char* e = getenv("G2V_APPLY_RUNS"); return !(e && atoi(e) == 0); }();
+  static const bool tile_on = [] { const char* e = getenv("G2V_APPLY_TILE"); return e && atoi(e) == 1; }();
+  if (vec && dwr && D <= RUNS_MAX_D && K < (1 << 22) && tile_on && N >= 4 * TILE_ROWS) {      // sort key = code << 9 | row
+    const int g = grid_for((N + TILE_ROWS - 1) / TILE_ROWS, 1, 2);
+    apply_tile_kernel<<<g, APPLY_WARPS * 32, smem, st>>>(x, zs, E, idx, N, K, D, out, sse, counts, dwr, dwr_replicas, use_hist);
+    G2V_LAUNCH_CHECK("apply_tile_kernel");
+    return G2V_OK;
+  }
   if (vec && dwr && D <= RUNS_MAX_D && K < (1 << 26) && runs_on) {      // sort key = code << 5 | lane
     const int g = grid_for((N + 31) / 32, APPLY_WARPS, 8);
     apply_runs_kernel<<<g, APPLY_WARPS * 32, smem, st>>>(x, zs, E, idx, N, K, D, out, sse, counts, dwr, dwr_replicas, use_hist);
