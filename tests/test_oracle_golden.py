@@ -148,3 +148,31 @@ def test_state_dict_key_contract_recorded():
     assert keys["vqvae.VQ_Payam"] == ["_embedding.weight", "pre_linear.bias", "pre_linear.weight"]
     assert keys["dae.VQ_Payam_EMA"] == keys["vqvae.VQ_Payam_EMA"] == [
         "_ema_cluster_size", "_ema_w", "_embedding.weight", "pre_linear.bias", "pre_linear.weight"]
+
+
+def test_gssoft_oracle_matches_reference():
+    """Soft quantizer: forward values and the closed-form backward of oracle/gssoft_oracle.py
+    against the real module's outputs and autograd gradients (tests/golden/make_gssoft_golden.py)."""
+    from make_gssoft_golden import CFG, ROWS, inputs
+    from oracle import gssoft_oracle as G
+    g = np.load(os.path.join(HERE, "golden", "gssoft_trinity.npz"))
+    x, E, Wm, bm, Wl, bl, g_out = inputs()
+    assert float(x.astype(np.float64).sum()) == float(g["x_sum"]), "RNG stream changed"
+    fw = G.forward(x, E, Wm, bm, Wl, bl, CFG["beta"])
+    np.testing.assert_allclose(fw["loss"], g["loss"], rtol=2e-6)
+    np.testing.assert_allclose(fw["perplexity"], g["perplexity"], rtol=1e-5)
+    D = CFG["D"]
+    np.testing.assert_allclose(fw["out"].reshape(-1, D)[ROWS], g["out_rows"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(fw["encodings"][ROWS], g["enc_rows"], rtol=2e-5)
+    np.testing.assert_allclose(fw["encodings"].astype(np.float64).sum(), float(g["enc_sum"]), rtol=1e-6)
+    bw = G.backward(fw, E, Wm, Wl, CFG["beta"], CFG["g_loss"], g_out)
+    # the reference's gradients are fp32 autograd through two GEMMs and an un-stabilised normalisation
+    for key, ref, scale in (("x", g["gx_rows"], None), ("E", g["gE_rows"], None), ("Wm", g["gWm_rows"], None),
+                            ("Wl", g["gWl_rows"], None)):
+        got = bw[key].reshape(-1, D)[ROWS]                            # x as rows of D, like the golden
+        np.testing.assert_allclose(got, ref, rtol=2e-3, atol=2e-4 * np.abs(ref).max())
+    np.testing.assert_allclose(bw["bm"], g["gbm"], rtol=2e-3, atol=2e-4 * np.abs(g["gbm"]).max())
+    np.testing.assert_allclose(bw["bl"], g["gbl"], rtol=2e-3, atol=2e-4 * np.abs(g["gbl"]).max())
+    np.testing.assert_allclose(np.abs(bw["x"]).sum(), float(g["gx_abssum"]), rtol=1e-4)
+    np.testing.assert_allclose(np.abs(bw["E"]).sum(), float(g["gE_abssum"]), rtol=1e-3)
+    assert "pre_linear.weight" in set(g["state_keys"].tolist())        # unused Linear still in the state_dict
