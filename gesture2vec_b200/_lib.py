@@ -34,7 +34,11 @@ SIGNATURES = {
     "g2v_vq_apply": (_i, [_p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _i, _p]),
     "g2v_vq_stats_pack": (_i, [_p, _p, _p, _i, _i64, _i, _i, _p, _p]),
     "g2v_vq_stats_finalize": (_i, [_p, _i, _i, _f, _f, _p, _p, _p]),
-    "g2v_vq_ema_update": (_i, [_p, _p, _p, _p, _p, _f, _f, _i, _i, _p, _sz, _p]),
+    "g2v_vq_ema_update": (_i, [_p, _p, _p, _p, _p, _p, _p, _f, _f, _i, _i, _p, _sz, _p]),
+    "g2v_vq_step_finalize": (_i, [_p, _p, _p, _i, _i64, _p, _i, _i, _f, _f, _p, _p, _i, _p, _p, _p, _p, _p, _p, _f, _f,
+                                  _p, _p, _sz, _p]),
+    "g2v_exact_workspace_bytes": (_sz, [_i]),
+    "g2v_vq_search_exact": (_i, [_p, _i, _p, _i64, _i, _i, _p, _p, _sz, _p]),
     "g2v_vq_backward": (_i, [_p, _p, _p, _p, _p, _f, _i64, _i, _i, _p, _p]),
     "g2v_vq_grad_codebook": (_i, [_p, _p, _f, _i, _i, _p, _p]),
     "g2v_kmeans_update": (_i, [_p, _p, _i, _i, _p, _p, _p, _sz, _p]),

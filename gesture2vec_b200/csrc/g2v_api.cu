@@ -172,15 +172,39 @@ int g2v_vq_stats_finalize(const float* packed, int K, int D, float coef_codebook
                                (cudaStream_t)stream);
 }
 
-int g2v_vq_ema_update(float* cluster_size, float* ema_w, const float* E_old, float* E_new,
-                      const float* packed, float decay, float eps, int K, int D, void* cb, size_t cb_bytes,
-                      void* stream) {
-  if (K <= 0 || D <= 0 || !cluster_size || !ema_w || !E_old || !E_new || !packed) return G2V_ERR_INVALID;
-  if (cb && cb_bytes < cb_total_bytes(K, D)) return G2V_ERR_WORKSPACE;
-  int rc = launch_ema_update(cluster_size, ema_w, E_old, E_new, packed, decay, eps, K, D, (cudaStream_t)stream);
+int g2v_vq_step_finalize(int32_t* counts, double* sse, float* dwr, int dwr_replicas, int64_t rows_local,
+                         float* packed, int K, int D, float coef_codebook, float coef_commit, float* loss,
+                         float* perplexity, int update, const float* cs_in, float* cs_out, const float* ema_w_in,
+                         float* ema_w_out, const float* E_old, float* E_new, float decay, float eps,
+                         double* shift2, void* cb, size_t cb_bytes, void* stream) {
+  if (K <= 0 || D <= 0 || rows_local < 0 || (dwr && dwr_replicas < 1)) return G2V_ERR_INVALID;
+  const int do_pack = (counts || sse || dwr) ? 1 : 0;
+  if ((do_pack || loss || perplexity || update != G2V_UPDATE_NONE) && !packed) return G2V_ERR_INVALID;
+  if (update == G2V_UPDATE_EMA) {
+    if (!cs_in || !cs_out || !ema_w_in || !ema_w_out || !E_old || !E_new || cs_in == cs_out) return G2V_ERR_INVALID;
+  } else if (update == G2V_UPDATE_KMEANS) {
+    if (!E_old || !E_new) return G2V_ERR_INVALID;
+  } else if (update != G2V_UPDATE_NONE) {
+    return G2V_ERR_INVALID;
+  }
+  if (cb) {
+    if (cb_bytes < cb_total_bytes(K, D)) return G2V_ERR_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(cb) & 255) return G2V_ERR_ALIGN;
+    if (update == G2V_UPDATE_NONE && !E_old) return G2V_ERR_INVALID;
+  }
+  int rc = check_arch();
   if (rc) return rc;
-  if (cb) rc = launch_codebook_prepare(E_new, K, D, cb, (cudaStream_t)stream);
-  return rc;
+  return launch_step_finalize(counts, sse, dwr, dwr_replicas, do_pack, rows_local, packed, K, D, coef_codebook,
+                              coef_commit, loss, perplexity, update, cs_in, cs_out, ema_w_in, ema_w_out, E_old, E_new,
+                              decay, eps, shift2, cb, E_old, (cudaStream_t)stream);
+}
+
+int g2v_vq_ema_update(const float* cs_in, float* cs_out, const float* ema_w_in, float* ema_w_out,
+                      const float* E_old, float* E_new, const float* packed, float decay, float eps, int K, int D,
+                      void* cb, size_t cb_bytes, void* stream) {
+  return g2v_vq_step_finalize(nullptr, nullptr, nullptr, 0, 0, const_cast<float*>(packed), K, D, 0.f, 0.f, nullptr,
+                              nullptr, G2V_UPDATE_EMA, cs_in, cs_out, ema_w_in, ema_w_out, E_old, E_new, decay, eps,
+                              nullptr, cb, cb_bytes, stream);
 }
 
 int g2v_vq_backward(const float* x, const float* E, const int32_t* idx, const float* g_out,
@@ -198,12 +222,23 @@ int g2v_vq_grad_codebook(const float* packed_dwr, const float* g_loss, float coe
 
 int g2v_kmeans_update(const float* E_old, const float* packed, int K, int D, float* E_new, double* shift2,
                       void* cb, size_t cb_bytes, void* stream) {
-  if (K <= 0 || D <= 0 || !E_old || !packed || !E_new) return G2V_ERR_INVALID;
-  if (cb && cb_bytes < cb_total_bytes(K, D)) return G2V_ERR_WORKSPACE;
-  int rc = launch_kmeans_update(E_old, packed, K, D, E_new, shift2, (cudaStream_t)stream);
+  return g2v_vq_step_finalize(nullptr, nullptr, nullptr, 0, 0, const_cast<float*>(packed), K, D, 0.f, 0.f, nullptr,
+                              nullptr, G2V_UPDATE_KMEANS, nullptr, nullptr, nullptr, nullptr, E_old, E_new, 0.f, 0.f,
+                              shift2, cb, cb_bytes, stream);
+}
+
+size_t g2v_exact_workspace_bytes(int K) { return K > 0 ? align_up((size_t)K * sizeof(double), 256) : 0; }
+
+int g2v_vq_search_exact(const void* z, int z_dtype, const float* E, int64_t N, int K, int D, int32_t* idx,
+                        void* ws, size_t ws_bytes, void* stream) {
+  if (bad_shape(N, K, D) || !E || (N > 0 && (!z || !idx))) return G2V_ERR_INVALID;
+  if (z_dtype != G2V_F32 && z_dtype != G2V_BF16 && z_dtype != G2V_F16) return G2V_ERR_DTYPE;
+  if (N == 0) return G2V_OK;
+  if (!ws || ws_bytes < g2v_exact_workspace_bytes(K)) return G2V_ERR_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(ws) & 7) return G2V_ERR_ALIGN;
+  int rc = check_arch();
   if (rc) return rc;
-  if (cb) rc = launch_codebook_prepare(E_new, K, D, cb, (cudaStream_t)stream);
-  return rc;
+  return launch_search_exact64(z, z_dtype, E, N, K, D, idx, ws, (cudaStream_t)stream);
 }
 
 int g2v_onehot(const int32_t* idx, int64_t N, int K, float* enc, void* stream) {

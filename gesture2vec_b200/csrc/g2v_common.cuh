@@ -101,10 +101,15 @@ int launch_stats_pack(const int32_t* counts, const double* sse, const float* dwr
                       int K, int D, float* packed, cudaStream_t st);
 int launch_stats_finalize(const float* packed, int K, int D, float coef_codebook, float coef_commit,
                           float* loss, float* ppl, cudaStream_t st);
-int launch_ema_update(float* cs, float* ema_w, const float* E_old, float* E_new, const float* packed,
-                      float decay, float eps, int K, int D, cudaStream_t st);
-int launch_kmeans_update(const float* E_old, const float* packed, int K, int D, float* E_new, double* shift2,
-                         cudaStream_t st);
+// g2v_finalize.cu: pack + scalars + codebook update (mode 0 none, 1 EMA, 2 Lloyd) + aux buffer, one cooperative launch
+int launch_step_finalize(int32_t* counts, double* sse, float* dwr, int dwr_replicas, int do_pack, int64_t rows_local,
+                         float* packed, int K, int D, float coef_codebook, float coef_commit, float* loss, float* ppl,
+                         int mode, const float* cs_in, float* cs_out, const float* w_in, float* w_out,
+                         const float* E_old, float* E_new, float decay, float eps, double* shift2, void* cb,
+                         const float* E_cb, cudaStream_t st);
+// g2v_audit.cu: exact fp64 argmin of every row (verification aid); ws holds K doubles
+int launch_search_exact64(const void* z, int z_dtype, const float* E, int64_t N, int K, int D, int32_t* idx, void* ws,
+                          cudaStream_t st);
 int launch_backward(const float* x, const float* E, const int32_t* idx, const float* g_out,
                     const float* g_loss, float coef_x, int64_t N, int K, int D, float* g_x,
                     cudaStream_t st);

@@ -43,86 +43,6 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ------------------------------------------------------------------------------------------
-// codebook preparation
-// ------------------------------------------------------------------------------------------
-__global__ void cb_rows_kernel(const float* __restrict__ E, int K, int D, int Kp, CbHeader* hdr,
-                               float* __restrict__ ntab, float* __restrict__ e2) {
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= Kp) return;
-  if (warp >= K) {
-    if (lane == 0) e2[warp] = INFINITY;
-    return;
-  }
-  const float* row = E + (size_t)warp * D;
-  double s2 = 0.0, s4 = 0.0;
-  float am = 0.f;
-  for (int j = lane; j < D; j += 32) {
-    float v = row[j];
-    double v2 = (double)v * (double)v;
-    s2 += v2;
-    s4 += v2 * v2;
-    am = fmaxf(am, fabsf(v));
-  }
-  s2 = warp_sum(s2);
-  s4 = warp_sum(s4);
-  am = warp_max(am);
-  if (lane == 0) {
-    float f2 = (float)s2;
-    e2[warp] = f2;
-    // non-negative floats order like their bit patterns
-    atomicMax(reinterpret_cast<int*>(&hdr->e2max), __float_as_int(f2));
-    atomicMin(reinterpret_cast<int*>(&hdr->e2min), __float_as_int(f2));
-    atomicMax(reinterpret_cast<int*>(&hdr->amax), __float_as_int(am));
-    const float nrm = sqrtf(f2) * 1.0001f;
-    atomicMax(reinterpret_cast<int*>(&ntab[norm_bucket(nrm)]), __float_as_int(nrm));
-  }
-}
-
-__global__ void cb_header_kernel(CbHeader* hdr, float* ntab, int K, int D, int Kp, int Dp) {
-  float run = 0.f;                                   // prefix maximum over the norm buckets
-  for (int b = 0; b < kNormBuckets; ++b) {
-    run = fmaxf(run, ntab[b]);
-    ntab[b] = run;
-  }
-  float am = hdr->amax;
-  float sc = 1.f;
-  if (am > 0.f && isfinite(am)) {
-    int e;
-    frexpf(am, &e);            // am = m * 2^e, m in [0.5,1)  ->  am*2^(9-e) in [256,512)
-    sc = ldexpf(1.f, 9 - e);
-  }
-  hdr->scale_e = sc;
-  hdr->K = K; hdr->D = D; hdr->Kp = Kp; hdr->Dp = Dp;
-  hdr->magic = kCbMagic;
-}
-
-// fp16 operand copy of the codebook (one warp per code) + the norm of its rounding residual
-__global__ void cb_fp16_kernel(const float* __restrict__ E, int K, int D, int Kp, int Dp, CbHeader* hdr,
-                               __half* __restrict__ E16) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= Kp) return;
-  const float sc = hdr->scale_e, inv = 1.f / sc;   // power of two: exact
-  __half* o = E16 + (size_t)warp * Dp;
-  float s2 = 0.f, n2 = 0.f;
-  for (int j = lane; j < Dp; j += 32) {
-    float v = (warp < K && j < D) ? E[(size_t)warp * D + j] : 0.f;
-    __half h = __float2half_rn(v * sc);
-    float r = v - __half2float(h) * inv;
-    s2 = fmaf(r, r, s2);
-    n2 = fmaf(v, v, n2);
-    o[j] = h;
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
-    n2 += __shfl_xor_sync(0xffffffffu, n2, off);
-  }
-  // residual relative to the code's own norm, so one scalar bounds every code: ||r_e,k|| <= sfrac ||e_k||
-  if (lane == 0 && warp < K && n2 > 0.f)
-    atomicMax(reinterpret_cast<int*>(&hdr->sfrac), __float_as_int(sqrtf(s2 / n2) * 1.001f));
-}
-
-// ------------------------------------------------------------------------------------------
 // fp32 search with fused top-2 and exact re-rank
 // ------------------------------------------------------------------------------------------
 constexpr int BM = 128, BN = 128, BK = 16, NT = 256, LDS = BM + 4;
@@ -698,134 +618,6 @@ __global__ void __launch_bounds__(APPLY_WARPS * 32) apply_runs_kernel(
   }
 }
 
-// Block-wide variant: the 256 threads sort the codes of a tile of TILE_ROWS rows (bitonic network in shared
-// memory, ~2 % of the tile's time) and every warp walks a contiguous eighth of the sorted tile.  Runs are
-// 16x longer than with the warp-wide grouping, so even near-uniform code usage (k-means on iid rows: ~1.7 rows
-// per code and tile) merges its reductions.
-constexpr int TILE_BITS = 9;
-constexpr int TILE_ROWS = 1 << TILE_BITS;
-
-__global__ void __launch_bounds__(APPLY_WARPS * 32) apply_tile_kernel(
-    const float* __restrict__ x, const float* __restrict__ zs, const float* __restrict__ E,
-    const int* __restrict__ idx, long long N, int K, int D, float* __restrict__ out, double* sse,
-    int* counts, float* dwr, int dwr_replicas, int use_hist) {
-  extern __shared__ int hist[];
-  __shared__ double wsum[APPLY_WARPS];
-  __shared__ unsigned skey[TILE_ROWS];
-  dwr += (size_t)(blockIdx.x % dwr_replicas) * K * D;               // this block's private copy
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (use_hist) {
-    for (int k = threadIdx.x; k < K; k += blockDim.x) hist[k] = 0;
-    __syncthreads();
-  }
-  const int nq = D >> 2;                                            // float4 columns per row
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  float acc = 0.f;
-  const long long stride = (long long)gridDim.x * TILE_ROWS;
-  for (long long base = (long long)blockIdx.x * TILE_ROWS; base < N; base += stride) {
-    const int tvalid = (int)min((long long)TILE_ROWS, N - base);
-    // (code, row) keys of the tile, sorted by the whole block (bitonic network in shared memory)
-    __syncthreads();                                                // previous tile's keys are no longer read
-    for (int t = threadIdx.x; t < TILE_ROWS; t += blockDim.x) {
-      int k = K;                                                    // rows past the end sort last
-      if (t < tvalid) {
-        k = min(max(__ldg(idx + base + t), 0), K - 1);
-        if (counts) {
-          if (use_hist) atomicAdd(&hist[k], 1);
-          else atomicAdd(counts + k, 1);
-        }
-      }
-      skey[t] = ((unsigned)k << TILE_BITS) | (unsigned)t;
-    }
-    for (int k2 = 2; k2 <= TILE_ROWS; k2 <<= 1) {
-      for (int j = k2 >> 1; j > 0; j >>= 1) {
-        __syncthreads();
-        for (int t = threadIdx.x; t < TILE_ROWS / 2; t += blockDim.x) {
-          const unsigned ia = (((unsigned)t & ~((unsigned)j - 1u)) << 1) | ((unsigned)t & ((unsigned)j - 1u)), ib = ia | (unsigned)j;
-          const unsigned xa = skey[ia], xb = skey[ib];
-          if ((xa > xb) == ((ia & (unsigned)k2) == 0u)) { skey[ia] = xb; skey[ib] = xa; }
-        }
-      }
-    }
-    __syncthreads();
-    // this warp walks its share of the sorted tile
-    constexpr int PER_WARP = TILE_ROWS / APPLY_WARPS;
-    const unsigned* wkey = skey + warp * PER_WARP;
-    const int nvalid = max(0, min(PER_WARP, tvalid - warp * PER_WARP));
-    float4 a[4], ev[4], xn[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) a[u] = ev[u] = zero4;
-    int cur = -1;
-    auto load_row = [&](const float* src, int i, float4 (&v)[4]) {
-      const unsigned ki = wkey[i];
-      const float* r = src + (size_t)(base + (ki & (TILE_ROWS - 1u))) * D;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = (lane + 32 * u < nq) ? ldg4(r + 4 * (lane + 32 * u)) : zero4;
-    };
-    auto flush = [&]() {
-      float* drow = dwr + (size_t)cur * D;
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (lane + 32 * u < nq) red_add_v4(drow + 4 * (lane + 32 * u), a[u].x, a[u].y, a[u].z, a[u].w);
-    };
-    if (nvalid > 0) load_row(x, 0, xn);
-    for (int i = 0; i < nvalid; ++i) {
-      const unsigned ki = wkey[i];
-      const int code = (int)(ki >> TILE_BITS);
-      const long long row = base + (ki & (TILE_ROWS - 1u));
-      float4 xv[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) xv[u] = xn[u];
-      if (i + 1 < nvalid) load_row(x, i + 1, xn);                   // next row in flight while this one is summed
-      if (code != cur) {                                            // warp-uniform
-        if (cur >= 0) flush();
-        cur = code;
-        const float* er = E + (size_t)code * D;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          ev[u] = (lane + 32 * u < nq) ? ldg4(er + 4 * (lane + 32 * u)) : zero4;
-          a[u] = zero4;
-        }
-      }
-      float4 zv[4];
-      if (zs) load_row(zs, i, zv);
-      float* orow = out ? out + (size_t)row * D : nullptr;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float4 d = make_float4(ev[u].x - xv[u].x, ev[u].y - xv[u].y, ev[u].z - xv[u].z, ev[u].w - xv[u].w);
-        acc = fmaf(d.x, d.x, acc); acc = fmaf(d.y, d.y, acc);
-        acc = fmaf(d.z, d.z, acc); acc = fmaf(d.w, d.w, acc);
-        if (orow && lane + 32 * u < nq)
-          __stcs(reinterpret_cast<float4*>(orow + 4 * (lane + 32 * u)),
-                 make_float4(xv[u].x + d.x, xv[u].y + d.y, xv[u].z + d.z, xv[u].w + d.w));
-        if (zs) {
-          a[u].x += zv[u].x - ev[u].x; a[u].y += zv[u].y - ev[u].y;
-          a[u].z += zv[u].z - ev[u].z; a[u].w += zv[u].w - ev[u].w;
-        } else {
-          a[u].x -= d.x; a[u].y -= d.y; a[u].z -= d.z; a[u].w -= d.w;
-        }
-      }
-    }
-    if (cur >= 0) flush();
-  }
-  if (sse) {
-    double s = warp_sum((double)acc);
-    if (lane == 0) wsum[warp] = s;
-  }
-  __syncthreads();
-  if (sse && threadIdx.x == 0) {
-    double s = 0.0;
-    for (int w = 0; w < APPLY_WARPS; ++w) s += wsum[w];
-    atomicAdd(sse, s);
-  }
-  if (use_hist && counts) {
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
-      int v = hist[k];
-      if (v) atomicAdd(counts + k, v);
-    }
-  }
-}
-
 template <bool VEC>
 __global__ void __launch_bounds__(256) backward_kernel(const float* __restrict__ x, const float* __restrict__ E,
                                                        const int* __restrict__ idx,
@@ -880,95 +672,6 @@ __global__ void stats_pack_kernel(const int* __restrict__ counts, const double* 
   }
 }
 
-__device__ double block_sum_1024(double v, double* sh) {
-  v = warp_sum(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-  __syncthreads();
-  double s = 0.0;
-  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sh[w];
-  return s;
-}
-
-__global__ void __launch_bounds__(1024) stats_finalize_kernel(const float* __restrict__ packed, int K, int D,
-                                                              float coef_codebook, float coef_commit,
-                                                              float* loss, float* ppl) {
-  __shared__ double sh[32];
-  const float* tail = packed + (size_t)K * D;
-  const float rows = tail[K + 1];
-  double h = 0.0;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    float p = tail[k] / rows;                 // avg_probs = mean(encodings, 0)
-    h += (double)(p * logf(p + 1e-10f));
-  }
-  h = block_sum_1024(h, sh);
-  if (threadIdx.x == 0) {
-    if (ppl) *ppl = expf(-(float)h);
-    if (loss) {
-      float mse = (float)((double)tail[K] / ((double)rows * (double)D));
-      *loss = __fadd_rn(__fmul_rn(coef_codebook, mse), __fmul_rn(coef_commit, mse));
-    }
-  }
-}
-
-__global__ void __launch_bounds__(1024) ema_cs_kernel(float* __restrict__ cs, const float* __restrict__ packed,
-                                                      float decay, float one_m, float eps, float keps,
-                                                      int K, int D) {
-  __shared__ double sh[32];
-  const float* counts = packed + (size_t)K * D;
-  double part = 0.0;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    float v = __fadd_rn(__fmul_rn(cs[k], decay), __fmul_rn(one_m, counts[k]));
-    cs[k] = v;
-    part += (double)v;
-  }
-  const float n = (float)block_sum_1024(part, sh);
-  const float den = __fadd_rn(n, keps);
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    float v = __fadd_rn(cs[k], eps);
-    cs[k] = __fmul_rn(__fdiv_rn(v, den), n);   // (cs + eps) / (n + K*eps) * n
-  }
-}
-
-__global__ void ema_w_kernel(const float* __restrict__ cs, float* __restrict__ ema_w, const float* E_old,
-                             float* E_new, const float* __restrict__ packed, float decay, float one_m, int K,
-                             int D) {
-  const float* counts = packed + (size_t)K * D;
-  const size_t total = (size_t)K * D;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int k = (int)(i / D);
-    float dw = fmaf(counts[k], E_old[i], packed[i]);   // sum of rows = residual sum + count * code
-    float w = __fadd_rn(__fmul_rn(ema_w[i], decay), __fmul_rn(one_m, dw));
-    ema_w[i] = w;
-    E_new[i] = __fdiv_rn(w, cs[k]);
-  }
-}
-
-// Lloyd M-step from the packed statistics of an assignment pass: centre k moves to the mean of its rows,
-// E[k] + dwr[k] / counts[k] (residual form: no cancellation); an empty cluster keeps its centre.
-// shift2 accumulates sum_k ||E_new[k] - E_old[k]||^2 (the convergence test of sklearn's Lloyd loop).
-__global__ void __launch_bounds__(256) kmeans_update_kernel(const float* __restrict__ E_old, const float* __restrict__ packed,
-                                                            int K, int D, float* __restrict__ E_new, double* shift2) {
-  __shared__ double sh[8];
-  const float* counts = packed + (size_t)K * D;
-  const size_t total = (size_t)K * D;
-  double part = 0.0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const float c = counts[i / D];
-    const float step = c > 0.f ? __fdiv_rn(packed[i], c) : 0.f;
-    E_new[i] = __fadd_rn(E_old[i], step);
-    part += (double)step * (double)step;
-  }
-  part = warp_sum(part);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
-  __syncthreads();
-  if (threadIdx.x == 0 && shift2) {
-    double t = 0.0;
-    for (int w = 0; w < 8; ++w) t += sh[w];
-    atomicAdd(shift2, t);
-  }
-}
-
 __global__ void grad_codebook_kernel(const float* __restrict__ dwr, const float* __restrict__ g_loss,
                                      float coef_e, size_t total, float* __restrict__ g_E) {
   const float c = -__ldg(g_loss) * coef_e;
@@ -1010,23 +713,6 @@ inline int grid_for(long long work_items, int per_block, int cap_mult) {
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-int launch_codebook_prepare(const float* E, int K, int D, void* cb, cudaStream_t st) {
-  const int Kp = round_up(K, 256), Dp = round_up(D, 16);
-  auto* hdr = reinterpret_cast<CbHeader*>(cb);
-  float* ntab = reinterpret_cast<float*>(reinterpret_cast<char*>(cb) + cb_tab_offset());
-  float* e2 = reinterpret_cast<float*>(reinterpret_cast<char*>(cb) + cb_e2_offset());
-  __half* e16 = reinterpret_cast<__half*>(reinterpret_cast<char*>(cb) + cb_e16_offset(K));
-  G2V_CUDA_CHECK(cudaMemsetAsync(hdr, 0, cb_e2_offset(), st));                  // header + norm table
-  G2V_CUDA_CHECK(cudaMemsetAsync(&hdr->e2min, 0x7f, sizeof(float), st));        // large positive for atomicMin
-  cb_rows_kernel<<<(Kp * 32 + 255) / 256, 256, 0, st>>>(E, K, D, Kp, hdr, ntab, e2);
-  G2V_LAUNCH_CHECK("cb_rows_kernel");
-  cb_header_kernel<<<1, 1, 0, st>>>(hdr, ntab, K, D, Kp, Dp);
-  G2V_LAUNCH_CHECK("cb_header_kernel");
-  cb_fp16_kernel<<<(Kp * 32 + 255) / 256, 256, 0, st>>>(E, K, D, Kp, Dp, hdr, e16);
-  G2V_LAUNCH_CHECK("cb_fp16_kernel");
-  return G2V_OK;
-}
-
 // Exact re-rank of a SMALL number of listed rows: one CTA per row, warps split the codes, lanes split
 // the dimensions (coalesced), straight fp64.  Used for the first kFull64Cap listed rows (the usual
 // case: a few hundred rows per million); anything beyond goes to the batched fp32+fp64 kernel above.
@@ -1194,14 +880,8 @@ int launch_apply(const float* x, const float* zs, const float* E, const int32_t*
   // EMA / codebook-gradient sums wanted: aggregate runs of equal codes in registers first (G2V_APPLY_RUNS=0:
   // one reduction per row, the older kernel)
   static const bool runs_on = [] { const char* e = getenv("G2V_APPLY_RUNS"); return !(e && atoi(e) == 0); }();
-  static const bool tile_on = [] { const char* e = getenv("G2V_APPLY_TILE"); return e && atoi(e) == 1; }();
-  if (vec && dwr && D <= RUNS_MAX_D && K < (1 << 22) && tile_on && N >= 4 * TILE_ROWS) {      // sort key = code << 9 | row
-    const int g = grid_for((N + TILE_ROWS - 1) / TILE_ROWS, 1, 2);
-    apply_tile_kernel<<<g, APPLY_WARPS * 32, smem, st>>>(x, zs, E, idx, N, K, D, out, sse, counts, dwr, dwr_replicas, use_hist);
-    G2V_LAUNCH_CHECK("apply_tile_kernel");
-    return G2V_OK;
-  }
-  if (vec && dwr && D <= RUNS_MAX_D && K < (1 << 26) && runs_on) {      // sort key = code << 5 | lane
+  // (small batches: a warp per row keeps every SM busy; the run walk serialises 32 rows per warp)
+  if (vec && dwr && D <= RUNS_MAX_D && K < (1 << 26) && runs_on && N >= 16384) {      // sort key = code << 5 | lane
     const int g = grid_for((N + 31) / 32, APPLY_WARPS, 8);
     apply_runs_kernel<<<g, APPLY_WARPS * 32, smem, st>>>(x, zs, E, idx, N, K, D, out, sse, counts, dwr, dwr_replicas, use_hist);
     G2V_LAUNCH_CHECK("apply_runs_kernel");
@@ -1220,24 +900,6 @@ int launch_stats_pack(const int32_t* counts, const double* sse, const float* dwr
   stats_pack_kernel<<<grid_for((long long)K * D + K + 2, 256, 8), 256, 0, st>>>(counts, sse, dwr, dwr ? dwr_replicas : 0, N,
                                                                                  K, D, packed);
   G2V_LAUNCH_CHECK("stats_pack_kernel");
-  return G2V_OK;
-}
-
-int launch_ema_update(float* cs, float* ema_w, const float* E_old, float* E_new, const float* packed,
-                      float decay, float eps, int K, int D, cudaStream_t st) {
-  const float one_m = (float)(1.0 - (double)decay);
-  const float keps = (float)((double)K * (double)eps);
-  ema_cs_kernel<<<1, 1024, 0, st>>>(cs, packed, decay, one_m, eps, keps, K, D);
-  G2V_LAUNCH_CHECK("ema_cs_kernel");
-  ema_w_kernel<<<grid_for((long long)K * D, 256, 8), 256, 0, st>>>(cs, ema_w, E_old, E_new, packed, decay, one_m, K, D);
-  G2V_LAUNCH_CHECK("ema_w_kernel");
-  return G2V_OK;
-}
-
-int launch_kmeans_update(const float* E_old, const float* packed, int K, int D, float* E_new, double* shift2,
-                         cudaStream_t st) {
-  kmeans_update_kernel<<<grid_for((long long)K * D, 256, 8), 256, 0, st>>>(E_old, packed, K, D, E_new, shift2);
-  G2V_LAUNCH_CHECK("kmeans_update_kernel");
   return G2V_OK;
 }
 
@@ -1265,13 +927,6 @@ int launch_onehot(const int32_t* idx, int64_t N, int K, float* enc, cudaStream_t
   if (vec) onehot_kernel<true><<<grid, 256, 0, st>>>(idx, N, K, enc);
   else onehot_kernel<false><<<grid, 256, 0, st>>>(idx, N, K, enc);
   G2V_LAUNCH_CHECK("onehot_kernel");
-  return G2V_OK;
-}
-
-int launch_stats_finalize(const float* packed, int K, int D, float coef_codebook, float coef_commit,
-                          float* loss, float* ppl, cudaStream_t st) {
-  stats_finalize_kernel<<<1, 1024, 0, st>>>(packed, K, D, coef_codebook, coef_commit, loss, ppl);
-  G2V_LAUNCH_CHECK("stats_finalize_kernel");
   return G2V_OK;
 }
 

@@ -1,7 +1,7 @@
 // Tensor-core nearest-code search for sm_100a: tcgen05.mma (fp16 operands, fp32 accumulators in
 // TMEM) fed by TMA, fused with an argmin epilogue, so the [N,K] distance matrix never exists.
 //
-// run_tc() picks one of three sweep kernels, all on the caller's stream:
+// run_tc() picks one of two sweep kernels, all on the caller's stream:
 //   tc_tmem_kernel<ZT>        few code tiles (K <= 576 at D = 400), fp32 / bf16 / fp16 rows.  CTA pairs
 //                             (cta_group::2, UMMA M = 256).  Rows stream by TMA into a ring of staging slots;
 //                             8 converter warps round them to fp16 in registers, keep ||z||^2 and the exact
@@ -10,7 +10,6 @@
 //   tc_search_kernel<CG,FUSED> everything else.  The A operand is an fp16 row tile in shared memory: written by
 //                             row_prep_kernel beforehand (with per-row constants; CTA pairs, deep codebook
 //                             ring -- the large-K path) or converted in-kernel from an fp32 staging ring (FUSED).
-//   tc_resident_kernel<ZT>    experimental (G2V_TC_RES=1): fp16 codebook resident in the pair's shared memory.
 // Warp roles in every variant: TMA producers (codebook stages / rows), one MMA-issuing warp (one elected lane;
 // two accumulator stages in TMEM), 8 epilogue warps: tcgen05.ld -> d = e2 - 2 z.e as a 23-bit fixed-point
 // key (packed FFMA2, FMNMX, IMAD) -> 32 running top-2 chains per row (3 VIMNMX per key).
@@ -58,8 +57,11 @@ constexpr int kMaxK = 16384;            // 9-bit column-group field of the key
 #define G2V_TRACE 0
 #endif
 constexpr bool kTraceBuild = G2V_TRACE != 0;
-constexpr unsigned kDbgSkipMma = 0x100u, kDbgSkipEpi = 0x200u, kDbgSkipConv = 0x400u, kDbgPrefetch = 0x800u,
-                   kDbgNoB = 0x1000u, kDbgNoZ = 0x2000u;   // G2V_TC_DEBUG bring-up switches (timing only)
+// bring-up switches (ablation timing, results are wrong with them): only in a -DG2V_TRACE=1 build, where the
+// G2V_TC_DEBUG environment variable sets them; in the product build the masks are 0 and every test on them folds away
+constexpr unsigned kDbgOn = kTraceBuild ? 1u : 0u;
+constexpr unsigned kDbgSkipMma = 0x100u * kDbgOn, kDbgSkipEpi = 0x200u * kDbgOn, kDbgSkipConv = 0x400u * kDbgOn,
+                   kDbgPrefetch = 0x800u * kDbgOn, kDbgNoB = 0x1000u * kDbgOn, kDbgNoZ = 0x2000u * kDbgOn;
 
 struct RowInfo {       // 32 bytes per row, written by row_prep_kernel
   float cS;            // -2 / (scale_z * scale_e) * S
@@ -963,59 +965,10 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------
-// codebook-resident variant: K * D small enough that half of the fp16 codebook stays in one SM
+// tensor-memory helpers of tc_tmem_kernel (A operand written by tcgen05.st, read by tcgen05.mma)
 // ------------------------------------------------------------------------------------------
-// A CTA pair (cta_group::2, M = 256 rows per MMA) keeps the whole fp16 codebook in shared memory, half
-// in each CTA, for the lifetime of the kernel: the codebook is read from L2 once per pair instead of
-// once per row tile, which is what bounds the streaming variant at K <= 512 (L2 -> SM throughput and
-// shared-memory bandwidth).  The rows never touch shared memory: 8 converter warps
-// load them from global memory (8 rows x 64 contiguous bytes per warp instruction), round to fp16 in
-// registers and write the A operand straight into tensor memory (tcgen05.st.16x256b: lane = row,
-// 32-bit column = two K elements), from where tcgen05.mma reads it.  TMEM columns: [0, Dp/2) A operand,
-// then two accumulator stages of `ntile` codes each.
-constexpr int RES_THREADS = 640;        // 4 control warps, 8 epilogue warps, 8 converter warps
-constexpr int RES_CONV_WARP0 = 12;
-constexpr int RES_CONV_WARPS = 8;
-
-struct ResParams {
-  long long N;
-  int K, D, Dp;
-  int n_full, n_tail, n_chunks;   // K panels of the A operand: 64 columns, then 16-column tails
-  int ntile, n_ntiles, n_last;    // codes per accumulator stage; code tiles; codes of the last tile (multiple of 16)
-  int a_bufs, acc_col0;           // A operand buffers in TMEM (1 or 2); first accumulator column
-  int n_row_tiles;                // tiles of 256 rows (128 per CTA)
-  int n_ksteps;
-  int Kpad;                       // (n_ntiles - 1) * ntile + n_last
-  uint32_t tile_stride;           // bytes of one full code tile in this CTA's half of the codebook
-  uint32_t b_bytes;               // bytes of this CTA's half of the codebook
-  const void* z;
-  const CbHeader* hdr;
-  const float* ntab;
-  const float* e2;
-  int* idx;
-  int* pair_list;
-  int* full_list;
-  int* chain_list;
-  int* counters;
-  long long* trace;               // bring-up aid (nullptr = off), as in TcParams
-  unsigned flags;
-};
-
-struct ResPlan {
-  uint32_t b_off, e2_off, xch_off, rs_off, bar_off, tmem_off, total;
-};
-constexpr int RES_NBARS = 2 + 6 * MAX_CHUNKS + 4 + RS_RING;
-__host__ __device__ inline ResPlan res_plan(uint32_t b_bytes, int Kpad) {
-  ResPlan p;
-  p.b_off = 0;
-  p.e2_off = (b_bytes + 1023u) & ~1023u;
-  p.xch_off = p.e2_off + (((uint32_t)Kpad * 4u + 127u) & ~127u);
-  p.rs_off = p.xch_off + TM * 12 * 4;
-  p.bar_off = p.rs_off + RS_RING * TM * 8;
-  p.tmem_off = p.bar_off + 8 * RES_NBARS;
-  p.total = p.tmem_off + 16;
-  return p;
-}
+constexpr int TME_CONV_WARP0 = 12;
+constexpr int TME_CONV_WARPS = 8;
 
 __device__ __forceinline__ void tc_mma_f16_ts2(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
                                                uint32_t accumulate) {
@@ -1040,393 +993,6 @@ __device__ __forceinline__ void tc_st_16x256b_x1(uint32_t taddr, uint32_t v0, ui
                : "memory");
 }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-// four consecutive row elements as fp32.  asm volatile: the loads must stay where they are issued (one
-// K panel ahead of their use); an ordinary invariant load would be sunk past the barrier waits to its use
-__device__ __forceinline__ float4 ld_row4(const float* p) {
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ uint2 ld_row4_raw16(const void* p) {
-  uint2 u;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0, %1}, [%2];" : "=r"(u.x), "=r"(u.y) : "l"(p));
-  return u;
-}
-__device__ __forceinline__ float4 ld_row4(const __half* p) {
-  const uint2 u = ld_row4_raw16(p);
-  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-  return make_float4(a.x, a.y, b.x, b.y);
-}
-__device__ __forceinline__ float4 ld_row4(const __nv_bfloat16* p) {
-  const uint2 u = ld_row4_raw16(p);
-  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16),
-                     __uint_as_float(u.y & 0xFFFF0000u));
-}
-
-template <typename ZT>
-__global__ void __launch_bounds__(RES_THREADS, 1)
-tc_resident_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBt,
-                   const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmBlt, const ResParams P) {
-  extern __shared__ unsigned char smem_dyn[];
-  const uint32_t raw = smem_u32(smem_dyn);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  unsigned char* gbase = smem_dyn + (base - raw);
-  const ResPlan sp = res_plan(P.b_bytes, P.Kpad);
-  const uint32_t cta_rank = cluster_ctarank();
-  const bool leader = cta_rank == 0;
-  const int n_groups = gridDim.x / 2, group = blockIdx.x / 2;
-
-  const uint32_t sB = base + sp.b_off;
-  float* e2s = reinterpret_cast<float*>(gbase + sp.e2_off);
-  uint32_t* xch = reinterpret_cast<uint32_t*>(gbase + sp.xch_off);
-  float2* rowstat = reinterpret_cast<float2*>(gbase + sp.rs_off);
-  const uint32_t bars = base + sp.bar_off;
-  const uint32_t bar_bfull = bars, bar_bpeer = bars + 8u;
-  // per A buffer b and K panel c
-  auto bar_aconv = [&](int b, int c) { return bars + 8u * (2 + b * MAX_CHUNKS + c); };                     // this CTA's converters wrote it
-  auto bar_apeer = [&](int b, int c) { return bars + 8u * (2 + (2 + b) * MAX_CHUNKS + c); };               // leader: the peer's converters did
-  auto bar_aempty = [&](int b, int c) { return bars + 8u * (2 + (4 + b) * MAX_CHUNKS + c); };              // the MMAs finished reading it
-  auto bar_accfull = [&](int a) { return bars + 8u * (2 + 6 * MAX_CHUNKS + a); };
-  auto bar_accempty = [&](int a) { return bars + 8u * (2 + 6 * MAX_CHUNKS + 2 + a); };
-  auto bar_rsfull = [&](int s) { return bars + 8u * (2 + 6 * MAX_CHUNKS + 4 + s); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + sp.tmem_off);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_chunks = P.n_chunks, n_full = P.n_full;
-  auto acc_col_of = [&](uint32_t a) { return (uint32_t)P.acc_col0 + a * (uint32_t)P.ntile; };   // accumulator stage a
-  const uint32_t a_cols = (uint32_t)P.Dp / 2, abm = (uint32_t)P.a_bufs - 1u, absh = (uint32_t)P.a_bufs >> 1;   // buffer = ti & abm, use = ti >> absh
-
-  if (threadIdx.x == 0) {
-    mbar_init(bar_bfull, 1);
-    mbar_init(bar_bpeer, 1);
-    for (int b = 0; b < 2; ++b)
-      for (int c = 0; c < MAX_CHUNKS; ++c) { mbar_init(bar_aconv(b, c), RES_CONV_WARPS); mbar_init(bar_apeer(b, c), 1); mbar_init(bar_aempty(b, c), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_accfull(a), 1); mbar_init(bar_accempty(a), 16); }
-    for (int s = 0; s < RS_RING; ++s) mbar_init(bar_rsfull(s), RES_CONV_WARPS);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-  for (int i = threadIdx.x; i < P.Kpad; i += RES_THREADS) e2s[i] = (i < P.K) ? __ldg(P.e2 + i) : 0.f;
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  int trace_n = 0;
-  auto TRACE = [&](int role, int tag) {   // role 1 MMA, 2 signaller (CTA 1 only), 3 epilogue warp 4, 4 converter warp 12
-    if (kTraceBuild && P.trace && blockIdx.x == (role == 2 ? 1 : 0) && lane == 0 && trace_n < 512) {
-      long long t;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      P.trace[(role * 512 + trace_n) * 2] = tag;
-      P.trace[(role * 512 + trace_n) * 2 + 1] = t;
-      ++trace_n;
-    }
-  };
-
-  // geometry of a code tile inside this CTA's half: rows = codes of the tile / 2, one K panel after the other
-  auto tile_rows = [&](int nt) { return (uint32_t)((nt == P.n_ntiles - 1) ? P.n_last : P.ntile) >> 1; };
-  auto panel_addr = [&](int nt, int c) {
-    const uint32_t rows = tile_rows(nt);
-    return sB + (uint32_t)nt * P.tile_stride + (c < n_full ? (uint32_t)c * rows * 128u : (uint32_t)n_full * rows * 128u + (uint32_t)(c - n_full) * rows * 32u);
-  };
-
-  if (warp == 0) {
-    // =========================== codebook loader, then L2 prefetcher of the row tiles ===========================
-    if (elect_one()) {
-      mbar_expect_tx(bar_bfull, (uint32_t)P.Kpad * (uint32_t)P.Dp);   // Kpad / 2 code rows of Dp fp16
-      for (int nt = 0; nt < P.n_ntiles; ++nt) {
-        const bool last = nt == P.n_ntiles - 1;
-        const int row = nt * P.ntile + (int)(cta_rank * tile_rows(nt));
-        for (int c = 0; c < n_chunks; ++c) {
-          const bool full = c < n_full;
-          const CUtensorMap* tm = last ? (full ? &tmBl : &tmBlt) : (full ? &tmB : &tmBt);
-          tma_load_2d<1>(panel_addr(nt, c), tm, full ? c * KC : n_full * KC + (c - n_full) * KT, row, bar_bfull);
-        }
-      }
-    }
-    __syncwarp();
-    const size_t row_bytes = (size_t)P.D * sizeof(ZT);
-    auto prefetch_tile = [&](int t) {
-      if (t < P.n_row_tiles && !(P.flags & kDbgPrefetch) && elect_one()) {
-        const long long row0 = ((long long)t * 2 + cta_rank) * TM;
-        const long long rows = min((long long)TM, P.N - row0);
-        if (rows > 0) {
-          const char* p = reinterpret_cast<const char*>(P.z) + (size_t)row0 * row_bytes;
-          size_t left = ((size_t)rows * row_bytes) & ~(size_t)15;
-          while (left > 0) {
-            const uint32_t n = left > 32768 ? 32768u : (uint32_t)left;
-            l2_prefetch(p, n);
-            p += n; left -= n;
-          }
-        }
-      }
-      __syncwarp();
-    };
-    prefetch_tile(group + n_groups);
-    prefetch_tile(group + 2 * n_groups);
-    uint32_t ti = 0;
-    for (int tile = group; tile < P.n_row_tiles; tile += n_groups, ++ti) {
-      mbar_wait(bar_rsfull(ti % RS_RING), (ti / RS_RING) & 1u);      // the converters are done with this tile
-      prefetch_tile(tile + 3 * n_groups);
-    }
-  } else if (warp == 1) {
-    if (leader) {
-      // =========================== MMA issuer ===========================
-      mbar_wait(bar_bfull, 0);
-      mbar_wait_cluster(bar_bpeer, 0);
-      uint32_t it = 0, ti = 0;
-      for (int tile = group; tile < P.n_row_tiles; tile += n_groups, ++ti) {
-        const int ab = (int)(ti & abm);
-        const uint32_t apar = (ti >> absh) & 1u;
-        for (int nt = 0; nt < P.n_ntiles; ++nt, ++it) {
-          const uint32_t as = it & 1u, around = it >> 1;
-          const bool last_nt = (nt == P.n_ntiles - 1);
-          const uint32_t idesc = umma_idesc(2 * TM, last_nt ? P.n_last : P.ntile);
-          TRACE(1, 100 + nt);
-          mbar_wait(bar_accempty(as), (around & 1u) ^ 1u);
-          TRACE(1, 200 + nt);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc_col_of(as);
-          for (int c = 0; c < n_chunks; ++c) {
-            if (nt == 0) {
-              mbar_wait(bar_aconv(ab, c), apar);
-              TRACE(1, 300 + c);
-              mbar_wait_cluster(bar_apeer(ab, c), apar);
-              TRACE(1, 400 + c);
-              tc_fence_after();
-            }
-            const bool fullp = c < n_full;
-            const uint32_t b_addr = panel_addr(nt, c);
-            const uint32_t a_tmem = tmem_base + (uint32_t)ab * a_cols + (fullp ? 32u * c : 32u * n_full + 8u * (c - n_full));
-            const uint64_t bd0 = fullp ? umma_desc(b_addr, 1024, 2) : umma_desc(b_addr, 256, 6);
-            if (elect_one()) {
-              if (P.flags & kDbgSkipMma) {
-              } else if (fullp) {
-#pragma unroll
-                for (int k = 0; k < KC / KT; ++k) tc_mma_f16_ts2(d_tmem, a_tmem + 8u * k, bd0 + 2u * k, idesc, (c | k) != 0);
-              } else {
-                tc_mma_f16_ts2(d_tmem, a_tmem, bd0, idesc, c != 0);
-              }
-              if (last_nt) tc_commit<2>(bar_aempty(ab, c));
-              if (c == n_chunks - 1) tc_commit<2>(bar_accfull(as));
-            }
-            __syncwarp();
-          }
-        }
-      }
-    } else {
-      // =========================== peer: forward "panel written" to the leader ===========================
-      mbar_wait(bar_bfull, 0);
-      if (elect_one()) mbar_arrive_cluster(bar_bpeer, 0);
-      __syncwarp();
-      uint32_t ti = 0;
-      for (int tile = group; tile < P.n_row_tiles; tile += n_groups, ++ti) {
-        for (int c = 0; c < n_chunks; ++c) {
-          mbar_wait(bar_aconv((int)(ti & abm), c), (ti >> absh) & 1u);
-          TRACE(2, 100 + c);
-          if (elect_one()) mbar_arrive_cluster(bar_apeer((int)(ti & abm), c), 0);
-          __syncwarp();
-        }
-      }
-    }
-  } else if (warp >= EPI_WARP0 && warp < RES_CONV_WARP0) {
-    // =========================== epilogue ===========================
-    // as in tc_search_kernel; a warp's 16-column pieces are the codes [32 g + 16 eh, +16) inside the tile
-    const int q = warp & 3;
-    const int eh = (warp - EPI_WARP0) >> 2;
-    const int r = q * 32 + lane;
-    uint32_t* xrow = xch + (size_t)r * 12;
-    uint32_t it = 0, ti = 0;
-    const float h_sfrac = P.hdr->sfrac, h_e2min = P.hdr->e2min, h_scale_e = P.hdr->scale_e;
-    for (int tile = group; tile < P.n_row_tiles; tile += n_groups, ++ti) {
-      const long long row = ((long long)tile * 2 + cta_rank) * TM + r;
-      const bool valid = row < P.N;
-      mbar_wait(bar_rsfull(ti % RS_RING), (ti / RS_RING) & 1u);
-      const float2 st = rowstat[(ti % RS_RING) * TM + r];
-      const RowInfo ri = make_rowinfo(st.x, st.y, 1.f, h_sfrac, h_e2min, h_scale_e, P.n_ksteps);
-      uint32_t m1[16], m2[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) { m1[j] = 0xFFFFFFFFu; m2[j] = 0xFFFFFFFFu; }
-
-      for (int nt = 0; nt < P.n_ntiles; ++nt, ++it) {
-        const uint32_t as = it & 1u, around = it >> 1;
-        const int s0 = nt * P.ntile;
-        const int e_valid = min(s0 + ((nt == P.n_ntiles - 1) ? P.n_last : P.ntile), P.K);
-        const int g0 = (s0 - 16 * eh + 31) >> 5, g1 = (e_valid - 16 * eh + 31) >> 5;     // pieces g0 .. g1-1
-        if (warp == EPI_WARP0) TRACE(3, 100 + nt);
-        mbar_wait(bar_accfull(as), around & 1u);
-        if (warp == EPI_WARP0) TRACE(3, 200 + nt);
-        tc_fence_after();
-        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col_of(as) + (uint32_t)(16 * eh - s0);
-        uint32_t va[16], vb[16];
-        if (g0 < g1) tc_ld16(taddr0 + 32u * g0, va);
-        for (int g = g0; g < g1; g += 2) {
-          tc_wait_ld();
-          if (g + 1 < g1) tc_ld16(taddr0 + 32u * (g + 1), vb);
-          if (!(P.flags & kDbgSkipEpi)) {
-            const int cb0 = 32 * g + 16 * eh, nv = e_valid - cb0;
-            if (nv >= 16) epi_chunk<false>(va, e2s + cb0, ri.cS, ri.S, (uint32_t)g, 16, m1, m2);
-            else epi_chunk<true>(va, e2s + cb0, ri.cS, ri.S, (uint32_t)g, nv, m1, m2);
-          }
-          if (g + 1 < g1) {
-            tc_wait_ld();
-            if (g + 2 < g1) tc_ld16(taddr0 + 32u * (g + 2), va);
-            if (!(P.flags & kDbgSkipEpi)) {
-              const int cb0 = 32 * (g + 1) + 16 * eh, nv = e_valid - cb0;
-              if (nv >= 16) epi_chunk<false>(vb, e2s + cb0, ri.cS, ri.S, (uint32_t)(g + 1), 16, m1, m2);
-              else epi_chunk<true>(vb, e2s + cb0, ri.cS, ri.S, (uint32_t)(g + 1), nv, m1, m2);
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (warp == EPI_WARP0) TRACE(3, 300 + nt);
-        if (lane == 0) {
-          if (leader) mbar_arrive(bar_accempty(as));
-          else mbar_arrive_cluster(bar_accempty(as), 0);
-        }
-      }
-
-      const Cand none{0xFFFFFFFFu, 0xFFFFFFFFu, 0};
-      Cand c1 = none, c2 = none, c3 = none;
-      uint32_t k4 = 0xFFFFFFFFu;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) cand_insert(c1, c2, c3, k4, Cand{m1[j], m2[j], eh * 16 + j});
-      if (eh == 1) {
-        xrow[0] = c1.key; xrow[1] = c1.key2; xrow[2] = (uint32_t)c1.j;
-        xrow[3] = c2.key; xrow[4] = c2.key2; xrow[5] = (uint32_t)c2.j;
-        xrow[6] = c3.key; xrow[7] = c3.key2; xrow[8] = (uint32_t)c3.j;
-        xrow[9] = k4;
-      }
-      asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
-      if (eh == 0) {
-        cand_insert(c1, c2, c3, k4, Cand{xrow[0], xrow[1], (int)xrow[2]});
-        cand_insert(c1, c2, c3, k4, Cand{xrow[3], xrow[4], (int)xrow[5]});
-        cand_insert(c1, c2, c3, k4, Cand{xrow[6], xrow[7], (int)xrow[8]});
-        k4 = min(k4, xrow[9]);
-        finish_row(c1, c2, c3, k4, ri, row, valid, P.K, P.ntab, P.flags, P.idx, P.pair_list, P.chain_list, P.full_list, P.counters);
-      }
-      asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
-    }
-  } else if (warp >= RES_CONV_WARP0) {
-    // =========================== converters ===========================
-    // warp cw owns the 16 TMEM lanes (rows) 32 (cw % 4) + 16 (cw / 4) ...; in the 16x256b store pattern
-    // lane i holds, per K step of 16, the elements 4 (i % 4) .. +3 of the rows i / 4 and i / 4 + 8
-    const int cw = warp - RES_CONV_WARP0;
-    const int lane0_row = 32 * (cw & 3) + 16 * (cw >> 2);
-    const int ra_l = lane0_row + (lane >> 2), rb_l = ra_l + 8;
-    const int kq = (lane & 3) * 4;
-    const uint32_t t_lane = tmem_base + ((uint32_t)lane0_row << 16);
-    const ZT* zb = reinterpret_cast<const ZT*>(P.z);
-    float z2a = 0.f, r2a = 0.f, z2b = 0.f, r2b = 0.f;
-
-    auto issue = [&](int tile, int c, float4 (&buf)[8]) {
-      const long long row0 = ((long long)tile * 2 + cta_rank) * TM;
-      const ZT* pa = zb + (size_t)min(row0 + ra_l, P.N - 1) * P.D + kq;
-      const ZT* pb = zb + (size_t)min(row0 + rb_l, P.N - 1) * P.D + kq;
-      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (P.flags & kDbgNoZ) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) buf[j] = zero;
-      } else if (c < n_full) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int col = c * KC + j * KT;
-          const bool in = col + kq < P.D;
-          buf[2 * j] = in ? ld_row4(pa + col) : zero;
-          buf[2 * j + 1] = in ? ld_row4(pb + col) : zero;
-        }
-      } else {
-        const int col = n_full * KC + (c - n_full) * KT;
-        const bool in = col + kq < P.D;
-        buf[0] = in ? ld_row4(pa + col) : zero;
-        buf[1] = in ? ld_row4(pb + col) : zero;
-      }
-    };
-    auto cvt = [&](const float4 v, float& z2, float& r2, uint32_t& w0, uint32_t& w1) {
-      const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
-      const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-      const float e0 = v.x - f01.x, e1 = v.y - f01.y, e2r = v.z - f23.x, e3 = v.w - f23.y;
-      z2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, z2))));
-      r2 = fmaf(e0, e0, fmaf(e1, e1, fmaf(e2r, e2r, fmaf(e3, e3, r2))));
-      w0 = *reinterpret_cast<const uint32_t*>(&h01);
-      w1 = *reinterpret_cast<const uint32_t*>(&h23);
-    };
-    auto process = [&](int c, uint32_t ti, const float4 (&buf)[8]) {
-      const int ab = (int)(ti & abm);
-      if (cw == 0) TRACE(4, 100 + c);
-      mbar_wait(bar_aempty(ab, c), ((ti >> absh) & 1u) ^ 1u);   // the MMAs of the buffer's previous row tile have read this panel
-      if (cw == 0) TRACE(4, 200 + c);
-      tc_fence_after();
-      const uint32_t t_buf = t_lane + (uint32_t)ab * a_cols;
-      if (c < n_full) {
-        uint32_t w[16];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          cvt(buf[2 * j], z2a, r2a, w[4 * j], w[4 * j + 1]);
-          cvt(buf[2 * j + 1], z2b, r2b, w[4 * j + 2], w[4 * j + 3]);
-        }
-        tc_st_16x256b_x4(t_buf + 32u * c, w);
-      } else {
-        uint32_t w0, w1, w2, w3;
-        cvt(buf[0], z2a, r2a, w0, w1);
-        cvt(buf[1], z2b, r2b, w2, w3);
-        tc_st_16x256b_x1(t_buf + 32u * n_full + 8u * (c - n_full), w0, w1, w2, w3);
-      }
-      if (cw == 0) TRACE(4, 300 + c);
-      tc_wait_st();
-      if (cw == 0) TRACE(4, 400 + c);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_aconv(ab, c));
-    };
-
-    float4 bA[8], bB[8];
-    int tile = group, c = 0;
-    uint32_t ti = 0;
-    bool ping = true;
-    if (tile < P.n_row_tiles) issue(tile, 0, bA);
-    while (tile < P.n_row_tiles) {
-      int nc = c + 1, ntl = tile;
-      if (nc == n_chunks) { nc = 0; ntl = tile + n_groups; }
-      if (ping) {
-        if (ntl < P.n_row_tiles) issue(ntl, nc, bB);
-        process(c, ti, bA);
-      } else {
-        if (ntl < P.n_row_tiles) issue(ntl, nc, bA);
-        process(c, ti, bB);
-      }
-      ping = !ping;
-      if (nc == 0) {
-        // row statistics of the finished tile: sum over the four lanes that share a row
-        z2a += __shfl_xor_sync(0xffffffffu, z2a, 1); r2a += __shfl_xor_sync(0xffffffffu, r2a, 1);
-        z2b += __shfl_xor_sync(0xffffffffu, z2b, 1); r2b += __shfl_xor_sync(0xffffffffu, r2b, 1);
-        z2a += __shfl_xor_sync(0xffffffffu, z2a, 2); r2a += __shfl_xor_sync(0xffffffffu, r2a, 2);
-        z2b += __shfl_xor_sync(0xffffffffu, z2b, 2); r2b += __shfl_xor_sync(0xffffffffu, r2b, 2);
-        if ((lane & 3) == 0) {
-          rowstat[(ti % RS_RING) * TM + ra_l] = make_float2(z2a, r2a);
-          rowstat[(ti % RS_RING) * TM + rb_l] = make_float2(z2b, r2b);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_rsfull(ti % RS_RING));
-        z2a = r2a = z2b = r2b = 0.f;
-        ++ti;
-      }
-      c = nc; tile = ntl;
-    }
-  }
-
-  tc_fence_before();
-  cluster_sync_all();
-  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-}
-
 // ------------------------------------------------------------------------------------------
 // "tmem" variant: fp32 rows -> fp16 A operand in tensor memory, CTA pairs, both operands streamed
 // ------------------------------------------------------------------------------------------
@@ -1540,11 +1106,11 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TME_MAX_BST; ++s) { mbar_init(bar_bfull(s), 1); mbar_init(bar_bempty(s), 1); }
-    for (int s = 0; s < TME_MAX_ZSLOTS; ++s) { mbar_init(bar_zfull(s), 1); mbar_init(bar_zempty(s), RES_CONV_WARPS); }
+    for (int s = 0; s < TME_MAX_ZSLOTS; ++s) { mbar_init(bar_zfull(s), 1); mbar_init(bar_zempty(s), TME_CONV_WARPS); }
     for (int b = 0; b < 2; ++b)
-      for (int c = 0; c < MAX_CHUNKS; ++c) { mbar_init(bar_aconv(b, c), RES_CONV_WARPS); mbar_init(bar_apeer(b, c), 1); mbar_init(bar_aempty(b, c), 1); }
+      for (int c = 0; c < MAX_CHUNKS; ++c) { mbar_init(bar_aconv(b, c), TME_CONV_WARPS); mbar_init(bar_apeer(b, c), 1); mbar_init(bar_aempty(b, c), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(bar_accfull(a), 1); mbar_init(bar_accempty(a), 16); }
-    for (int s = 0; s < RS_RING; ++s) mbar_init(bar_rsfull(s), RES_CONV_WARPS);
+    for (int s = 0; s < RS_RING; ++s) mbar_init(bar_rsfull(s), TME_CONV_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -1686,7 +1252,7 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
         if (++slot == NZ) { slot = 0; ph ^= 1u; }
       }
     }
-  } else if (warp >= EPI_WARP0 && warp < RES_CONV_WARP0) {
+  } else if (warp >= EPI_WARP0 && warp < TME_CONV_WARP0) {
     // =========================== epilogue ===========================
     // as in tc_search_kernel; a warp's 16-column pieces are the codes [32 g + 16 eh, +16) inside the tile
     const int q = warp & 3;
@@ -1753,13 +1319,13 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
       }
       asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
     }
-  } else if (warp >= RES_CONV_WARP0) {
+  } else if (warp >= TME_CONV_WARP0) {
     // =========================== converters ===========================
     // warp cw owns the 16 TMEM lanes (rows) 32 (cw % 4) + 16 (cw / 4) ...; in the 16x256b store pattern
     // lane i holds, per K step of 16, the elements 4 (i % 4) .. +3 of the rows i / 4 and i / 4 + 8.
     // A slot row is 128 bytes (32 fp32) with the 16-byte chunks XOR-swizzled by row % 8, so the eight rows
     // a quarter-warp reads hit all banks.
-    const int cw = warp - RES_CONV_WARP0;
+    const int cw = warp - TME_CONV_WARP0;
     const int lane0_row = 32 * (cw & 3) + 16 * (cw >> 2);
     const int ra_l = lane0_row + (lane >> 2), rb_l = ra_l + 8;
     const uint32_t t_lane = tmem_base + ((uint32_t)lane0_row << 16);
@@ -2211,8 +1777,36 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// Tensor maps are pure functions of (pointer, extents, box, swizzle, element type); encoding one costs a driver
+// call, and a search needs six or seven.  A small per-thread cache keeps the maps of the buffers a training loop
+// or a tokeniser reuses every step (codebook aux buffer, workspace, input batch), so the steady state of a
+// small-batch step makes no driver calls for them.
+struct MapKey {
+  const void* gptr;
+  uint64_t rows, cols;
+  uint32_t box_cols, box_rows;
+  int sw, f32;
+  bool operator==(const MapKey& o) const {
+    return gptr == o.gptr && rows == o.rows && cols == o.cols && box_cols == o.box_cols && box_rows == o.box_rows &&
+           sw == o.sw && f32 == o.f32;
+  }
+};
+constexpr int kMapCache = 32;
+struct MapCache {
+  MapKey key[kMapCache];
+  alignas(64) CUtensorMap map[kMapCache];
+  int used = 0, next = 0;
+};
+
 int make_map(CUtensorMap* tm, const void* gptr, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows,
              CUtensorMapSwizzle sw, bool f32 = false) {
+  static thread_local MapCache cache;
+  const MapKey k{gptr, rows, cols, box_cols, box_rows, (int)sw, f32 ? 1 : 0};
+  for (int i = 0; i < cache.used; ++i)
+    if (cache.key[i] == k) {
+      *tm = cache.map[i];
+      return G2V_OK;
+    }
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error_detail("cuTensorMapEncodeTiled entry point not available");
@@ -2231,10 +1825,60 @@ int make_map(CUtensorMap* tm, const void* gptr, uint64_t rows, uint64_t cols, ui
                      (unsigned long long)rows, (unsigned long long)cols, box_cols, box_rows);
     return G2V_ERR_CUDA;
   }
+  const int slot = cache.used < kMapCache ? cache.used++ : (cache.next++ % kMapCache);
+  cache.key[slot] = k;
+  cache.map[slot] = *tm;
+  return G2V_OK;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device, size): the attribute sticks
+int set_dyn_smem(const void* func, size_t bytes) {
+  struct Ent { const void* f; int dev; size_t bytes; };
+  static thread_local Ent ent[16];
+  static thread_local int n = 0;
+  int dev = 0;
+  G2V_CUDA_CHECK(cudaGetDevice(&dev));
+  for (int i = 0; i < n; ++i)
+    if (ent[i].f == func && ent[i].dev == dev) {
+      if (ent[i].bytes >= bytes) return G2V_OK;
+      G2V_CUDA_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      ent[i].bytes = bytes;
+      return G2V_OK;
+    }
+  G2V_CUDA_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  if (n < 16) ent[n++] = Ent{func, dev, bytes};
   return G2V_OK;
 }
 
 inline size_t al256(size_t v) { return (v + 255) / 256 * 256; }
+
+// Experiment knobs, read from the environment ONCE per process (-1 = not set).  None of them changes results.
+struct Tuning {
+  int tmem_mode, a_bufs, bstages, zslots, fused, cg, tmem16;
+  unsigned dbg_flags;          // -DG2V_TRACE=1 builds only
+  long long* trace;            // -DG2V_TRACE=1 builds only: device buffer the role timeline is written to
+};
+const Tuning& tuning() {
+  static const Tuning t = [] {
+    auto geti = [](const char* name) { const char* e = getenv(name); return e ? atoi(e) : -1; };
+    Tuning u;
+    u.tmem_mode = geti("G2V_TC_TMEM");
+    u.a_bufs = geti("G2V_TC_ABUFS");
+    u.bstages = geti("G2V_TC_BSTAGES");
+    u.zslots = geti("G2V_TC_ZSLOTS");
+    u.fused = geti("G2V_TC_FUSED");
+    u.cg = geti("G2V_TC_CG");
+    u.tmem16 = geti("G2V_TC_TMEM16");
+    u.dbg_flags = 0;
+    u.trace = nullptr;
+#if G2V_TRACE
+    if (const char* e = getenv("G2V_TC_DEBUG")) u.dbg_flags = ((unsigned)atoi(e) & 63u) << 8;
+    if (const char* e = getenv("G2V_TC_TRACE")) u.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
+#endif
+    return u;
+  }();
+  return t;
+}
 
 struct TcWs {
   size_t z16, rowinfo, pairs, fulls, chains, counters, scratch, total;
@@ -2267,78 +1911,14 @@ int run_recheck(const ZT* z, int z_dtype, const float* E, const void* cb, int64_
   if (K >= 96 && slices < 4) slices = 4;
   int* arrive = counters + 64;
   const size_t smem = (size_t)((D + 31) / 32 * 32) * sizeof(float);
-  rerank_kernel<ZT><<<num_sms() * 4, 256, smem, st>>>(z, E, K, D, pairs, chains, fulls, counters, slices,
+  // every list holds at most N entries and a CTA's eight warps take one entry each per pass: a small batch gets
+  // a small grid (a fixed 4-CTAs-per-SM grid costs ~25 us of launch + drain for a 128-row step)
+  const long long want = (N + 7) / 8, cap = (long long)num_sms() * 4;
+  const int rgrid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
+  rerank_kernel<ZT><<<rgrid, 256, smem, st>>>(z, E, K, D, pairs, chains, fulls, counters, slices,
                                                      reinterpret_cast<RerankSlot*>(scratch), arrive, idx, stats);
   G2V_LAUNCH_CHECK("rerank_kernel");
   return launch_full_recheck(z, z_dtype, E, cb, K, D, fulls, counters + 1, N, idx, stats, true, st);
-}
-
-// Codebook-resident variant: geometry, or false if the shape does not qualify.
-//  * half of the fp16 codebook (+ small per-CTA state) must fit in one SM's shared memory;
-//  * TMEM holds the A operand (Dp / 2 columns) and two accumulator stages of `ntile` codes;
-//  * rows are read as 16-byte (fp32) / 8-byte (16-bit) vectors.
-bool plan_resident(const void* z, int z_dtype, int64_t N, int K, int D, ResParams* R) {
-  const int Dp = round_up(D, 16);
-  const size_t esz = z_dtype == G2V_F32 ? 4 : 2;
-  if (D % 4 != 0 || (reinterpret_cast<uintptr_t>(z) & (4 * esz - 1)) != 0) return false;
-  if (N <= TM || Dp > kMaxDp) return false;
-  // two A buffers when TMEM still has room for two accumulator stages of >= 48 codes (G2V_TC_ABUFS=1|2 overrides)
-  int a_bufs = (512 - 2 * (Dp / 2)) / 2 >= 48 ? 2 : 1;
-  if (const char* env = getenv("G2V_TC_ABUFS")) a_bufs = atoi(env) == 2 && (512 - 2 * (Dp / 2)) / 2 >= 16 ? 2 : 1;
-  const int acc_col0 = round_up(a_bufs * (Dp / 2), 16);
-  const int nt_max = std::min(256, ((512 - acc_col0) / 2) & ~15);
-  int best_nt = 0, best_n = 1 << 30, best_pad = 1 << 30, best_last = 0;
-  for (int nt = nt_max; nt >= 16 && nt >= nt_max - 64; nt -= 16) {
-    const int n = (K + nt - 1) / nt;
-    const int last = round_up(K - (n - 1) * nt, 16);
-    if (last > nt) continue;
-    const int pad = (n - 1) * nt + last;
-    if (n < best_n || (n == best_n && pad < best_pad)) { best_nt = nt; best_n = n; best_pad = pad; best_last = last; }
-  }
-  if (best_nt == 0) return false;
-  R->N = N; R->K = K; R->D = D; R->Dp = Dp;
-  R->n_full = Dp / KC; R->n_tail = (Dp % KC) / KT; R->n_chunks = R->n_full + R->n_tail;
-  if (R->n_chunks > MAX_CHUNKS) return false;
-  R->ntile = best_nt; R->n_ntiles = best_n; R->n_last = best_last; R->Kpad = best_pad;
-  R->a_bufs = a_bufs; R->acc_col0 = acc_col0;
-  R->n_ksteps = Dp / KT;
-  R->tile_stride = (uint32_t)round_up((best_nt / 2) * Dp * 2, 1024);
-  R->b_bytes = (uint32_t)(best_n - 1) * R->tile_stride + (uint32_t)(best_last / 2) * Dp * 2;
-  R->n_row_tiles = (int)((N + 2 * TM - 1) / (2 * TM));
-  R->z = z;
-  return res_plan(R->b_bytes, R->Kpad).total + 1024 <= 227 * 1024;
-}
-
-template <typename ZT>
-int launch_resident(ResParams& R, const __half* e16, int Kp, cudaStream_t st) {
-  alignas(64) CUtensorMap tmB, tmBt, tmBl, tmBlt;
-  int rc;
-  const uint32_t main_box = (R.Dp >= KC) ? KC : KT;
-  const CUtensorMapSwizzle main_sw = (R.Dp >= KC) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
-  const uint32_t brow = (uint32_t)R.ntile / 2, blast = (uint32_t)R.n_last / 2;
-  if ((rc = make_map(&tmB, e16, (uint64_t)Kp, (uint64_t)R.Dp, main_box, brow, main_sw))) return rc;
-  if ((rc = make_map(&tmBt, e16, (uint64_t)Kp, (uint64_t)R.Dp, KT, brow, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
-  if ((rc = make_map(&tmBl, e16, (uint64_t)Kp, (uint64_t)R.Dp, main_box, blast, main_sw))) return rc;
-  if ((rc = make_map(&tmBlt, e16, (uint64_t)Kp, (uint64_t)R.Dp, KT, blast, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
-  const size_t smem = res_plan(R.b_bytes, R.Kpad).total + 1024;
-  G2V_CUDA_CHECK(cudaFuncSetAttribute(tc_resident_kernel<ZT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int max_groups = num_sms() / 2;
-  const int groups = R.n_row_tiles < max_groups ? R.n_row_tiles : max_groups;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(groups * 2);
-  cfg.blockDim = dim3(RES_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  G2V_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_resident_kernel<ZT>, tmB, tmBt, tmBl, tmBlt, R));
-  G2V_LAUNCH_CHECK("tc_resident_kernel");
-  return G2V_OK;
 }
 
 // "tmem" variant: geometry, or false if the shape does not qualify (fp32 rows read through TMA: D % 4 == 0
@@ -2347,8 +1927,7 @@ bool plan_tmem(const void* z, int z_dtype, int64_t N, int K, int D, int a_bufs, 
   const int Dp = round_up(D, 16);
   // rows are read through TMA: 16-byte aligned base and row pitch (G2V_TC_TMEM16=0 keeps 16-bit rows on the
   // row_prep + shared-memory-operand path)
-  static const bool tmem16 = [] { const char* e = getenv("G2V_TC_TMEM16"); return !(e && atoi(e) == 0); }();
-  if (z_dtype != G2V_F32 && !tmem16) return false;
+  if (z_dtype != G2V_F32 && tuning().tmem16 == 0) return false;
   if (D % (z_dtype == G2V_F32 ? 4 : 8) != 0 || (reinterpret_cast<uintptr_t>(z) & 15) != 0) return false;
   if (N <= TM || Dp > kMaxDp || Dp < KC) return false;
   // a_bufs == 2: the fp16 rows of the next tile are converted while the MMAs still read this one's; what is
@@ -2376,9 +1955,9 @@ bool plan_tmem(const void* z, int z_dtype, int64_t N, int K, int D, int a_bufs, 
   // codebook ring: ~1.5 us of L2 latency at 288 MMA cycles per full panel of 144 codes (~105 KB in flight,
   // whatever the stage size); the rest goes to the row slots
   int nb = std::max(5, std::min(TME_MAX_BST, (int)((5u * 21504u + R->b_stage - 1) / R->b_stage)));
-  if (const char* env = getenv("G2V_TC_BSTAGES")) nb = std::max(2, std::min(TME_MAX_BST, atoi(env)));
+  if (tuning().bstages >= 0) nb = std::max(2, std::min(TME_MAX_BST, tuning().bstages));
   int nz = TME_MAX_ZSLOTS;
-  if (const char* env = getenv("G2V_TC_ZSLOTS")) nz = std::max(2, std::min(TME_MAX_ZSLOTS, atoi(env)));
+  if (tuning().zslots >= 0) nz = std::max(2, std::min(TME_MAX_ZSLOTS, tuning().zslots));
   while (nz > 2 && tme_plan(nb, R->b_stage, nz, R->Kpad).total + 1024 > 227 * 1024) --nz;
   R->nb = nb; R->nz = nz;
   return tme_plan(nb, R->b_stage, nz, R->Kpad).total + 1024 <= 227 * 1024;
@@ -2397,7 +1976,7 @@ int launch_tmem(TmeParams& R, const ZT* z, const __half* e16, int Kp, cudaStream
   if ((rc = make_map(&tmBl, e16, (uint64_t)Kp, (uint64_t)R.Dp, KC, blast, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map(&tmBlt, e16, (uint64_t)Kp, (uint64_t)R.Dp, KT, blast, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
   const size_t smem = tme_plan(R.nb, R.b_stage, R.nz, R.Kpad).total + 1024;
-  G2V_CUDA_CHECK(cudaFuncSetAttribute(tc_tmem_kernel<ZT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  { const int rc_attr = set_dyn_smem(reinterpret_cast<const void*>(&tc_tmem_kernel<ZT>), smem); if (rc_attr) return rc_attr; }
   const int max_groups = num_sms() / 2;
   const int groups = R.n_row_tiles < max_groups ? R.n_row_tiles : max_groups;
   cudaLaunchConfig_t cfg = {};
@@ -2436,12 +2015,11 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
   {   // fp32 rows, few code tiles: A operand in tensor memory, CTA pairs (G2V_TC_TMEM=0 switches the variant off,
       // =2 forces it for any K)
     TmeParams R;
-    const char* env = getenv("G2V_TC_TMEM");
-    const int mode = env ? atoi(env) : 1;
+    const int mode = tuning().tmem_mode >= 0 ? tuning().tmem_mode : 1;
     bool use = mode != 0 && plan_tmem(z, z_dtype, N, K, D, 1, &R) && (mode == 2 || R.n_ntiles <= 4);
     if (use) {      // G2V_TC_ABUFS=1|2: single / double A operand buffer
       int a_bufs = kTmeDefaultABufs;
-      if (const char* ab = getenv("G2V_TC_ABUFS")) a_bufs = atoi(ab) == 2 ? 2 : 1;
+      if (tuning().a_bufs >= 0) a_bufs = tuning().a_bufs == 2 ? 2 : 1;
       TmeParams R2;
       if (a_bufs == 2 && plan_tmem(z, z_dtype, N, K, D, 2, &R2)) R = R2;
     }
@@ -2449,35 +2027,13 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
       R.hdr = hdr; R.e2 = e2; R.idx = idx;
       R.ntab = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_tab_offset());
       R.pair_list = pairs; R.full_list = fulls; R.chain_list = chains; R.counters = counters; R.flags = flags;
-      if (const char* dbg = getenv("G2V_TC_DEBUG")) R.flags |= ((unsigned)atoi(dbg) & 63u) << 8;
-      R.trace = nullptr;
-      if (const char* tr = getenv("G2V_TC_TRACE")) R.trace = reinterpret_cast<long long*>(strtoull(tr, nullptr, 0));
+      R.flags |= tuning().dbg_flags;
+      R.trace = tuning().trace;
       G2V_CUDA_CHECK(cudaMemsetAsync(counters, 0, 256 + kRerankArriveBytes, st));
       cudaEvent_t pev0, pev1;
       profile_take(&pev0, &pev1);
       if (pev0) G2V_CUDA_CHECK(cudaEventRecord(pev0, st));
       const int rc = launch_tmem<ZT>(R, z, e16, Kp, st);
-      if (rc) return rc;
-      if (pev1) G2V_CUDA_CHECK(cudaEventRecord(pev1, st));
-      return run_recheck(z, z_dtype, E, cb, N, K, D, pairs, chains, fulls, counters, base + w.scratch, idx, stats, flags, st);
-    }
-  }
-  {   // K * D small: codebook-resident CTA pairs.  Experimental (G2V_TC_RES=1): correct, but slower than the
-      // fused streaming variant until its row stream is staged through shared memory
-    ResParams R;
-    const char* env = getenv("G2V_TC_RES");
-    if (env && atoi(env) == 1 && plan_resident(z, z_dtype, N, K, D, &R)) {
-      R.hdr = hdr; R.e2 = e2; R.idx = idx;
-      R.ntab = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_tab_offset());
-      R.pair_list = pairs; R.full_list = fulls; R.chain_list = chains; R.counters = counters; R.flags = flags;
-      if (const char* dbg = getenv("G2V_TC_DEBUG")) R.flags |= ((unsigned)atoi(dbg) & 63u) << 8;
-      R.trace = nullptr;
-      if (const char* tr = getenv("G2V_TC_TRACE")) R.trace = reinterpret_cast<long long*>(strtoull(tr, nullptr, 0));
-      G2V_CUDA_CHECK(cudaMemsetAsync(counters, 0, 256 + kRerankArriveBytes, st));
-      cudaEvent_t pev0, pev1;
-      profile_take(&pev0, &pev1);
-      if (pev0) G2V_CUDA_CHECK(cudaEventRecord(pev0, st));
-      const int rc = launch_resident<ZT>(R, e16, Kp, st);
       if (rc) return rc;
       if (pev1) G2V_CUDA_CHECK(cudaEventRecord(pev1, st));
       return run_recheck(z, z_dtype, E, cb, N, K, D, pairs, chains, fulls, counters, base + w.scratch, idx, stats, flags, st);
@@ -2498,21 +2054,20 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
   P.n_ntiles = (K + TN - 1) / TN;
   bool fused = (z_dtype == G2V_F32) && (D % 4 == 0) && (D >= KC) && P.n_ntiles <= 2 &&
                ((reinterpret_cast<uintptr_t>(z) & 15) == 0);
-  if (const char* env = getenv("G2V_TC_FUSED")) {
-    if (atoi(env) == 0) fused = false;
+  if (tuning().fused >= 0) {
+    if (tuning().fused == 0) fused = false;
     else fused = (z_dtype == G2V_F32) && (D % 4 == 0) && (D >= KC) && ((reinterpret_cast<uintptr_t>(z) & 15) == 0);
   }
   int cg = fused ? 1 : ((N > TM) ? 2 : 1);
-  if (const char* env = getenv("G2V_TC_CG")) cg = (atoi(env) == 1) ? 1 : ((N > TM) ? 2 : 1);
+  if (tuning().cg >= 0) cg = (tuning().cg == 1) ? 1 : ((N > TM) ? 2 : 1);
   if (fused && smem_plan(P.n_full, P.n_tail, cg, 2, 3).total + 1024 > 227 * 1024) fused = false;   // needs >= 3 staging slots
   P.n_last_mma = round_up(K - (P.n_ntiles - 1) * TN, 16 * cg);
   P.n_row_tiles = (int)((N + (long long)TM * cg - 1) / ((long long)TM * cg));   // tiles of 128*cg rows
   P.rowinfo = rowinfo; P.e2 = e2; P.idx = idx;
   P.ntab = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_tab_offset());
   P.pair_list = pairs; P.full_list = fulls; P.chain_list = chains; P.counters = counters; P.flags = flags;
-  P.trace = nullptr;
-  if (const char* env = getenv("G2V_TC_TRACE")) P.trace = reinterpret_cast<long long*>(strtoull(env, nullptr, 0));
-  if (const char* env = getenv("G2V_TC_DEBUG")) P.flags |= ((unsigned)atoi(env) & 63u) << 8;   // results are wrong with these
+  P.trace = tuning().trace;
+  P.flags |= tuning().dbg_flags;
 
   const int n_ksteps = P.n_full * (KC / KT) + P.n_tail;
   P.n_ksteps = n_ksteps;
@@ -2550,11 +2105,11 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
   // ring depth: whatever shared memory is left after the resident row tile, capped at MAX_STAGES
   // (the ring has to cover the TMA round trip, ~2.5k cycles, at 512 MMA cycles per full panel)
   int nstage = fused ? (cg == 2 ? 4 : 2) : MAX_STAGES, nzslot = 0;
-  if (const char* env = getenv("G2V_TC_BSTAGES")) nstage = atoi(env) >= 2 && atoi(env) <= MAX_STAGES ? atoi(env) : nstage;
+  if (tuning().bstages >= 2 && tuning().bstages <= MAX_STAGES) nstage = tuning().bstages;
   while (nstage > 2 && smem_plan(P.n_full, P.n_tail, cg, nstage).total + 1024 > 227 * 1024) --nstage;
   if (fused) {      // the rest of shared memory becomes the fp32 staging ring (>= 3 slots or give up fusing)
     nzslot = MAX_ZSLOTS;
-    if (const char* env = getenv("G2V_TC_ZSLOTS")) nzslot = atoi(env) >= 2 && atoi(env) <= MAX_ZSLOTS ? atoi(env) : nzslot;
+    if (tuning().zslots >= 2 && tuning().zslots <= MAX_ZSLOTS) nzslot = tuning().zslots;
     while (nzslot > 0 && smem_plan(P.n_full, P.n_tail, cg, nstage, nzslot).total + 1024 > 227 * 1024) --nzslot;
     if (nzslot < 2) return G2V_ERR_UNSUPPORTED;   // cannot happen: checked when `fused` was decided
   }
@@ -2569,17 +2124,17 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
   const int groups = P.n_row_tiles < max_groups ? P.n_row_tiles : max_groups;
   if (cg == 1) {
     if (fused) {
-      G2V_CUDA_CHECK(cudaFuncSetAttribute(tc_search_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      { const int rc_attr = set_dyn_smem(reinterpret_cast<const void*>(&tc_search_kernel<1, true>), smem); if (rc_attr) return rc_attr; }
       tc_search_kernel<1, true><<<groups, NTHREADS_FUSED, smem, st>>>(tmA, tmAt, tmB, tmBt, tmBl, tmBlt, tmPf, P);
     } else {
-      G2V_CUDA_CHECK(cudaFuncSetAttribute(tc_search_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      { const int rc_attr = set_dyn_smem(reinterpret_cast<const void*>(&tc_search_kernel<1, false>), smem); if (rc_attr) return rc_attr; }
       tc_search_kernel<1, false><<<groups, NTHREADS, smem, st>>>(tmA, tmAt, tmB, tmBt, tmBl, tmBlt, tmPf, P);
     }
   } else {
     if (fused)
-      G2V_CUDA_CHECK(cudaFuncSetAttribute(tc_search_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      { const int rc_attr = set_dyn_smem(reinterpret_cast<const void*>(&tc_search_kernel<2, true>), smem); if (rc_attr) return rc_attr; }
     else
-      G2V_CUDA_CHECK(cudaFuncSetAttribute(tc_search_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      { const int rc_attr = set_dyn_smem(reinterpret_cast<const void*>(&tc_search_kernel<2, false>), smem); if (rc_attr) return rc_attr; }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(groups * 2);
     cfg.blockDim = dim3(fused ? NTHREADS_FUSED : NTHREADS);

@@ -31,12 +31,24 @@ def packed_layout(K: int, D: int) -> dict:
 
 class StatsAllReduce:
     """Callable handed to a quantizer (`layer.stats_reduce = StatsAllReduce(group)`): in-place sum
-    all-reduce of the packed statistics, stream-ordered with the surrounding kernels."""
+    all-reduce of the packed statistics.
 
-    def __init__(self, group: Optional[dist.ProcessGroup] = None):
+    overlap=False: stream-ordered on the compute stream between the pack and the finalise launch.
+    overlap=True (CUDA only): the module runs the exchange AND the finalise launch (loss, perplexity, EMA
+    update, codebook aux) on `self.stream`, a side stream that waits for the pack; the main stream meanwhile
+    runs whatever the forward pass still has to enqueue (the dense one-hot the reference's contract returns)
+    and waits for the side stream's event before the module returns -- SURVEY.md 8e "Overlap"."""
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None, overlap: bool = False,
+                 device: Optional[torch.device] = None):
         self.group = group
         self.calls = 0
         self.bytes = 0
+        self.stream: Optional[torch.cuda.Stream] = None
+        if overlap:
+            if not torch.cuda.is_available():
+                raise RuntimeError("StatsAllReduce(overlap=True) needs a CUDA device")
+            self.stream = torch.cuda.Stream(device=device)
 
     def __call__(self, packed: torch.Tensor) -> None:
         if not (dist.is_available() and dist.is_initialized()):
@@ -47,7 +59,7 @@ class StatsAllReduce:
 
 
 def enable_data_parallel_ema(layer: torch.nn.Module, group: Optional[dist.ProcessGroup] = None,
-                             ddp_mean_gradients: bool = True) -> StatsAllReduce:
+                             ddp_mean_gradients: bool = True, overlap: bool = False) -> StatsAllReduce:
     """Turn on the statistics all-reduce for an EMA quantizer.
 
     The returned loss is the loss of the concatenated batch (from the all-reduced SSE / row count).
@@ -55,7 +67,8 @@ def enable_data_parallel_ema(layer: torch.nn.Module, group: Optional[dist.Proces
     ranks by DDP (`ddp_mean_gradients=True`) it equals the single-process gradient on the
     concatenated batch; if the caller SUMS gradients across ranks instead, it is divided by the
     world size here."""
-    red = StatsAllReduce(group)
+    dev = next(layer.parameters()).device
+    red = StatsAllReduce(group, overlap=overlap and dev.type == "cuda", device=dev if dev.type == "cuda" else None)
     layer.stats_reduce = red
     layer.grad_scale = 1.0 if ddp_mean_gradients else 1.0 / float(dist.get_world_size(group))
     return red

@@ -1,9 +1,17 @@
 """Tensor-level entry points over the C ABI: search, apply, statistics, EMA, backward, and the
 autograd.Function the quantizer modules use.  PyTorch owns every buffer; the C side only
-enqueues kernels on the current stream.
+enqueues kernels on the current stream of the tensors' device.
+
+A training step is at most five launches of this library's kernels:
+  g2v_vq_search         tcgen05 sweep (or the fp32 sweep) + one exact re-rank launch
+  g2v_vq_apply          gather, straight-through value, SSE / histogram / EMA residual sums
+  g2v_vq_step_finalize  pack, loss, perplexity, EMA update, codebook aux re-preparation (one cooperative launch)
+  g2v_vq_backward       (in backward) gradient wrt the inputs
+(data-parallel EMA adds one pack launch in front of the all-reduce).
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from typing import Optional, Tuple
 
@@ -12,6 +20,7 @@ import torch
 from . import _lib
 
 _DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}
+UPDATE_NONE, UPDATE_EMA, UPDATE_KMEANS = 0, 1, 2
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -20,6 +29,18 @@ def _ptr(t: Optional[torch.Tensor]):
 
 def _stream(dev) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+_NULL = contextlib.nullcontext()
+
+
+def _on(dev: torch.device):
+    """Make `dev` the CUDA runtime's current device around a library call: kernels, memsets, the arch
+    check and the SM count all refer to the current device, while the stream we pass belongs to the
+    tensors' device (a module on cuda:1 with current device 0 must work, as the reference's do)."""
+    if dev.index is None or dev.index == torch.cuda.current_device():
+        return _NULL
+    return torch.cuda.device(dev)
 
 
 def _need_cuda(t: torch.Tensor, name: str) -> None:
@@ -48,6 +69,47 @@ class _Scratch:
 _scratch = _Scratch()
 
 
+class _Accum:
+    """Accumulators of the row pass (sse, counts, dwr replicas) for one (device, K, D, replicas).
+
+    They are zero whenever `clean` is True: g2v_vq_step_finalize hands them back zeroed after packing, so
+    a steady-state step issues no memset for them.  A step that dies between the row pass and the pack
+    leaves `clean` False and the next user zeroes them explicitly."""
+
+    def __init__(self, dev: torch.device, K: int, D: int, reps: int):
+        self.head = torch.zeros(8 + 4 * K, dtype=torch.uint8, device=dev)      # double sse | int32 counts[K]
+        self.sse = self.head[:8].view(torch.float64)
+        self.counts = self.head[8:].view(torch.int32)
+        self.dwr = torch.zeros(reps * K * D, dtype=torch.float32, device=dev) if reps else None
+        self.reps = reps
+        self.clean = True
+
+    def take(self) -> "_Accum":
+        if not self.clean:
+            self.head.zero_()
+            if self.dwr is not None:
+                self.dwr.zero_()
+        self.clean = False
+        return self
+
+
+_accums = {}
+
+
+def _accum(dev: torch.device, K: int, D: int, reps: int) -> _Accum:
+    key = (dev.index, K, D, reps)
+    a = _accums.get(key)
+    if a is None:
+        a = _accums[key] = _Accum(dev, K, D, reps)
+    return a.take()
+
+
+def dwr_replicas(N: int, K: int, D: int) -> int:
+    """Private copies of the [K, D] sums that keep hot codes from serialising the fp32 atomics: large
+    batches get up to 8 copies (bounded to 64 MB), small ones a single copy."""
+    return 1 if N < 32768 else max(1, min(8, (64 << 20) // (K * D * 4)))
+
+
 # ------------------------------------------------------------------------------------------------
 # codebook aux
 # ------------------------------------------------------------------------------------------------
@@ -64,8 +126,9 @@ def prepare_codebook(E: torch.Tensor, cb: Optional[torch.Tensor] = None) -> torc
     nbytes = codebook_bytes(K, D)
     if cb is None or cb.numel() < nbytes or cb.device != E.device:
         cb = torch.empty(nbytes, dtype=torch.uint8, device=E.device)
-    _lib.check(lib.g2v_codebook_prepare(_ptr(E), K, D, _ptr(cb), cb.numel(), _stream(E.device)),
-               "g2v_codebook_prepare")
+    with _on(E.device):
+        _lib.check(lib.g2v_codebook_prepare(_ptr(E), K, D, _ptr(cb), cb.numel(), _stream(E.device)),
+                   "g2v_codebook_prepare")
     return cb
 
 
@@ -84,6 +147,8 @@ def vq_search(z: torch.Tensor, E: torch.Tensor, cb: Optional[torch.Tensor] = Non
     if z.dtype not in _DT:
         raise RuntimeError(f"unsupported latent dtype {z.dtype}")
     assert z.dim() == 2 and z.is_contiguous() and E.is_contiguous() and E.dtype == torch.float32
+    if z.device != E.device:
+        raise RuntimeError(f"rows are on {z.device}, the codebook on {E.device}")
     N, D = z.shape
     K = E.shape[0]
     assert E.shape[1] == D, "latent dim != codebook dim"
@@ -94,9 +159,29 @@ def vq_search(z: torch.Tensor, E: torch.Tensor, cb: Optional[torch.Tensor] = Non
     if N == 0:
         return idx
     dt = _DT[z.dtype]
-    ws = _scratch.get(z.device, "search", lib.g2v_workspace_bytes(N, K, D, dt, flags))
-    _lib.check(lib.g2v_vq_search(_ptr(z), dt, _ptr(E), _ptr(cb), N, K, D, _ptr(idx), _ptr(stats),
-                                 _ptr(ws), ws.numel(), flags, _stream(z.device)), "g2v_vq_search")
+    with _on(z.device):
+        ws = _scratch.get(z.device, "search", lib.g2v_workspace_bytes(N, K, D, dt, flags))
+        _lib.check(lib.g2v_vq_search(_ptr(z), dt, _ptr(E), _ptr(cb), N, K, D, _ptr(idx), _ptr(stats),
+                                     _ptr(ws), ws.numel(), flags, _stream(z.device)), "g2v_vq_search")
+    return idx
+
+
+def vq_search_exact(z: torch.Tensor, E: torch.Tensor) -> torch.Tensor:
+    """Verification aid: exact-arithmetic (fp64) nearest code of every row, first index on ties (int32).
+    Slow by design (FP64-bound); shares nothing with the fast search paths."""
+    _need_cuda(z, "z")
+    _need_cuda(E, "codebook")
+    assert z.dim() == 2 and z.is_contiguous() and E.is_contiguous() and E.dtype == torch.float32 and z.dtype in _DT
+    N, D = z.shape
+    K = E.shape[0]
+    lib = _lib.load()
+    idx = torch.empty(N, dtype=torch.int32, device=z.device)
+    if N == 0:
+        return idx
+    with _on(z.device):
+        ws = torch.empty(int(lib.g2v_exact_workspace_bytes(K)), dtype=torch.uint8, device=z.device)
+        _lib.check(lib.g2v_vq_search_exact(_ptr(z), _DT[z.dtype], _ptr(E), N, K, D, _ptr(idx), _ptr(ws), ws.numel(),
+                                           _stream(z.device)), "g2v_vq_search_exact")
     return idx
 
 
@@ -104,68 +189,102 @@ def packed_numel(K: int, D: int) -> int:
     return K * D + K + 2
 
 
+def _apply_rows(x, zs, E, idx, out, acc: Optional[_Accum], want_dwr: bool) -> None:
+    """g2v_vq_apply: out = x + (E[idx]-x) and, if `acc`, SSE / counts (/ residual sums) into the accumulators."""
+    N, D = x.shape
+    K = E.shape[0]
+    dwr = acc.dwr if (acc is not None and want_dwr) else None
+    _lib.check(_lib.load().g2v_vq_apply(
+        _ptr(x), _ptr(zs), _ptr(E), _ptr(idx), N, K, D, _ptr(out),
+        _ptr(acc.sse) if acc is not None else None, _ptr(acc.counts) if acc is not None else None,
+        _ptr(dwr), acc.reps if dwr is not None else 0, _stream(x.device)), "g2v_vq_apply")
+
+
+def step_finalize(K: int, D: int, packed: torch.Tensor, *, acc: Optional[_Accum] = None, use_dwr: bool = True,
+                  rows_local: int = 0, coefs: Optional[Tuple[float, float]] = None, update: int = UPDATE_NONE,
+                  cs_in=None, cs_out=None, w_in=None, w_out=None, E_old=None, E_new=None, decay: float = 0.0,
+                  eps: float = 0.0, shift2=None, cb=None, res: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """g2v_vq_step_finalize.  `acc`: pack these accumulators first (they come back zeroed); otherwise `packed`
+    already holds the statistics.  `coefs` = (coef_codebook, coef_commit): also produce [loss, perplexity]
+    (returned as a 2-element device tensor)."""
+    lib = _lib.load()
+    dev = packed.device
+    if res is None and coefs is not None:
+        res = torch.empty(2, dtype=torch.float32, device=dev)
+    cc, cm = coefs if coefs is not None else (0.0, 0.0)
+    dwr = acc.dwr if (acc is not None and use_dwr) else None
+    rc = lib.g2v_vq_step_finalize(
+        _ptr(acc.counts) if acc is not None else None, _ptr(acc.sse) if acc is not None else None, _ptr(dwr),
+        acc.reps if dwr is not None else 0, rows_local, _ptr(packed), K, D, cc, cm,
+        C.c_void_p(res.data_ptr()) if res is not None else None,
+        C.c_void_p(res.data_ptr() + 4) if res is not None else None,
+        update, _ptr(cs_in), _ptr(cs_out), _ptr(w_in), _ptr(w_out), _ptr(E_old), _ptr(E_new), decay, eps,
+        _ptr(shift2), _ptr(cb), 0 if cb is None else cb.numel(), _stream(dev))
+    _lib.check(rc, "g2v_vq_step_finalize")
+    if acc is not None:
+        # the pack pass zeroes what it read: sse / counts always, the residual sums when they were packed
+        acc.clean = use_dwr or acc.dwr is None
+    return res
+
+
 def vq_apply(x: torch.Tensor, E: torch.Tensor, idx: torch.Tensor, *, zs: Optional[torch.Tensor] = None,
              want_out: bool = True, want_stats: bool = True, want_dwr: bool = False
              ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """One pass over the rows: out = x + (E[idx]-x) and, if asked, the packed statistics buffer
     [dwr (K*D) | counts (K) | sse | rows] (fp32, ready for an all-reduce)."""
-    lib = _lib.load()
     N, D = x.shape
     K = E.shape[0]
     dev = x.device
-    st = _stream(dev)
-    out = torch.empty_like(x) if want_out else None
-    packed = None
-    counts = sse = dwr = None
-    reps = 0
-    if want_stats:
-        packed = torch.empty(packed_numel(K, D), dtype=torch.float32, device=dev)
-        acc = torch.zeros(K * 4 + 8, dtype=torch.uint8, device=dev)   # int32 counts[K] + double sse
-        sse = acc[:8].view(torch.float64)
-        counts = acc[8:].view(torch.int32)
-        if want_dwr:
-            # private copies of the [K, D] sums keep hot codes from serialising the fp32 atomics;
-            # large batches get up to 8 copies (bounded to 64 MB), small ones a single copy
-            reps = 1 if N < 32768 else max(1, min(8, (64 << 20) // (K * D * 4)))
-            dwr = torch.zeros(reps * K * D, dtype=torch.float32, device=dev)
-    _lib.check(lib.g2v_vq_apply(_ptr(x), _ptr(zs), _ptr(E), _ptr(idx), N, K, D, _ptr(out), _ptr(sse),
-                                _ptr(counts), _ptr(dwr), reps, st), "g2v_vq_apply")
-    if want_stats:
-        _lib.check(lib.g2v_vq_stats_pack(_ptr(counts), _ptr(sse), _ptr(dwr), reps, N, K, D, _ptr(packed), st),
-                   "g2v_vq_stats_pack")
+    with _on(dev):
+        out = torch.empty_like(x) if want_out else None
+        acc = _accum(dev, K, D, dwr_replicas(N, K, D) if want_dwr else 0) if want_stats else None
+        _apply_rows(x, zs, E, idx, out, acc, want_dwr)
+        packed = None
+        if want_stats:
+            packed = torch.empty(packed_numel(K, D), dtype=torch.float32, device=dev)
+            step_finalize(K, D, packed, acc=acc, use_dwr=want_dwr, rows_local=N)
     return out, packed
 
 
 def stats_finalize(packed: torch.Tensor, K: int, D: int, coef_codebook: float, coef_commit: float
                    ) -> Tuple[torch.Tensor, torch.Tensor]:
-    lib = _lib.load()
-    res = torch.empty(2, dtype=torch.float32, device=packed.device)
-    _lib.check(lib.g2v_vq_stats_finalize(_ptr(packed), K, D, coef_codebook, coef_commit,
-                                         C.c_void_p(res.data_ptr()), C.c_void_p(res.data_ptr() + 4),
-                                         _stream(packed.device)), "g2v_vq_stats_finalize")
+    with _on(packed.device):
+        res = step_finalize(K, D, packed, coefs=(coef_codebook, coef_commit))
     return res[0], res[1]
 
 
-def ema_update(cluster_size: torch.Tensor, ema_w: torch.Tensor, E_old: torch.Tensor, E_new: torch.Tensor,
-               packed: torch.Tensor, decay: float, eps: float, cb: Optional[torch.Tensor]) -> None:
-    lib = _lib.load()
+def ema_update(cs_in: torch.Tensor, cs_out: torch.Tensor, w_in: torch.Tensor, w_out: torch.Tensor,
+               E_old: torch.Tensor, E_new: torch.Tensor, packed: torch.Tensor, decay: float, eps: float,
+               cb: Optional[torch.Tensor]) -> None:
+    """EMA update from a packed statistics buffer (cs_out must not alias cs_in); `cb` is re-prepared for E_new."""
     K, D = E_old.shape
-    _lib.check(lib.g2v_vq_ema_update(_ptr(cluster_size), _ptr(ema_w), _ptr(E_old), _ptr(E_new), _ptr(packed),
-                                     decay, eps, K, D, _ptr(cb), 0 if cb is None else cb.numel(),
-                                     _stream(E_old.device)), "g2v_vq_ema_update")
+    with _on(E_old.device):
+        step_finalize(K, D, packed, update=UPDATE_EMA, cs_in=cs_in, cs_out=cs_out, w_in=w_in, w_out=w_out,
+                      E_old=E_old, E_new=E_new, decay=decay, eps=eps, cb=cb)
 
 
 def one_hot(idx: torch.Tensor, K: int) -> torch.Tensor:
     lib = _lib.load()
     N = idx.numel()
-    enc = torch.empty(N, K, dtype=torch.float32, device=idx.device)
-    _lib.check(lib.g2v_onehot(_ptr(idx), N, K, _ptr(enc), _stream(idx.device)), "g2v_onehot")
+    with _on(idx.device):
+        enc = torch.empty(N, K, dtype=torch.float32, device=idx.device)
+        _lib.check(lib.g2v_onehot(_ptr(idx), N, K, _ptr(enc), _stream(idx.device)), "g2v_onehot")
     return enc
 
 
 # ------------------------------------------------------------------------------------------------
 # autograd
 # ------------------------------------------------------------------------------------------------
+class EmaState:
+    """EMA inputs of one step and, after `quantize`, its outputs (fresh tensors, like the reference's
+    re-created Parameters, Autoencoder_VQVAE_model.py:1276-1282)."""
+
+    def __init__(self, cluster_size: torch.Tensor, ema_w: torch.Tensor, decay: float, eps: float):
+        self.cs_in, self.w_in, self.decay, self.eps = cluster_size, ema_w, float(decay), float(eps)
+        self.cs_out = self.w_out = self.E_new = None
+        self.pending: Optional[torch.cuda.Event] = None      # side-stream work the caller must wait for
+
+
 class _QuantizeFn(torch.autograd.Function):
     """(x, E) -> (loss, quantized, perplexity, idx, packed).
 
@@ -175,14 +294,47 @@ class _QuantizeFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x2d, E, zs, cb, beta, coef_codebook, want_dwr, reduce_fn, grad_scale, flags):
-        search_rows = x2d if zs is None else zs
-        idx = vq_search(search_rows, E, cb, flags=flags)
-        out, packed = vq_apply(x2d, E, idx, zs=zs, want_out=True, want_stats=True, want_dwr=want_dwr)
-        if reduce_fn is not None:
-            reduce_fn(packed)                      # data-parallel all-reduce (sum) of the statistics
-        K, D = E.shape
-        loss, ppl = stats_finalize(packed, K, D, coef_codebook, beta)
+    def forward(ctx, x2d, E, zs, cb, beta, coef_codebook, want_dwr, reduce_fn, grad_scale, flags, ema):
+        dev = x2d.device
+        N, D = x2d.shape
+        K = E.shape[0]
+        with _on(dev):
+            idx = vq_search(x2d if zs is None else zs, E, cb, flags=flags)
+            out = torch.empty_like(x2d)
+            packed = torch.empty(packed_numel(K, D), dtype=torch.float32, device=dev)
+            if N == 0:
+                packed.zero_()
+                acc = None
+            else:
+                acc = _accum(dev, K, D, dwr_replicas(N, K, D) if want_dwr else 0)
+                _apply_rows(x2d, zs, E, idx, out, acc, want_dwr)
+            kw = dict(coefs=(coef_codebook, beta), res=torch.empty(2, dtype=torch.float32, device=dev))
+            if ema is not None:
+                ema.cs_out = torch.empty_like(ema.cs_in)
+                ema.w_out = torch.empty_like(ema.w_in)
+                ema.E_new = torch.empty_like(E)
+                kw.update(update=UPDATE_EMA, cs_in=ema.cs_in, cs_out=ema.cs_out, w_in=ema.w_in, w_out=ema.w_out,
+                          E_old=E, E_new=ema.E_new, decay=ema.decay, eps=ema.eps, cb=cb)
+            if reduce_fn is None:
+                res = step_finalize(K, D, packed, acc=acc, use_dwr=want_dwr, rows_local=N, **kw)
+            else:
+                # data-parallel: pack, ONE sum all-reduce of the packed statistics, then the identical finalise
+                # on every rank.  With a side stream (StatsAllReduce(overlap=True)) the exchange and the
+                # finalise overlap whatever the caller enqueues next on the main stream (the dense one-hot).
+                step_finalize(K, D, packed, acc=acc, use_dwr=want_dwr, rows_local=N)
+                side = getattr(reduce_fn, "stream", None)
+                if side is None or ema is None:
+                    reduce_fn(packed)
+                    res = step_finalize(K, D, packed, **kw)
+                else:
+                    main = torch.cuda.current_stream(dev)
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        reduce_fn(packed)
+                        res = step_finalize(K, D, packed, **kw)
+                        ema.pending = torch.cuda.Event()
+                        ema.pending.record(side)
+        loss, ppl = res[0], res[1]
         ctx.save_for_backward(x2d, E, idx, packed)
         ctx.beta, ctx.coef_codebook, ctx.grad_scale = beta, coef_codebook, grad_scale
         ctx.mark_non_differentiable(ppl, idx, packed)
@@ -195,31 +347,32 @@ class _QuantizeFn(torch.autograd.Function):
         N, D = x2d.shape
         K = E.shape[0]
         dev = x2d.device
-        st = _stream(dev)
         M = float(N) * float(D)
-        if g_loss is None:
-            g_loss = torch.zeros((), dtype=torch.float32, device=dev)
-        g_loss = g_loss.to(torch.float32).contiguous()
         gx = gE = None
-        if ctx.needs_input_grad[0]:
-            gx = torch.empty_like(x2d)
-            if g_out is not None:
-                g_out = g_out.contiguous()
-            _lib.check(lib.g2v_vq_backward(_ptr(x2d), _ptr(E), _ptr(idx), _ptr(g_out), _ptr(g_loss),
-                                           2.0 * ctx.beta * ctx.grad_scale / M, N, K, D, _ptr(gx), st),
-                       "g2v_vq_backward")
-        if ctx.needs_input_grad[1] and ctx.coef_codebook != 0.0:
-            gE = torch.empty_like(E)
-            _lib.check(lib.g2v_vq_grad_codebook(_ptr(packed), _ptr(g_loss),
-                                                2.0 * ctx.coef_codebook * ctx.grad_scale / M, K, D, _ptr(gE), st),
-                       "g2v_vq_grad_codebook")
-        return gx, gE, None, None, None, None, None, None, None, None
+        with _on(dev):
+            st = _stream(dev)
+            if g_loss is None:
+                g_loss = torch.zeros((), dtype=torch.float32, device=dev)
+            g_loss = g_loss.to(torch.float32).contiguous()
+            if ctx.needs_input_grad[0]:
+                gx = torch.empty_like(x2d)
+                if g_out is not None:
+                    g_out = g_out.contiguous()
+                _lib.check(lib.g2v_vq_backward(_ptr(x2d), _ptr(E), _ptr(idx), _ptr(g_out), _ptr(g_loss),
+                                               2.0 * ctx.beta * ctx.grad_scale / M if M else 0.0, N, K, D, _ptr(gx), st),
+                           "g2v_vq_backward")
+            if ctx.needs_input_grad[1] and ctx.coef_codebook != 0.0:
+                gE = torch.empty_like(E)
+                _lib.check(lib.g2v_vq_grad_codebook(_ptr(packed), _ptr(g_loss),
+                                                    2.0 * ctx.coef_codebook * ctx.grad_scale / M if M else 0.0,
+                                                    K, D, _ptr(gE), st), "g2v_vq_grad_codebook")
+        return gx, gE, None, None, None, None, None, None, None, None, None
 
 
 def quantize(x2d, E, *, zs=None, cb=None, beta=0.25, coef_codebook=1.0, want_dwr=False,
-             reduce_fn=None, grad_scale=1.0, flags=_lib.ALGO_AUTO):
+             reduce_fn=None, grad_scale=1.0, flags=_lib.ALGO_AUTO, ema: Optional[EmaState] = None):
     return _QuantizeFn.apply(x2d, E, zs, cb, float(beta), float(coef_codebook), bool(want_dwr),
-                             reduce_fn, float(grad_scale), int(flags))
+                             reduce_fn, float(grad_scale), int(flags), ema)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -248,10 +401,10 @@ def tokenize_host(z_host: torch.Tensor, E: torch.Tensor, cb: Optional[torch.Tens
     chunk_rows = max(1, min(int(chunk_rows), max(N, 1)))
     if out is None:
         out = torch.empty(N, dtype=torch.int32, pin_memory=True)
-    ws = _scratch.get(E.device, "tokhost", lib.g2v_tokenize_host_bytes(chunk_rows, K, D, dt, flags))
     stats = torch.zeros(8, dtype=torch.int64)
     torch.cuda.current_stream(E.device).synchronize()   # cb / E were produced on the caller's stream
     with torch.cuda.device(E.device):
+        ws = _scratch.get(E.device, "tokhost", lib.g2v_tokenize_host_bytes(chunk_rows, K, D, dt, flags))
         _lib.check(lib.g2v_tokenize_host(C.c_void_p(z_host.data_ptr()), dt, N, _ptr(E), _ptr(cb), K, D,
                                          C.c_void_p(out.data_ptr()), chunk_rows,
                                          C.c_void_p(stats.data_ptr()), _ptr(ws), ws.numel(), flags),

@@ -24,16 +24,17 @@ import numpy as np
 import torch
 
 from . import _lib
-from .functional import _need_cuda, _ptr, _stream, prepare_codebook, vq_apply, vq_search
+from .functional import _need_cuda, _on, _ptr, _stream, prepare_codebook, vq_apply, vq_search
 
 
 def kmeans_update(E_old: torch.Tensor, packed: torch.Tensor, E_new: torch.Tensor, shift2: Optional[torch.Tensor] = None,
                   cb: Optional[torch.Tensor] = None) -> None:
     """Lloyd M-step from a packed statistics buffer (include/g2v_vq.h g2v_kmeans_update)."""
     K, D = E_old.shape
-    _lib.check(_lib.load().g2v_kmeans_update(_ptr(E_old), _ptr(packed), K, D, _ptr(E_new), _ptr(shift2), _ptr(cb),
-                                             0 if cb is None else cb.numel(), _stream(E_old.device)),
-               "g2v_kmeans_update")
+    with _on(E_old.device):
+        _lib.check(_lib.load().g2v_kmeans_update(_ptr(E_old), _ptr(packed), K, D, _ptr(E_new), _ptr(shift2), _ptr(cb),
+                                                 0 if cb is None else cb.numel(), _stream(E_old.device)),
+                   "g2v_kmeans_update")
 
 
 def kmeans_plusplus(X: torch.Tensor, K: int, generator: torch.Generator) -> torch.Tensor:

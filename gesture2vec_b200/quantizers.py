@@ -33,6 +33,7 @@ from . import functional as F
 class _HardQuantizerBase(nn.Module):
     #: set by subclasses
     _ema: bool = False
+    _projects: bool = False      # the search runs on a projection of the rows (`_search_rows`)
 
     def _init_common(self, num_embeddings: int, embedding_dim: int, commitment_cost: float):
         self._embedding_dim = int(embedding_dim)
@@ -69,6 +70,10 @@ class _HardQuantizerBase(nn.Module):
         return W, self._cb
 
     def invalidate_codebook_cache(self) -> None:
+        """Call after writing the codebook in place through `.data` (`W.data.copy_()`, `dist.broadcast(W.data)`,
+        `.data.normal_()` ...): such writes do not bump `W._version`, which is what keys the cached fp16 /
+        ||e||^2 aux buffer.  Assigning a new tensor (`W.data = t`, as train_DAE.py:261 does), optimizer steps,
+        `load_state_dict` and `copy_` on the Parameter itself are all detected without this call."""
         self._cb_key = None
 
     def _search_rows(self, flat: torch.Tensor) -> Optional[torch.Tensor]:
@@ -90,47 +95,50 @@ class _HardQuantizerBase(nn.Module):
         if inputs.dtype != torch.float32:
             inputs = inputs.float()
         flat = inputs.contiguous().view(-1, self._embedding_dim)          # a1: inputs.view(-1, D)
-        W, cb = self._codebook(flat.device)
-        with torch.no_grad():
-            zs = self._search_rows(flat.detach())
-        training_ema = self._ema and self.training
-        want_dwr = training_ema or (not self._ema and W.requires_grad and torch.is_grad_enabled())
-        reduce_fn = self.stats_reduce if training_ema else None
-        E_arg = W if (not self._ema) else W.detach()
-        loss, out, ppl, idx, packed = F.quantize(
-            flat, E_arg, zs=zs, cb=cb, beta=self._commitment_cost,
-            coef_codebook=0.0 if self._ema else 1.0, want_dwr=want_dwr, reduce_fn=reduce_fn,
-            grad_scale=self.grad_scale, flags=self.search_flags)
-        if training_ema:
-            self._ema_step(W, packed)
-        self.last_indices = idx
-        quantized = out.view(inputs.shape)
-        enc = F.one_hot(idx, self._num_embeddings) if self.return_encodings else idx.long().unsqueeze(1)
+        with F._on(flat.device):
+            W, cb = self._codebook(flat.device)
+            with torch.no_grad():
+                zs = self._search_rows(flat.detach())
+            training_ema = self._ema and self.training
+            want_dwr = training_ema or (not self._ema and W.requires_grad and torch.is_grad_enabled())
+            reduce_fn = self.stats_reduce if training_ema else None
+            E_arg = W if (not self._ema) else W.detach()
+            ema = None
+            if training_ema:
+                if not (self._ema_w.data.is_contiguous() and self._ema_cluster_size.is_contiguous()):
+                    raise RuntimeError("EMA state must be contiguous")
+                ema = F.EmaState(self._ema_cluster_size, self._ema_w.data, self._decay, self._epsilon)
+            loss, out, ppl, idx, packed = F.quantize(
+                flat, E_arg, zs=zs, cb=cb, beta=self._commitment_cost,
+                coef_codebook=0.0 if self._ema else 1.0, want_dwr=want_dwr, reduce_fn=reduce_fn,
+                grad_scale=self.grad_scale, flags=self.search_flags, ema=ema)
+            self.last_indices = idx
+            quantized = out.view(inputs.shape)
+            enc = F.one_hot(idx, self._num_embeddings) if self.return_encodings else idx.long().unsqueeze(1)
+            if ema is not None:
+                if ema.pending is not None:          # statistics exchange + finalise ran on the side stream
+                    torch.cuda.current_stream(flat.device).wait_event(ema.pending)
+                # the step's single finalise launch wrote the new state into fresh tensors (the reference
+                # re-creates its Parameters each step, :1276-1282) and re-prepared `cb` for the new codebook
+                with torch.no_grad():
+                    self._ema_cluster_size = ema.cs_out   # registered buffer: assignment keeps it registered
+                    self._ema_w.data = ema.w_out
+                    W.data = ema.E_new
+                    self._cb_key = (ema.E_new.data_ptr(), W._version, str(ema.E_new.device))
         if src_dev != quantized.device:
             loss, quantized, ppl, enc = (t.to(src_dev) for t in (loss, quantized, ppl, enc))
         return loss, quantized, ppl, enc
 
-    def _ema_step(self, W: nn.Parameter, packed: torch.Tensor) -> None:
-        with torch.no_grad():
-            E_old = W.data
-            E_new = torch.empty_like(E_old)
-            w_old = self._ema_w.data
-            if not (w_old.is_contiguous() and self._ema_cluster_size.is_contiguous()):
-                raise RuntimeError("EMA state must be contiguous")
-            w_new = w_old.clone()         # the reference also produces a fresh _ema_w tensor
-            cs = self._ema_cluster_size.clone()
-            F.ema_update(cs, w_new, E_old, E_new, packed, self._decay, self._epsilon, self._cb)
-            self._ema_cluster_size = cs   # registered buffer: assignment keeps it registered
-            self._ema_w.data = w_new
-            W.data = E_new
-            self._cb_key = (E_new.data_ptr(), W._version, str(E_new.device))
-
     def tokenize(self, inputs: torch.Tensor) -> torch.Tensor:
-        """Bulk path: int32 code ids for the rows of `inputs`, no one-hot / gather / loss."""
+        """Bulk path: int32 code ids for the rows of `inputs` -- the same ids as `argmax(forward(x)[3], 1)` --
+        with no one-hot / gather / loss.  16-bit rows are searched as stored unless the flavour projects them
+        first (`_search_rows`), in which case they go through the projection in fp32 like the forward pass."""
         flat = inputs.contiguous().view(-1, self._embedding_dim)
-        W, cb = self._codebook(flat.device)
-        zs = self._search_rows(flat) if flat.dtype == torch.float32 else None
-        return F.vq_search(flat if zs is None else zs, W.detach(), cb, flags=self.search_flags)
+        with F._on(flat.device):
+            W, cb = self._codebook(flat.device)
+            with torch.no_grad():
+                zs = self._search_rows(flat.float() if self._projects else flat)
+            return F.vq_search(flat if zs is None else zs, W.detach(), cb, flags=self.search_flags)
 
     def forward(self, inputs: torch.Tensor):
         return self._run(inputs)
@@ -200,6 +208,8 @@ class VQVAE_VQ_Payam_EMA(_HardQuantizerBase):
         self._ema_w.data.normal_()
         self._decay = decay
         self._epsilon = epsilon
+
+    _projects = True
 
     def _search_rows(self, flat: torch.Tensor) -> Optional[torch.Tensor]:
         # plain library GEMM (cuBLAS through torch); no gradient reaches pre_linear

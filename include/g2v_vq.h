@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define G2V_VERSION 100
+#define G2V_VERSION 200
 
 /* error codes */
 #define G2V_OK 0
@@ -127,16 +127,38 @@ int g2v_vq_stats_pack(const int32_t* counts, const double* sse, const float* dwr
 int g2v_vq_stats_finalize(const float* packed, int K, int D, float coef_codebook, float coef_commit,
                           float* loss, float* perplexity, void* stream);
 
-/* EMA codebook update from a packed statistics buffer; cluster_size and ema_w are updated in
- * place, the new codebook goes to E_new (E_new == E_old is allowed; a separate buffer keeps the
- * old codes alive for the backward pass, as the reference's re-created Parameter does).  Replaces
- * DAE_model.py:451-471 / Autoencoder_VQVAE_model.py:1262-1282, 1777-1797:
+/* EMA codebook update from a packed statistics buffer.  Replaces DAE_model.py:451-471 /
+ * Autoencoder_VQVAE_model.py:1262-1282, 1777-1797:
  *   cs <- cs*decay + (1-decay)*counts ; n = sum cs ; cs <- (cs+eps)/(n+K*eps)*n
  *   ema_w <- ema_w*decay + (1-decay)*dw ; E <- ema_w / cs[:,None]      (dw = dwr + counts*E)
- * If cb != NULL the aux buffer is re-prepared for E_new on the same stream. */
-int g2v_vq_ema_update(float* cluster_size, float* ema_w, const float* E_old, float* E_new,
-                      const float* packed, float decay, float eps, int K, int D, void* cb,
-                      size_t cb_bytes, void* stream);
+ * The new state goes to cs_out / ema_w_out / E_new, like the fresh tensors the reference produces each step
+ * (:1276-1282).  ema_w_out == ema_w_in and E_new == E_old are allowed; cs_out MUST NOT alias cs_in (every
+ * thread block reads all of cs_in for the Laplace-smoothing sum while one of them writes cs_out).
+ * If cb != NULL the aux buffer is re-prepared for E_new in the same launch. */
+int g2v_vq_ema_update(const float* cs_in, float* cs_out, const float* ema_w_in, float* ema_w_out,
+                      const float* E_old, float* E_new, const float* packed, float decay, float eps, int K, int D,
+                      void* cb, size_t cb_bytes, void* stream);
+
+/* Everything a step does after the row pass, in ONE (cooperative) launch: pack the accumulators of
+ * g2v_vq_apply (= g2v_vq_stats_pack, and the accumulators are handed back ZEROED, ready for the next step),
+ * loss / perplexity (= g2v_vq_stats_finalize), the codebook update selected by `update` (= g2v_vq_ema_update
+ * or g2v_kmeans_update) and the aux buffer of the new codebook (= g2v_codebook_prepare).
+ *   counts / sse / dwr   accumulators; all three NULL = `packed` already holds the statistics (e.g. it was packed
+ *                        by g2v_vq_stats_pack and all-reduced across ranks)
+ *   rows_local           rows of this call (written to packed[K*D+K+1] when packing)
+ *   loss, perplexity     optional device scalars
+ *   update               G2V_UPDATE_NONE: no codebook change (cs / ema_w / E_new unused); cb, if given, is prepared
+ *                        for E_old.  G2V_UPDATE_EMA: as g2v_vq_ema_update (cs_out must not alias cs_in).
+ *                        G2V_UPDATE_KMEANS: as g2v_kmeans_update (shift2 optional).  cb, if given, is prepared
+ *                        for E_new in both. */
+#define G2V_UPDATE_NONE 0
+#define G2V_UPDATE_EMA 1
+#define G2V_UPDATE_KMEANS 2
+int g2v_vq_step_finalize(int32_t* counts, double* sse, float* dwr, int dwr_replicas, int64_t rows_local,
+                         float* packed, int K, int D, float coef_codebook, float coef_commit, float* loss,
+                         float* perplexity, int update, const float* cs_in, float* cs_out, const float* ema_w_in,
+                         float* ema_w_out, const float* E_old, float* E_new, float decay, float eps,
+                         double* shift2, void* cb, size_t cb_bytes, void* stream);
 
 /* Backward of the layer wrt the inputs (closed form of the autograd graph the reference
  * builds):  g_x = g_out + g_loss[0]*coef_x*(x - E[idx]),
@@ -162,6 +184,14 @@ int g2v_kmeans_update(const float* E_old, const float* packed, int K, int D, flo
 /* encodings = one_hot(idx) as a dense fp32 [N,K] (DAE_model.py:328-331); the reference
  * returns it and callers argmax it (Clustering.py:156, lmdb_data_loader.py:1281). */
 int g2v_onehot(const int32_t* idx, int64_t N, int K, float* enc, void* stream);
+
+/* Verification aid, not a product path: the exact-arithmetic nearest code of EVERY row, all products and
+ * sums in fp64 (no error bounds, candidate lists or operand rounding shared with g2v_vq_search), first index
+ * on exact ties -- what torch.argmin over fp64 distances of DAE_model.py:320-327 would return.  FP64-bound
+ * (~10 s per million rows at K = D = 400).  ws: g2v_exact_workspace_bytes(K) bytes of scratch. */
+size_t g2v_exact_workspace_bytes(int K);
+int g2v_vq_search_exact(const void* z, int z_dtype, const float* E, int64_t N, int K, int D, int32_t* idx,
+                        void* ws, size_t ws_bytes, void* stream);
 
 /* End-to-end tokenisation with HOST buffers (the batched form of Clustering.py:102-166):
  * copies z_host -> device in chunks, searches, copies idx back; copies and kernels overlap
