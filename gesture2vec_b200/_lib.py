@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("G2V_LIB_PATH") or os.path.join(HERE, "csrc", "libg2v_
 # dtype / flag codes (mirror include/g2v_vq.h)
 F32, BF16, F16 = 0, 1, 2
 ALGO_AUTO, ALGO_SIMT, ALGO_TC, NO_RECHECK = 0, 1, 2, 4
+TC_VARIANT_TMEM, TC_VARIANT_FUSED, TC_VARIANT_PREP = 1 << 8, 2 << 8, 3 << 8
 STAT_ROWS, STAT_PAIR_RECHECK, STAT_FULL_RECHECK, STAT_FALLBACK_ROWS = 0, 1, 2, 3
 
 _p, _i, _i64, _f, _sz, _u = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t, C.c_uint
@@ -25,6 +26,7 @@ SIGNATURES = {
     "g2v_version": (_i, []),
     "g2v_strerror": (C.c_char_p, [_i]),
     "g2v_last_error_detail": (C.c_char_p, []),
+    "g2v_launch_count": (C.c_ulonglong, []),
     "g2v_codebook_bytes": (_sz, [_i, _i]),
     "g2v_codebook_prepare": (_i, [_p, _i, _i, _p, _sz, _p]),
     "g2v_profile_next_search": (_i, [_p, _p]),
@@ -35,7 +37,7 @@ SIGNATURES = {
     "g2v_vq_stats_pack": (_i, [_p, _p, _p, _i, _i64, _i, _i, _p, _p]),
     "g2v_vq_stats_finalize": (_i, [_p, _i, _i, _f, _f, _p, _p, _p]),
     "g2v_vq_ema_update": (_i, [_p, _p, _p, _p, _p, _p, _p, _f, _f, _i, _i, _p, _sz, _p]),
-    "g2v_vq_step_finalize": (_i, [_p, _p, _p, _i, _i64, _p, _i, _i, _f, _f, _p, _p, _i, _p, _p, _p, _p, _p, _p, _f, _f,
+    "g2v_vq_step_finalize": (_i, [_p, _p, _p, _i, _i64, _p, _i, _i, _f, _f, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _f, _f,
                                   _p, _p, _sz, _p]),
     "g2v_exact_workspace_bytes": (_sz, [_i]),
     "g2v_vq_search_exact": (_i, [_p, _i, _p, _i64, _i, _i, _p, _p, _sz, _p]),

@@ -9,6 +9,7 @@
 namespace g2v {
 
 static thread_local char g_detail[512] = "";
+unsigned long long g_launches = 0;
 
 void set_error_detail(const char* fmt, ...) {
   va_list ap;
@@ -86,6 +87,8 @@ const char* g2v_strerror(int code) {
 }
 
 const char* g2v_last_error_detail(void) { return g_detail; }
+
+unsigned long long g2v_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 size_t g2v_codebook_bytes(int K, int D) {
   if (K <= 0 || D <= 0) return 0;
@@ -175,13 +178,14 @@ int g2v_vq_stats_finalize(const float* packed, int K, int D, float coef_codebook
 int g2v_vq_step_finalize(int32_t* counts, double* sse, float* dwr, int dwr_replicas, int64_t rows_local,
                          float* packed, int K, int D, float coef_codebook, float coef_commit, float* loss,
                          float* perplexity, int update, const float* cs_in, float* cs_out, const float* ema_w_in,
-                         float* ema_w_out, const float* E_old, float* E_new, float decay, float eps,
+                         float* ema_w_out, const float* E_old, float* E_new, float* E_prev, float decay, float eps,
                          double* shift2, void* cb, size_t cb_bytes, void* stream) {
   if (K <= 0 || D <= 0 || rows_local < 0 || (dwr && dwr_replicas < 1)) return G2V_ERR_INVALID;
   const int do_pack = (counts || sse || dwr) ? 1 : 0;
   if ((do_pack || loss || perplexity || update != G2V_UPDATE_NONE) && !packed) return G2V_ERR_INVALID;
   if (update == G2V_UPDATE_EMA) {
-    if (!cs_in || !cs_out || !ema_w_in || !ema_w_out || !E_old || !E_new || cs_in == cs_out) return G2V_ERR_INVALID;
+    if (!cs_in || !cs_out || !ema_w_in || !ema_w_out || !E_old || !E_new) return G2V_ERR_INVALID;
+    if (E_prev && (E_prev == E_old || E_prev == E_new)) return G2V_ERR_INVALID;
   } else if (update == G2V_UPDATE_KMEANS) {
     if (!E_old || !E_new) return G2V_ERR_INVALID;
   } else if (update != G2V_UPDATE_NONE) {
@@ -196,15 +200,16 @@ int g2v_vq_step_finalize(int32_t* counts, double* sse, float* dwr, int dwr_repli
   if (rc) return rc;
   return launch_step_finalize(counts, sse, dwr, dwr_replicas, do_pack, rows_local, packed, K, D, coef_codebook,
                               coef_commit, loss, perplexity, update, cs_in, cs_out, ema_w_in, ema_w_out, E_old, E_new,
-                              decay, eps, shift2, cb, E_old, (cudaStream_t)stream);
+                              update == G2V_UPDATE_EMA ? E_prev : nullptr, decay, eps, shift2, cb, E_old,
+                              (cudaStream_t)stream);
 }
 
 int g2v_vq_ema_update(const float* cs_in, float* cs_out, const float* ema_w_in, float* ema_w_out,
                       const float* E_old, float* E_new, const float* packed, float decay, float eps, int K, int D,
                       void* cb, size_t cb_bytes, void* stream) {
   return g2v_vq_step_finalize(nullptr, nullptr, nullptr, 0, 0, const_cast<float*>(packed), K, D, 0.f, 0.f, nullptr,
-                              nullptr, G2V_UPDATE_EMA, cs_in, cs_out, ema_w_in, ema_w_out, E_old, E_new, decay, eps,
-                              nullptr, cb, cb_bytes, stream);
+                              nullptr, G2V_UPDATE_EMA, cs_in, cs_out, ema_w_in, ema_w_out, E_old, E_new, nullptr, decay,
+                              eps, nullptr, cb, cb_bytes, stream);
 }
 
 int g2v_vq_backward(const float* x, const float* E, const int32_t* idx, const float* g_out,
@@ -223,8 +228,8 @@ int g2v_vq_grad_codebook(const float* packed_dwr, const float* g_loss, float coe
 int g2v_kmeans_update(const float* E_old, const float* packed, int K, int D, float* E_new, double* shift2,
                       void* cb, size_t cb_bytes, void* stream) {
   return g2v_vq_step_finalize(nullptr, nullptr, nullptr, 0, 0, const_cast<float*>(packed), K, D, 0.f, 0.f, nullptr,
-                              nullptr, G2V_UPDATE_KMEANS, nullptr, nullptr, nullptr, nullptr, E_old, E_new, 0.f, 0.f,
-                              shift2, cb, cb_bytes, stream);
+                              nullptr, G2V_UPDATE_KMEANS, nullptr, nullptr, nullptr, nullptr, E_old, E_new, nullptr, 0.f,
+                              0.f, shift2, cb, cb_bytes, stream);
 }
 
 size_t g2v_exact_workspace_bytes(int K) { return K > 0 ? align_up((size_t)K * sizeof(double), 256) : 0; }

@@ -71,10 +71,13 @@ int cuda_fail(cudaError_t e, const char* what);
     if (_e != cudaSuccess) return ::g2v::cuda_fail(_e, #expr); \
   } while (0)
 
+// every kernel launch of the library passes through here: g_launches is the count g2v_launch_count() reports
+extern unsigned long long g_launches;
 #define G2V_LAUNCH_CHECK(name)                                  \
   do {                                                          \
     cudaError_t _e = cudaGetLastError();                        \
     if (_e != cudaSuccess) return ::g2v::cuda_fail(_e, name);   \
+    __atomic_add_fetch(&::g2v::g_launches, 1ULL, __ATOMIC_RELAXED); \
   } while (0)
 
 int num_sms();
@@ -105,8 +108,8 @@ int launch_stats_finalize(const float* packed, int K, int D, float coef_codebook
 int launch_step_finalize(int32_t* counts, double* sse, float* dwr, int dwr_replicas, int do_pack, int64_t rows_local,
                          float* packed, int K, int D, float coef_codebook, float coef_commit, float* loss, float* ppl,
                          int mode, const float* cs_in, float* cs_out, const float* w_in, float* w_out,
-                         const float* E_old, float* E_new, float decay, float eps, double* shift2, void* cb,
-                         const float* E_cb, cudaStream_t st);
+                         const float* E_old, float* E_new, float* E_prev, float decay, float eps, double* shift2,
+                         void* cb, const float* E_cb, cudaStream_t st);
 // g2v_audit.cu: exact fp64 argmin of every row (verification aid); ws holds K doubles
 int launch_search_exact64(const void* z, int z_dtype, const float* E, int64_t N, int K, int D, int32_t* idx, void* ws,
                           cudaStream_t st);

@@ -50,6 +50,7 @@ struct FinParams {
   float* w_out;
   const float* E_old;
   float* E_new;
+  float* E_prev;          // optional copy of E_old (EMA mode), for in-place updates
   float decay, one_m, eps, keps;
   double* shift2;
   // aux buffer to prepare (null = skip) for the codebook E_cb (== E_new when mode != 0)
@@ -166,12 +167,16 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const FinParams P
       part += (double)__fadd_rn(__fmul_rn(P.cs_in[k], P.decay), __fmul_rn(P.one_m, __ldcg(tail + k)));
     n_cs = (float)block_sum_fixed(part, sh);
     den_cs = __fadd_rn(n_cs, P.keps);
+  }
+  // cs_out may alias cs_in (in-place state for CUDA-graph replay): it is written by block 0 only after a
+  // grid-wide barrier, once every block has read cs_in for the sum above and for its own code rows
+  auto write_cs = [&]() {
     if (blockIdx.x == 0)
       for (int k = tid; k < K; k += FIN_THREADS) {
         const float v = __fadd_rn(__fmul_rn(P.cs_in[k], P.decay), __fmul_rn(P.one_m, __ldcg(tail + k)));
         P.cs_out[k] = __fmul_rn(__fdiv_rn(__fadd_rn(v, P.eps), den_cs), n_cs);
       }
-  }
+  };
   double shift_part = 0.0;
   if (P.mode != 0 || P.cb) {
     for (int k = blockIdx.x * FIN_WARPS + warp; k < P.Kp; k += gridDim.x * FIN_WARPS) {
@@ -191,7 +196,9 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const FinParams P
       for (int j = lane; j < D; j += 32) {
         float e;
         if (P.mode == 1) {
-          const float dw = fmaf(cnt, P.E_old[r0 + j], __ldcg(P.packed + r0 + j));   // sum of rows = residual sum + count * code
+          const float eo = P.E_old[r0 + j];
+          if (P.E_prev) P.E_prev[r0 + j] = eo;          // the backward pass still needs the old codes
+          const float dw = fmaf(cnt, eo, __ldcg(P.packed + r0 + j));   // sum of rows = residual sum + count * code
           const float w = __fadd_rn(__fmul_rn(P.w_in[r0 + j], P.decay), __fmul_rn(P.one_m, dw));
           P.w_out[r0 + j] = w;
           e = __fdiv_rn(w, csn);
@@ -228,8 +235,15 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const FinParams P
     const double t = block_sum_fixed(shift_part, sh);
     if (tid == 0 && t != 0.0) atomicAdd(P.shift2, t);
   }
-  if (!P.cb) return;                                       // uniform over the grid
+  if (!P.cb) {                                             // uniform over the grid
+    if (P.mode == 1) {
+      grid.sync();
+      write_cs();
+    }
+    return;
+  }
   grid.sync();
+  if (P.mode == 1) write_cs();
 
   // ------------------------------------------------------------------ phase C
   const float amax = __ldcg(&hdr->amax);
@@ -313,6 +327,7 @@ int launch_fin(FinParams& P, cudaStream_t st) {
   void* args[] = {&P};
   G2V_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&finalize_kernel), dim3(grid), dim3(FIN_THREADS),
                                              args, 0, st));
+  G2V_LAUNCH_CHECK("finalize_kernel");
   return G2V_OK;
 }
 
@@ -349,9 +364,10 @@ int launch_stats_finalize(const float* packed, int K, int D, float coef_codebook
 int launch_step_finalize(int32_t* counts, double* sse, float* dwr, int dwr_replicas, int do_pack, int64_t rows_local,
                          float* packed, int K, int D, float coef_codebook, float coef_commit, float* loss, float* ppl,
                          int mode, const float* cs_in, float* cs_out, const float* w_in, float* w_out,
-                         const float* E_old, float* E_new, float decay, float eps, double* shift2, void* cb,
-                         const float* E_cb, cudaStream_t st) {
+                         const float* E_old, float* E_new, float* E_prev, float decay, float eps, double* shift2,
+                         void* cb, const float* E_cb, cudaStream_t st) {
   FinParams P = fin_blank(K, D);
+  P.E_prev = E_prev;
   P.rows_local = rows_local;
   P.counts = counts;
   P.sse = sse;

@@ -60,8 +60,8 @@ constexpr bool kTraceBuild = G2V_TRACE != 0;
 // bring-up switches (ablation timing, results are wrong with them): only in a -DG2V_TRACE=1 build, where the
 // G2V_TC_DEBUG environment variable sets them; in the product build the masks are 0 and every test on them folds away
 constexpr unsigned kDbgOn = kTraceBuild ? 1u : 0u;
-constexpr unsigned kDbgSkipMma = 0x100u * kDbgOn, kDbgSkipEpi = 0x200u * kDbgOn, kDbgSkipConv = 0x400u * kDbgOn,
-                   kDbgPrefetch = 0x800u * kDbgOn, kDbgNoB = 0x1000u * kDbgOn, kDbgNoZ = 0x2000u * kDbgOn;
+constexpr unsigned kDbgSkipMma = 0x10000u * kDbgOn, kDbgSkipEpi = 0x20000u * kDbgOn, kDbgSkipConv = 0x40000u * kDbgOn,
+                   kDbgPrefetch = 0x80000u * kDbgOn, kDbgNoB = 0x100000u * kDbgOn, kDbgNoZ = 0x200000u * kDbgOn;
 
 struct RowInfo {       // 32 bytes per row, written by row_prep_kernel
   float cS;            // -2 / (scale_z * scale_e) * S
@@ -1526,7 +1526,7 @@ __device__ __forceinline__ void pair_entries(const ZT* __restrict__ z, const flo
   const int lane = threadIdx.x & 31;
   const int wstride = (gridDim.x * blockDim.x) >> 5;
   constexpr int U = 2;                                   // 2 x 128 columns per pass (registers -> occupancy)
-  const bool vec = (D % 4 == 0) && sizeof(ZT) == 4;
+  const bool vec = (D % 4 == 0) && sizeof(ZT) == 4 && ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(E)) & 15) == 0;
   for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n; e += wstride) {
     const int4 ent = reinterpret_cast<const int4*>(pair_list)[e];
     const int row = ent.x, a = ent.y, b = ent.z, c = ent.w;
@@ -1872,7 +1872,7 @@ const Tuning& tuning() {
     u.dbg_flags = 0;
     u.trace = nullptr;
 #if G2V_TRACE
-    if (const char* e = getenv("G2V_TC_DEBUG")) u.dbg_flags = ((unsigned)atoi(e) & 63u) << 8;
+    if (const char* e = getenv("G2V_TC_DEBUG")) u.dbg_flags = ((unsigned)atoi(e) & 63u) << 16;
     if (const char* e = getenv("G2V_TC_TRACE")) u.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
 #endif
     return u;
@@ -2000,6 +2000,7 @@ template <typename ZT>
 int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, int K, int D, int32_t* idx,
            unsigned long long* stats, void* ws, unsigned flags, cudaStream_t st) {
   const int Dp = round_up(D, 16), Kp = round_up(K, 256);
+  const unsigned variant = flags & G2V_TC_VARIANT_MASK;      // test / benchmark aid: pin the sweep kernel
   const TcWs w = tc_ws(N, D);
   char* base = reinterpret_cast<char*>(ws);
   __half* z16 = reinterpret_cast<__half*>(base + w.z16);
@@ -2015,7 +2016,9 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
   {   // fp32 rows, few code tiles: A operand in tensor memory, CTA pairs (G2V_TC_TMEM=0 switches the variant off,
       // =2 forces it for any K)
     TmeParams R;
-    const int mode = tuning().tmem_mode >= 0 ? tuning().tmem_mode : 1;
+    int mode = tuning().tmem_mode >= 0 ? tuning().tmem_mode : 1;
+    if (variant == G2V_TC_VARIANT_TMEM) mode = 2;
+    else if (variant != G2V_TC_VARIANT_AUTO) mode = 0;
     bool use = mode != 0 && plan_tmem(z, z_dtype, N, K, D, 1, &R) && (mode == 2 || R.n_ntiles <= 4);
     if (use) {      // G2V_TC_ABUFS=1|2: single / double A operand buffer
       int a_bufs = kTmeDefaultABufs;
@@ -2054,7 +2057,10 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
   P.n_ntiles = (K + TN - 1) / TN;
   bool fused = (z_dtype == G2V_F32) && (D % 4 == 0) && (D >= KC) && P.n_ntiles <= 2 &&
                ((reinterpret_cast<uintptr_t>(z) & 15) == 0);
-  if (tuning().fused >= 0) {
+  const bool fusable = (z_dtype == G2V_F32) && (D % 4 == 0) && (D >= KC) && ((reinterpret_cast<uintptr_t>(z) & 15) == 0);
+  if (variant == G2V_TC_VARIANT_FUSED) fused = fusable;
+  else if (variant == G2V_TC_VARIANT_PREP) fused = false;
+  else if (tuning().fused >= 0) {
     if (tuning().fused == 0) fused = false;
     else fused = (z_dtype == G2V_F32) && (D % 4 == 0) && (D >= KC) && ((reinterpret_cast<uintptr_t>(z) & 15) == 0);
   }

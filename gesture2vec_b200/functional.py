@@ -202,7 +202,7 @@ def _apply_rows(x, zs, E, idx, out, acc: Optional[_Accum], want_dwr: bool) -> No
 
 def step_finalize(K: int, D: int, packed: torch.Tensor, *, acc: Optional[_Accum] = None, use_dwr: bool = True,
                   rows_local: int = 0, coefs: Optional[Tuple[float, float]] = None, update: int = UPDATE_NONE,
-                  cs_in=None, cs_out=None, w_in=None, w_out=None, E_old=None, E_new=None, decay: float = 0.0,
+                  cs_in=None, cs_out=None, w_in=None, w_out=None, E_old=None, E_new=None, E_prev=None, decay: float = 0.0,
                   eps: float = 0.0, shift2=None, cb=None, res: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
     """g2v_vq_step_finalize.  `acc`: pack these accumulators first (they come back zeroed); otherwise `packed`
     already holds the statistics.  `coefs` = (coef_codebook, coef_commit): also produce [loss, perplexity]
@@ -218,7 +218,7 @@ def step_finalize(K: int, D: int, packed: torch.Tensor, *, acc: Optional[_Accum]
         acc.reps if dwr is not None else 0, rows_local, _ptr(packed), K, D, cc, cm,
         C.c_void_p(res.data_ptr()) if res is not None else None,
         C.c_void_p(res.data_ptr() + 4) if res is not None else None,
-        update, _ptr(cs_in), _ptr(cs_out), _ptr(w_in), _ptr(w_out), _ptr(E_old), _ptr(E_new), decay, eps,
+        update, _ptr(cs_in), _ptr(cs_out), _ptr(w_in), _ptr(w_out), _ptr(E_old), _ptr(E_new), _ptr(E_prev), decay, eps,
         _ptr(shift2), _ptr(cb), 0 if cb is None else cb.numel(), _stream(dev))
     _lib.check(rc, "g2v_vq_step_finalize")
     if acc is not None:
@@ -276,11 +276,15 @@ def one_hot(idx: torch.Tensor, K: int) -> torch.Tensor:
 # autograd
 # ------------------------------------------------------------------------------------------------
 class EmaState:
-    """EMA inputs of one step and, after `quantize`, its outputs (fresh tensors, like the reference's
-    re-created Parameters, Autoencoder_VQVAE_model.py:1276-1282)."""
+    """EMA inputs of one step and, after `quantize`, its outputs: fresh tensors by default, like the reference's
+    re-created Parameters (Autoencoder_VQVAE_model.py:1276-1282).  With `E_prev` (a persistent [K, D] buffer) the
+    state is updated IN PLACE instead -- every address stays fixed, so a captured CUDA graph of the step advances
+    the state on every replay -- and the old codebook the backward pass needs is kept in `E_prev`."""
 
-    def __init__(self, cluster_size: torch.Tensor, ema_w: torch.Tensor, decay: float, eps: float):
+    def __init__(self, cluster_size: torch.Tensor, ema_w: torch.Tensor, decay: float, eps: float,
+                 E_prev: Optional[torch.Tensor] = None):
         self.cs_in, self.w_in, self.decay, self.eps = cluster_size, ema_w, float(decay), float(eps)
+        self.E_prev = E_prev
         self.cs_out = self.w_out = self.E_new = None
         self.pending: Optional[torch.cuda.Event] = None      # side-stream work the caller must wait for
 
@@ -294,12 +298,12 @@ class _QuantizeFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x2d, E, zs, cb, beta, coef_codebook, want_dwr, reduce_fn, grad_scale, flags, ema):
+    def forward(ctx, x2d, E, zs, cb, beta, coef_codebook, want_dwr, reduce_fn, grad_scale, flags, ema, idx_given):
         dev = x2d.device
         N, D = x2d.shape
         K = E.shape[0]
         with _on(dev):
-            idx = vq_search(x2d if zs is None else zs, E, cb, flags=flags)
+            idx = idx_given if idx_given is not None else vq_search(x2d if zs is None else zs, E, cb, flags=flags)
             out = torch.empty_like(x2d)
             packed = torch.empty(packed_numel(K, D), dtype=torch.float32, device=dev)
             if N == 0:
@@ -309,12 +313,16 @@ class _QuantizeFn(torch.autograd.Function):
                 acc = _accum(dev, K, D, dwr_replicas(N, K, D) if want_dwr else 0)
                 _apply_rows(x2d, zs, E, idx, out, acc, want_dwr)
             kw = dict(coefs=(coef_codebook, beta), res=torch.empty(2, dtype=torch.float32, device=dev))
+            E_bwd = E
             if ema is not None:
-                ema.cs_out = torch.empty_like(ema.cs_in)
-                ema.w_out = torch.empty_like(ema.w_in)
-                ema.E_new = torch.empty_like(E)
+                if ema.E_prev is not None:
+                    ema.cs_out, ema.w_out, ema.E_new, E_bwd = ema.cs_in, ema.w_in, E, ema.E_prev
+                else:
+                    ema.cs_out = torch.empty_like(ema.cs_in)
+                    ema.w_out = torch.empty_like(ema.w_in)
+                    ema.E_new = torch.empty_like(E)
                 kw.update(update=UPDATE_EMA, cs_in=ema.cs_in, cs_out=ema.cs_out, w_in=ema.w_in, w_out=ema.w_out,
-                          E_old=E, E_new=ema.E_new, decay=ema.decay, eps=ema.eps, cb=cb)
+                          E_old=E, E_new=ema.E_new, E_prev=ema.E_prev, decay=ema.decay, eps=ema.eps, cb=cb)
             if reduce_fn is None:
                 res = step_finalize(K, D, packed, acc=acc, use_dwr=want_dwr, rows_local=N, **kw)
             else:
@@ -335,7 +343,7 @@ class _QuantizeFn(torch.autograd.Function):
                         ema.pending = torch.cuda.Event()
                         ema.pending.record(side)
         loss, ppl = res[0], res[1]
-        ctx.save_for_backward(x2d, E, idx, packed)
+        ctx.save_for_backward(x2d, E_bwd, idx, packed)
         ctx.beta, ctx.coef_codebook, ctx.grad_scale = beta, coef_codebook, grad_scale
         ctx.mark_non_differentiable(ppl, idx, packed)
         return loss, out, ppl, idx, packed
@@ -366,13 +374,20 @@ class _QuantizeFn(torch.autograd.Function):
                 _lib.check(lib.g2v_vq_grad_codebook(_ptr(packed), _ptr(g_loss),
                                                     2.0 * ctx.coef_codebook * ctx.grad_scale / M if M else 0.0,
                                                     K, D, _ptr(gE), st), "g2v_vq_grad_codebook")
-        return gx, gE, None, None, None, None, None, None, None, None, None
+        return gx, gE, None, None, None, None, None, None, None, None, None, None
 
 
 def quantize(x2d, E, *, zs=None, cb=None, beta=0.25, coef_codebook=1.0, want_dwr=False,
-             reduce_fn=None, grad_scale=1.0, flags=_lib.ALGO_AUTO, ema: Optional[EmaState] = None):
+             reduce_fn=None, grad_scale=1.0, flags=_lib.ALGO_AUTO, ema: Optional[EmaState] = None,
+             idx: Optional[torch.Tensor] = None):
+    """The whole layer on [N, D] rows.  `idx`: int32 code ids to use instead of searching (rows tokenised
+    earlier; also how the parity tests evaluate the downstream arithmetic at the reference's indices)."""
+    if idx is not None:
+        idx = idx.to(device=x2d.device, dtype=torch.int32).contiguous()
+        if idx.numel() != x2d.shape[0]:
+            raise RuntimeError("one code id per row expected")
     return _QuantizeFn.apply(x2d, E, zs, cb, float(beta), float(coef_codebook), bool(want_dwr),
-                             reduce_fn, float(grad_scale), int(flags), ema)
+                             reduce_fn, float(grad_scale), int(flags), ema, idx)
 
 
 # ------------------------------------------------------------------------------------------------

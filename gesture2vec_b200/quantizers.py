@@ -48,6 +48,11 @@ class _HardQuantizerBase(nn.Module):
         # data-parallel EMA: callable(packed fp32 tensor) doing an in-place sum all-reduce
         self.stats_reduce: Optional[Callable[[torch.Tensor], None]] = None
         self.grad_scale: float = 1.0
+        # EMA state updated in place (fixed addresses: a captured CUDA graph of the training step advances the
+        # state on every replay).  The backward pass then reads the old codebook from a private copy, so at most
+        # one forward may be pending its backward.  Default: fresh tensors per step, like the reference.
+        self.ema_inplace: bool = False
+        self._E_prev: Optional[torch.Tensor] = None
 
     # -- reference API -------------------------------------------------------------------------
     def embedding_grad(self, what: bool) -> None:
@@ -80,7 +85,7 @@ class _HardQuantizerBase(nn.Module):
         """Rows the search (and the EMA sums) run on, if different from the raw rows."""
         return None
 
-    def _run(self, inputs: torch.Tensor):
+    def _run(self, inputs: torch.Tensor, indices: Optional[torch.Tensor] = None):
         if inputs.numel() % self._embedding_dim:
             raise RuntimeError(
                 f"shape '[-1, {self._embedding_dim}]' is invalid for input of size {inputs.numel()}")
@@ -107,11 +112,16 @@ class _HardQuantizerBase(nn.Module):
             if training_ema:
                 if not (self._ema_w.data.is_contiguous() and self._ema_cluster_size.is_contiguous()):
                     raise RuntimeError("EMA state must be contiguous")
-                ema = F.EmaState(self._ema_cluster_size, self._ema_w.data, self._decay, self._epsilon)
+                E_prev = None
+                if self.ema_inplace:
+                    if self._E_prev is None or self._E_prev.shape != W.shape or self._E_prev.device != W.device:
+                        self._E_prev = torch.empty_like(W.data)
+                    E_prev = self._E_prev
+                ema = F.EmaState(self._ema_cluster_size, self._ema_w.data, self._decay, self._epsilon, E_prev)
             loss, out, ppl, idx, packed = F.quantize(
                 flat, E_arg, zs=zs, cb=cb, beta=self._commitment_cost,
                 coef_codebook=0.0 if self._ema else 1.0, want_dwr=want_dwr, reduce_fn=reduce_fn,
-                grad_scale=self.grad_scale, flags=self.search_flags, ema=ema)
+                grad_scale=self.grad_scale, flags=self.search_flags, ema=ema, idx=indices)
             self.last_indices = idx
             quantized = out.view(inputs.shape)
             enc = F.one_hot(idx, self._num_embeddings) if self.return_encodings else idx.long().unsqueeze(1)
@@ -120,11 +130,12 @@ class _HardQuantizerBase(nn.Module):
                     torch.cuda.current_stream(flat.device).wait_event(ema.pending)
                 # the step's single finalise launch wrote the new state into fresh tensors (the reference
                 # re-creates its Parameters each step, :1276-1282) and re-prepared `cb` for the new codebook
-                with torch.no_grad():
-                    self._ema_cluster_size = ema.cs_out   # registered buffer: assignment keeps it registered
-                    self._ema_w.data = ema.w_out
-                    W.data = ema.E_new
-                    self._cb_key = (ema.E_new.data_ptr(), W._version, str(ema.E_new.device))
+                if not self.ema_inplace:
+                    with torch.no_grad():
+                        self._ema_cluster_size = ema.cs_out   # registered buffer: assignment keeps it registered
+                        self._ema_w.data = ema.w_out
+                        W.data = ema.E_new
+                self._cb_key = (ema.E_new.data_ptr(), W._version, str(ema.E_new.device))
         if src_dev != quantized.device:
             loss, quantized, ppl, enc = (t.to(src_dev) for t in (loss, quantized, ppl, enc))
         return loss, quantized, ppl, enc
@@ -142,6 +153,11 @@ class _HardQuantizerBase(nn.Module):
 
     def forward(self, inputs: torch.Tensor):
         return self._run(inputs)
+
+    def forward_with_indices(self, inputs: torch.Tensor, indices: torch.Tensor):
+        """`forward` with the code ids given (one per row of `inputs.view(-1, D)`) instead of searched: rows
+        tokenised earlier by `tokenize`, or -- in the parity tests -- the reference's own indices."""
+        return self._run(inputs, indices=indices.reshape(-1))
 
 
 # ================================================================================================

@@ -39,6 +39,15 @@ class GestureTokenizer:
     ``[K, D]`` array.  The fp16/||e||^2 aux buffer of the codebook is prepared once and reused."""
 
     def __init__(self, codebook, device: Union[str, torch.device, None] = None, host_chunk_rows: int = 131072):
+        # a quantizer module whose search runs on a projection of the rows (Autoencoder_VQVAE_model.VQ_Payam_EMA
+        # searches pre_linear(z), :1230; VectorQuantizerEMA its pre_lin, :1755): the ids must be those of
+        # module.forward, so the rows go through the module's own projection first
+        self._project = None
+        if getattr(codebook, "_projects", False) and hasattr(codebook, "_search_rows"):
+            self._project = codebook._search_rows
+        elif hasattr(codebook, "pre_lin") and hasattr(codebook, "_embedding"):
+            self._project = lambda rows, _m=codebook: torch.nn.functional.linear(
+                rows, _m.pre_lin.weight.detach(), _m.pre_lin.bias.detach()).contiguous()
         w = getattr(getattr(codebook, "_embedding", None), "weight", codebook)
         if isinstance(w, np.ndarray):
             w = torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32))
@@ -59,11 +68,23 @@ class GestureTokenizer:
             return np.zeros(0, dtype=np.int64)
         if isinstance(rows, torch.Tensor) and rows.is_cuda:
             r = rows if rows.dtype in (torch.float32, torch.bfloat16, torch.float16) else rows.float()
+            if self._project is not None:
+                with torch.no_grad():
+                    r = self._project(r.float().contiguous())
             return vq_search(r.contiguous(), self.E, self.cb).cpu().numpy().astype(np.int64)
         t = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float32)) if isinstance(rows, np.ndarray) else rows
         if t.dtype not in (torch.float32, torch.bfloat16, torch.float16):
             t = t.float()
         t = t.contiguous()
+        if self._project is not None:
+            # projected flavour: chunks go to the device, through the projection, and are searched there
+            out = np.empty(t.shape[0], dtype=np.int64)
+            for r0 in range(0, t.shape[0], self.host_chunk_rows):
+                blk = t[r0:r0 + self.host_chunk_rows].to(self.E.device, non_blocking=True)
+                with torch.no_grad():
+                    blk = self._project(blk.float().contiguous())
+                out[r0:r0 + blk.shape[0]] = vq_search(blk.contiguous(), self.E, self.cb).cpu().numpy()
+            return out
         if not t.is_pinned() and t.numel() >= (1 << 22):
             t = t.pin_memory()
         return tokenize_host(t, self.E, self.cb, chunk_rows=self.host_chunk_rows).numpy().astype(np.int64)

@@ -51,6 +51,13 @@ extern "C" {
 #define G2V_ALGO_TC 2u          /* tcgen05 tensor-core path, error if unsupported */
 #define G2V_ALGO_MASK 3u
 #define G2V_NO_RECHECK 4u       /* keep the fast-pass winner (bf16/fp16 "fast" variant) */
+/* test / benchmark aid: pin the tensor-core sweep kernel (results are identical; a variant that does not cover
+ * the shape falls back to the automatic choice) */
+#define G2V_TC_VARIANT_MASK (7u << 8)
+#define G2V_TC_VARIANT_AUTO (0u << 8)
+#define G2V_TC_VARIANT_TMEM (1u << 8)   /* tc_tmem_kernel: rows -> fp16 A operand in tensor memory, CTA pairs */
+#define G2V_TC_VARIANT_FUSED (2u << 8)  /* tc_search_kernel<1,true>: fp32 rows converted in-kernel, single CTA */
+#define G2V_TC_VARIANT_PREP (3u << 8)   /* row_prep_kernel + tc_search_kernel<.,false>: fp16 rows in shared memory */
 
 /* slots of the optional int64 search_stats[8] output */
 #define G2V_STAT_ROWS 0         /* rows searched                                      */
@@ -62,6 +69,9 @@ int g2v_version(void);
 const char* g2v_strerror(int code);
 /* text of the last failure on the calling thread (CUDA error string etc.) */
 const char* g2v_last_error_detail(void);
+/* kernels this library has launched so far in this process (all threads); a benchmark reports the difference
+ * around its timed region as its launch count */
+unsigned long long g2v_launch_count(void);
 
 /* Codebook auxiliary data (||e||^2 in fp32 rounded from fp64, norm maxima for the
  * error bounds, and the fp16 operand copy the tensor-core path streams by TMA).
@@ -132,8 +142,7 @@ int g2v_vq_stats_finalize(const float* packed, int K, int D, float coef_codebook
  *   cs <- cs*decay + (1-decay)*counts ; n = sum cs ; cs <- (cs+eps)/(n+K*eps)*n
  *   ema_w <- ema_w*decay + (1-decay)*dw ; E <- ema_w / cs[:,None]      (dw = dwr + counts*E)
  * The new state goes to cs_out / ema_w_out / E_new, like the fresh tensors the reference produces each step
- * (:1276-1282).  ema_w_out == ema_w_in and E_new == E_old are allowed; cs_out MUST NOT alias cs_in (every
- * thread block reads all of cs_in for the Laplace-smoothing sum while one of them writes cs_out).
+ * (:1276-1282); each may alias its input (in-place state, e.g. for CUDA-graph replay).
  * If cb != NULL the aux buffer is re-prepared for E_new in the same launch. */
 int g2v_vq_ema_update(const float* cs_in, float* cs_out, const float* ema_w_in, float* ema_w_out,
                       const float* E_old, float* E_new, const float* packed, float decay, float eps, int K, int D,
@@ -148,7 +157,8 @@ int g2v_vq_ema_update(const float* cs_in, float* cs_out, const float* ema_w_in, 
  *   rows_local           rows of this call (written to packed[K*D+K+1] when packing)
  *   loss, perplexity     optional device scalars
  *   update               G2V_UPDATE_NONE: no codebook change (cs / ema_w / E_new unused); cb, if given, is prepared
- *                        for E_old.  G2V_UPDATE_EMA: as g2v_vq_ema_update (cs_out must not alias cs_in).
+ *                        for E_old.  G2V_UPDATE_EMA: as g2v_vq_ema_update; E_prev (optional, [K,D]) receives a
+ *                        copy of E_old, which an in-place update (E_new == E_old) needs for the backward pass.
  *                        G2V_UPDATE_KMEANS: as g2v_kmeans_update (shift2 optional).  cb, if given, is prepared
  *                        for E_new in both. */
 #define G2V_UPDATE_NONE 0
@@ -157,7 +167,7 @@ int g2v_vq_ema_update(const float* cs_in, float* cs_out, const float* ema_w_in, 
 int g2v_vq_step_finalize(int32_t* counts, double* sse, float* dwr, int dwr_replicas, int64_t rows_local,
                          float* packed, int K, int D, float coef_codebook, float coef_commit, float* loss,
                          float* perplexity, int update, const float* cs_in, float* cs_out, const float* ema_w_in,
-                         float* ema_w_out, const float* E_old, float* E_new, float decay, float eps,
+                         float* ema_w_out, const float* E_old, float* E_new, float* E_prev, float decay, float eps,
                          double* shift2, void* cb, size_t cb_bytes, void* stream);
 
 /* Backward of the layer wrt the inputs (closed form of the autograd graph the reference

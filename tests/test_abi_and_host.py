@@ -62,12 +62,12 @@ def test_size_queries_and_validation_without_gpu(lib):
     assert lib.g2v_tokenize_host_bytes(0, 4, 4, 0, 0) == 0
     # the fused finalise: bad update mode, EMA with aliased cluster sizes, missing statistics buffer
     assert lib.g2v_vq_step_finalize(None, None, None, 0, 0, None, 4, 4, 0.0, 0.0, None, None, 7, None, None, None, None,
-                                    None, None, 0.0, 0.0, None, None, 0, None) == -1
+                                    None, None, None, 0.0, 0.0, None, None, 0, None) == -1
     buf = (ctypes.c_float * 64)()
     p = ctypes.cast(buf, ctypes.c_void_p)
-    assert lib.g2v_vq_step_finalize(None, None, None, 0, 0, p, 4, 4, 0.0, 0.0, None, None, 1, p, p, p, p, p, p, 0.9, 1e-5,
-                                    None, None, 0, None) == -1          # cs_out aliases cs_in
-    assert lib.g2v_vq_ema_update(p, p, p, p, p, p, p, 0.9, 1e-5, 4, 4, None, 0, None) == -1
+    assert lib.g2v_vq_step_finalize(None, None, None, 0, 0, p, 4, 4, 0.0, 0.0, None, None, 1, p, p, p, p, p, p, p, 0.9,
+                                    1e-5, None, None, 0, None) == -1    # E_prev aliases the codebook
+    assert lib.g2v_vq_ema_update(p, p, p, p, None, p, p, 0.9, 1e-5, 4, 4, None, 0, None) == -1
     assert lib.g2v_exact_workspace_bytes(400) >= 400 * 8 and lib.g2v_exact_workspace_bytes(0) == 0
     assert lib.g2v_vq_search_exact(None, 0, None, 10, 4, 4, None, None, 0, None) == -1
 

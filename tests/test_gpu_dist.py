@@ -39,7 +39,7 @@ def _commitment_grad(layer, x):
     return x.grad.cpu().numpy()
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, overlap):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
@@ -47,7 +47,8 @@ def _worker(rank, world, port, out):
     try:
         import gesture2vec_b200 as g
         layer = _make_layer(dev)
-        red = g.enable_data_parallel_ema(layer)
+        red = g.enable_data_parallel_ema(layer, overlap=overlap)
+        assert (red.stream is not None) == overlap
         z = torch.from_numpy(O.synth_latents("gru", N, D, seed=2))
         b, e = g.shard_rows(N, rank, world)
         x = z[b:e].to(dev).requires_grad_(True)
@@ -67,11 +68,13 @@ def _worker(rank, world, port, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_ema_matches_single_gpu():
+@pytest.mark.parametrize("overlap", [False, True])
+def test_two_gpu_ema_matches_single_gpu(overlap):
+    """overlap=True: the all-reduce and the finalise launch run on a side stream under the one-hot kernel."""
     world = 2
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), out, overlap), nprocs=world, join=True)
     r0, r1 = out[0], out[1]
     for k in ("E", "w", "cs"):
         assert np.array_equal(r0[k], r1[k]), k             # identical all-reduce result -> identical state

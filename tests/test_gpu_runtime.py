@@ -1,0 +1,132 @@
+"""Runtime behaviour of the drop-in modules on the GPU: CUDA-graph capture and replay of the training step,
+in-place EMA state, a module on a device that is not the current one, and the tokenisers on the flavour that
+projects its rows first (Autoencoder_VQVAE_model.VQ_Payam_EMA, :1230)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vq_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+
+
+def _layer(g, dev, K=512, D=400, cls="DAE_VQ_Payam_EMA", seed=0):
+    layer = getattr(g, cls)(K, D, 0.25, 0.85)
+    with torch.no_grad():
+        layer._embedding.weight.copy_(torch.from_numpy(O.synth_codebook("uniform1", K, D, seed=seed)))
+        layer._ema_w.copy_(torch.from_numpy(np.random.default_rng(seed + 1).standard_normal((K, D), dtype=np.float32)))
+    return layer.to(dev).train()
+
+
+def _state(layer):
+    return [t.detach().clone() for t in (layer._embedding.weight, layer._ema_w, layer._ema_cluster_size)]
+
+
+def test_inplace_ema_equals_fresh_tensor_ema():
+    import gesture2vec_b200 as g
+    a, b = _layer(g, DEV), _layer(g, DEV)
+    b.ema_inplace = True
+    ptrs = [t.data_ptr() for t in (b._embedding.weight, b._ema_w, b._ema_cluster_size)]
+    gq = torch.randn(2, 128, 200, device=DEV)
+    for s in range(3):
+        x = torch.from_numpy(O.synth_latents("gru", 128, 400, seed=10 + s).reshape(2, 128, 200)).to(DEV)
+        outs = []
+        for layer in (a, b):
+            xi = x.clone().requires_grad_(True)
+            loss, q, ppl, enc = layer(xi)
+            (loss * 3.0 + (q * gq).sum()).backward()
+            outs.append((loss.detach(), q.detach(), ppl, enc, xi.grad))
+        for u, v in zip(*outs):
+            assert torch.equal(u, v)
+        for u, v in zip(_state(a), _state(b)):
+            assert torch.equal(u, v)
+    assert ptrs == [t.data_ptr() for t in (b._embedding.weight, b._ema_w, b._ema_cluster_size)]
+
+
+def test_cuda_graph_capture_and_replay_of_the_training_step():
+    """The N = 128 step of config/VQ-VAE.yml as ONE graph launch: capture forward + backward of the in-place EMA
+    layer, replay it three times on new inputs, and compare every output and the state with the eager layer."""
+    import gesture2vec_b200 as g
+    eager, graphed = _layer(g, DEV), _layer(g, DEV)
+    graphed.ema_inplace = True
+    xs = [torch.from_numpy(O.synth_latents("gru", 128, 400, seed=20 + s).reshape(2, 128, 200)).to(DEV) for s in range(5)]
+    gq = torch.randn(2, 128, 200, device=DEV)
+    static_x = xs[0].clone().requires_grad_(True)
+    # warm-up on a side stream (allocations, tensor maps, codebook aux), as torch.cuda.graphs asks for
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for s in range(2):
+            static_x.grad = None
+            with torch.no_grad():
+                static_x.copy_(xs[s])
+            loss, q, ppl, enc = graphed(static_x)
+            (loss * 3.0 + (q * gq).sum()).backward()
+    torch.cuda.current_stream().wait_stream(side)
+    for s in range(2):
+        xi = xs[s].clone().requires_grad_(True)
+        loss, q, ppl, enc = eager(xi)
+        (loss * 3.0 + (q * gq).sum()).backward()
+    graph = torch.cuda.CUDAGraph()
+    static_x.grad = None
+    with torch.cuda.graph(graph):
+        s_loss, s_q, s_ppl, s_enc = graphed(static_x)
+        (s_loss * 3.0 + (s_q * gq).sum()).backward()
+    s_grad = static_x.grad
+    for s in range(2, 5):
+        with torch.no_grad():
+            static_x.copy_(xs[s])
+        graph.replay()
+        xi = xs[s].clone().requires_grad_(True)
+        loss, q, ppl, enc = eager(xi)
+        (loss * 3.0 + (q * gq).sum()).backward()
+        torch.cuda.synchronize()
+        assert torch.equal(s_loss, loss.detach()) and torch.equal(s_q, q.detach()) and torch.equal(s_ppl, ppl)
+        assert torch.equal(s_enc, enc) and torch.equal(s_grad, xi.grad)
+        for u, v in zip(_state(eager), _state(graphed)):
+            assert torch.equal(u, v)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_module_on_a_device_that_is_not_current():
+    import gesture2vec_b200 as g
+    d1 = torch.device("cuda:1")
+    assert torch.cuda.current_device() == 0
+    a, b = _layer(g, DEV), _layer(g, d1)
+    x = torch.from_numpy(O.synth_latents("gru", 300, 400, seed=3))
+    ra = a(x.to(DEV).requires_grad_(True))
+    rb = b(x.to(d1).requires_grad_(True))
+    assert torch.cuda.current_device() == 0
+    for u, v in zip(ra, rb):
+        assert v.device == d1 and torch.equal(u.cpu(), v.cpu())
+    ids = g.tokenize(x.to(d1), b._embedding.weight.detach())
+    assert ids.device == d1 and torch.equal(ids.cpu(), g.tokenize(x.to(DEV), a._embedding.weight.detach()).cpu())
+    km = g.KMeans(n_clusters=8, init=x[:8].numpy(), max_iter=3, device=d1).fit(x.numpy())
+    km0 = g.KMeans(n_clusters=8, init=x[:8].numpy(), max_iter=3, device=DEV).fit(x.numpy())
+    assert np.array_equal(km.labels_, km0.labels_)
+
+
+def test_tokenizers_apply_the_projection_of_the_vqvae_flavour():
+    """GestureTokenizer(module) and module.tokenize() give argmax(forward(x).encodings) for the flavour whose
+    search runs on pre_linear(x) -- fp32 and bf16 rows, device and host inputs."""
+    import gesture2vec_b200 as g
+    K, D, N = 512, 400, 3000
+    layer = _layer(g, DEV, K, D, cls="VQVAE_VQ_Payam_EMA", seed=4).eval()
+    x = torch.from_numpy(O.synth_latents("gru", N, D, seed=5)).to(DEV)
+    with torch.no_grad():
+        enc = layer(x)[3]
+    want = torch.argmax(enc, 1)
+    assert torch.equal(layer.tokenize(x).long(), want)
+    tok = g.GestureTokenizer(layer)
+    assert np.array_equal(tok.encode_rows(x), want.cpu().numpy())
+    assert np.array_equal(tok.encode_rows(x.cpu().numpy()), want.cpu().numpy())
+    # 16-bit rows: projected in fp32 from the stored values, like forward() does with a 16-bit input
+    x16 = x.to(torch.bfloat16)
+    with torch.no_grad():
+        want16 = torch.argmax(layer(x16)[3], 1)
+    assert torch.equal(layer.tokenize(x16).long(), want16)
+    assert np.array_equal(tok.encode_rows(x16), want16.cpu().numpy())
+    # and the raw codebook (no projection) differs, which is what the old tokenizer silently returned
+    raw = g.tokenize(x, layer._embedding.weight.detach()).long()
+    assert not torch.equal(raw, want)
