@@ -23,6 +23,16 @@ def _state(layer):
     return [t.detach().clone() for t in (layer._embedding.weight, layer._ema_w, layer._ema_cluster_size)]
 
 
+def _close(u, v, what=""):
+    """Two runs of the same step agree to fp32 atomics order: the per-code residual sums are accumulated with
+    red.add.f32 in a scheduling-dependent order, so EMA state (and everything computed from it one step later)
+    matches to a few ulp, not bitwise.  Integer outputs and one-hots must be identical."""
+    if u.dtype in (torch.int32, torch.int64):
+        assert torch.equal(u, v), what
+    else:
+        torch.testing.assert_close(u, v, rtol=2e-5, atol=1e-6, msg=lambda m: f"{what}: {m}")
+
+
 def test_inplace_ema_equals_fresh_tensor_ema():
     import gesture2vec_b200 as g
     a, b = _layer(g, DEV), _layer(g, DEV)
@@ -82,10 +92,10 @@ def test_cuda_graph_capture_and_replay_of_the_training_step():
         loss, q, ppl, enc = eager(xi)
         (loss * 3.0 + (q * gq).sum()).backward()
         torch.cuda.synchronize()
-        assert torch.equal(s_loss, loss.detach()) and torch.equal(s_q, q.detach()) and torch.equal(s_ppl, ppl)
-        assert torch.equal(s_enc, enc) and torch.equal(s_grad, xi.grad)
+        for u, v in zip((s_loss, s_q, s_ppl, s_enc, s_grad), (loss.detach(), q.detach(), ppl, enc, xi.grad)):
+            _close(u, v, f"replay {s} outputs")
         for u, v in zip(_state(eager), _state(graphed)):
-            assert torch.equal(u, v)
+            _close(u, v, f"replay {s} state")
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")

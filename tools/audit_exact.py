@@ -37,7 +37,8 @@ def main():
     dev = torch.device("cuda:0")
     D = 400
     variants = {"auto": L.ALGO_AUTO, "simt": L.ALGO_SIMT, "tmem": L.ALGO_TC | L.TC_VARIANT_TMEM,
-                "fused": L.ALGO_TC | L.TC_VARIANT_FUSED, "prep": L.ALGO_TC | L.TC_VARIANT_PREP}
+                "fused": L.ALGO_TC | L.TC_VARIANT_FUSED, "prep": L.ALGO_TC | L.TC_VARIANT_PREP,
+            "pair": L.ALGO_TC | L.TC_VARIANT_PAIR}
     lines = []
 
     def log(rec):
@@ -60,7 +61,7 @@ def main():
         cb = g.prepare_codebook(E)
         names = list(variants) if K <= 2048 else ["auto", "prep", "simt"]
         for name in names:
-            if name == "tmem" and K > 576:
+            if name in ("tmem", "pair") and K > 576:
                 continue
             stats = torch.zeros(8, dtype=torch.int64, device=dev)
             idx = g.vq_search(z, E, cb, flags=variants[name], stats=stats)
@@ -74,7 +75,9 @@ def main():
         for dt in (torch.bfloat16, torch.float16):
             z16 = z[:n16].to(dt).contiguous()
             ex16 = g.vq_search_exact(z16, E)
-            for name in ("auto", "prep", "simt"):
+            for name in ("auto", "prep", "simt", "pair"):
+                if name == "pair" and K > 576:
+                    continue
                 idx = g.vq_search(z16, E, cb, flags=variants[name])
                 r = S.audit(z16.float(), E, idx, ex16, eps_tie=2.0 ** -40)
                 r.update(latents=lk, codebook=ck, K=K, dtype=str(dt).replace("torch.", ""), variant=name)
