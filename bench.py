@@ -327,7 +327,7 @@ def tmem_variant(dtype, N, K, D):
     dp = (D + 15) // 16 * 16
     acc0 = (dp // 2 + 15) // 16 * 16
     nt_max = min(256, ((512 - acc0) // 2) & ~15)
-    return nt_max >= 32 and -(-K // nt_max) <= 4
+    return nt_max >= 32 and -(-K // nt_max) <= (1 << 30 if dtype == "f32" else 16)
 
 
 # -------------------------------------------------------------------------------------------------

@@ -178,6 +178,9 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const FinParams P
       }
   };
   double shift_part = 0.0;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool vec_rows = (D % 4 == 0) && D <= 512 && al16(P.E_old) && al16(P.E_new) && al16(P.E_cb) && al16(P.packed) &&
+                        al16(P.w_in) && al16(P.w_out) && al16(P.E_prev);
   if (P.mode != 0 || P.cb) {
     for (int k = blockIdx.x * FIN_WARPS + warp; k < P.Kp; k += gridDim.x * FIN_WARPS) {
       if (k >= K) {
@@ -193,27 +196,68 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const FinParams P
       }
       double s2 = 0.0;
       float am = 0.f;
-      for (int j = lane; j < D; j += 32) {
+      // one code row.  Vector path (D % 4 == 0, 16-byte aligned rows, D <= 512): a lane owns the float4 columns
+      // lane, lane + 32, lane + 64, lane + 96 and issues all of its loads before the first use, so the row costs
+      // one memory round trip instead of D / 32 dependent ones (this launch is the latency of a small-batch step)
+      auto elem = [&](float eo, float pk, float wi, float& wo, float& en) {
         float e;
         if (P.mode == 1) {
-          const float eo = P.E_old[r0 + j];
-          if (P.E_prev) P.E_prev[r0 + j] = eo;          // the backward pass still needs the old codes
-          const float dw = fmaf(cnt, eo, __ldcg(P.packed + r0 + j));   // sum of rows = residual sum + count * code
-          const float w = __fadd_rn(__fmul_rn(P.w_in[r0 + j], P.decay), __fmul_rn(P.one_m, dw));
-          P.w_out[r0 + j] = w;
-          e = __fdiv_rn(w, csn);
-          P.E_new[r0 + j] = e;
+          const float dw = fmaf(cnt, eo, pk);              // sum of rows = residual sum + count * code
+          wo = __fadd_rn(__fmul_rn(wi, P.decay), __fmul_rn(P.one_m, dw));
+          e = __fdiv_rn(wo, csn);
         } else if (P.mode == 2) {
-          const float step = cnt > 0.f ? __fdiv_rn(__ldcg(P.packed + r0 + j), cnt) : 0.f;   // empty cluster keeps its centre
-          e = __fadd_rn(P.E_old[r0 + j], step);
-          P.E_new[r0 + j] = e;
+          const float step = cnt > 0.f ? __fdiv_rn(pk, cnt) : 0.f;   // empty cluster keeps its centre
+          e = __fadd_rn(eo, step);
           shift_part += (double)step * (double)step;
         } else {
-          e = P.E_cb[r0 + j];
+          e = eo;
         }
-        const double e2d = (double)e * (double)e;
-        s2 += e2d;
+        en = e;
+        s2 += (double)e * (double)e;
         am = fmaxf(am, fabsf(e));
+      };
+      const float* src_e = P.mode ? P.E_old : P.E_cb;
+      if (vec_rows) {
+        const int nq = D >> 2;
+        float4 eo[4], pk[4], wi[4];
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = lane + 32 * u;
+          const bool on = c < nq;
+          eo[u] = on ? *reinterpret_cast<const float4*>(src_e + r0 + 4 * c) : z4;
+          pk[u] = (on && P.mode) ? __ldcg(reinterpret_cast<const float4*>(P.packed + r0 + 4 * c)) : z4;
+          wi[u] = (on && P.mode == 1) ? *reinterpret_cast<const float4*>(P.w_in + r0 + 4 * c) : z4;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = lane + 32 * u;
+          if (c < nq) {
+            float4 wo = z4, en;
+            elem(eo[u].x, pk[u].x, wi[u].x, wo.x, en.x);
+            elem(eo[u].y, pk[u].y, wi[u].y, wo.y, en.y);
+            elem(eo[u].z, pk[u].z, wi[u].z, wo.z, en.z);
+            elem(eo[u].w, pk[u].w, wi[u].w, wo.w, en.w);
+            if (P.mode == 1) {
+              if (P.E_prev) *reinterpret_cast<float4*>(P.E_prev + r0 + 4 * c) = eo[u];   // the backward pass still needs the old codes
+              *reinterpret_cast<float4*>(P.w_out + r0 + 4 * c) = wo;
+            }
+            if (P.mode) *reinterpret_cast<float4*>(P.E_new + r0 + 4 * c) = en;
+          }
+        }
+      } else {
+        for (int j = lane; j < D; j += 32) {
+          const float eo = src_e[r0 + j];
+          const float pk = P.mode ? __ldcg(P.packed + r0 + j) : 0.f;
+          const float wi = P.mode == 1 ? P.w_in[r0 + j] : 0.f;
+          float wo = 0.f, en;
+          elem(eo, pk, wi, wo, en);
+          if (P.mode == 1) {
+            if (P.E_prev) P.E_prev[r0 + j] = eo;
+            P.w_out[r0 + j] = wo;
+          }
+          if (P.mode) P.E_new[r0 + j] = en;
+        }
       }
       if (P.cb) {
         s2 = warp_sum_d(s2);
@@ -275,16 +319,48 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const FinParams P
       hdr->magic = kCbMagic;
     }
   }
+  const bool vec_c = (D % 4 == 0) && P.Dp <= 512 && al16(P.E_cb);
   for (int k = blockIdx.x * FIN_WARPS + warp; k < P.Kp; k += gridDim.x * FIN_WARPS) {
     __half* o = e16 + (size_t)k * P.Dp;
     float s2 = 0.f, n2 = 0.f;
-    for (int j = lane; j < P.Dp; j += 32) {
-      const float v = (k < K && j < D) ? __ldcg(P.E_cb + (size_t)k * D + j) : 0.f;
-      const __half h = __float2half_rn(v * sc);
-      const float r = v - __half2float(h) * inv;
-      s2 = fmaf(r, r, s2);
-      n2 = fmaf(v, v, n2);
-      o[j] = h;
+    if (vec_c) {                                           // float4 in, 4 x fp16 (8 bytes) out; Dp % 16 == 0
+      const int nq = D >> 2, nqp = P.Dp >> 2;
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = lane + 32 * u;
+        v[u] = (k < K && c < nq) ? __ldcg(reinterpret_cast<const float4*>(P.E_cb + (size_t)k * D + 4 * c))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = lane + 32 * u;
+        if (c < nqp) {
+          const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+          const __half2 h01 = __floats2half2_rn(vv[0] * sc, vv[1] * sc), h23 = __floats2half2_rn(vv[2] * sc, vv[3] * sc);
+          const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+          const float back[4] = {f01.x, f01.y, f23.x, f23.y};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float r = vv[t] - back[t] * inv;
+            s2 = fmaf(r, r, s2);
+            n2 = fmaf(vv[t], vv[t], n2);
+          }
+          uint2 pk2;
+          pk2.x = *reinterpret_cast<const uint32_t*>(&h01);
+          pk2.y = *reinterpret_cast<const uint32_t*>(&h23);
+          *reinterpret_cast<uint2*>(o + 4 * c) = pk2;
+        }
+      }
+    } else {
+      for (int j = lane; j < P.Dp; j += 32) {
+        const float v = (k < K && j < D) ? __ldcg(P.E_cb + (size_t)k * D + j) : 0.f;
+        const __half h = __float2half_rn(v * sc);
+        const float r = v - __half2float(h) * inv;
+        s2 = fmaf(r, r, s2);
+        n2 = fmaf(v, v, n2);
+        o[j] = h;
+      }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {

@@ -343,6 +343,7 @@ class _QuantizeFn(torch.autograd.Function):
                         ema.pending = torch.cuda.Event()
                         ema.pending.record(side)
         loss, ppl = res[0], res[1]
+        ctx.set_materialize_grads(False)      # an output nobody differentiates gets None, not a zero tensor of its size
         ctx.save_for_backward(x2d, E_bwd, idx, packed)
         ctx.beta, ctx.coef_codebook, ctx.grad_scale = beta, coef_codebook, grad_scale
         ctx.mark_non_differentiable(ppl, idx, packed)
