@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("G2V_LIB_PATH") or os.path.join(HERE, "csrc", "libg2v_
 # dtype / flag codes (mirror include/g2v_vq.h)
 F32, BF16, F16 = 0, 1, 2
 ALGO_AUTO, ALGO_SIMT, ALGO_TC, NO_RECHECK = 0, 1, 2, 4
+GEMM_ACCUMULATE, GEMM_FP16 = 1, 2
 TC_VARIANT_TMEM, TC_VARIANT_FUSED, TC_VARIANT_PREP, TC_VARIANT_PAIR = 1 << 8, 2 << 8, 3 << 8, 4 << 8
 STAT_ROWS, STAT_PAIR_RECHECK, STAT_FULL_RECHECK, STAT_FALLBACK_ROWS = 0, 1, 2, 3
 
@@ -39,6 +40,8 @@ SIGNATURES = {
     "g2v_vq_ema_update": (_i, [_p, _p, _p, _p, _p, _p, _p, _f, _f, _i, _i, _p, _sz, _p]),
     "g2v_vq_step_finalize": (_i, [_p, _p, _p, _i, _i64, _p, _i, _i, _f, _f, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _f, _f,
                                   _p, _p, _sz, _p]),
+    "g2v_gemm_workspace_bytes": (_sz, [_i64, _i, _i64, _u]),
+    "g2v_gemm_f32": (_i, [_p, _i64, _i, _p, _i64, _i, _i64, _i, _i64, _p, _p, _i64, _f, _u, _p, _sz, _p]),
     "g2v_exact_workspace_bytes": (_sz, [_i]),
     "g2v_vq_search_exact": (_i, [_p, _i, _p, _i64, _i, _i, _p, _p, _sz, _p]),
     "g2v_vq_backward": (_i, [_p, _p, _p, _p, _p, _f, _i64, _i, _i, _p, _p]),

@@ -232,6 +232,25 @@ int g2v_kmeans_update(const float* E_old, const float* packed, int K, int D, flo
                               0.f, shift2, cb, cb_bytes, stream);
 }
 
+size_t g2v_gemm_workspace_bytes(int64_t M, int N, int64_t K, unsigned flags) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  return gemm_workspace_bytes(M, N, K, (flags & G2V_GEMM_FP16) ? 1 : 0);
+}
+
+int g2v_gemm_f32(const float* A, int64_t lda, int transA, const float* B, int64_t ldb, int transB, int64_t M, int N,
+                 int64_t K, const float* bias, float* C, int64_t ldc, float alpha, unsigned flags, void* ws,
+                 size_t ws_bytes, void* stream) {
+  const int single = (flags & G2V_GEMM_FP16) ? 1 : 0, accumulate = (flags & G2V_GEMM_ACCUMULATE) ? 1 : 0;
+  if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C || M > 0x7fffffffLL || K > 0x7fffffffLL) return G2V_ERR_INVALID;
+  if (lda < (transA ? M : K) || ldb < (transB ? (int64_t)N : K) || ldc < N) return G2V_ERR_INVALID;
+  if (!ws || ws_bytes < gemm_workspace_bytes(M, N, K, single)) return G2V_ERR_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(ws) & 255) return G2V_ERR_ALIGN;
+  int rc = check_arch();
+  if (rc) return rc;
+  return launch_gemm_f32(A, lda, transA, B, ldb, transB, M, N, K, bias, C, ldc, alpha, accumulate, single, ws,
+                         (cudaStream_t)stream);
+}
+
 size_t g2v_exact_workspace_bytes(int K) { return K > 0 ? align_up((size_t)K * sizeof(double), 256) : 0; }
 
 int g2v_vq_search_exact(const void* z, int z_dtype, const float* E, int64_t N, int K, int D, int32_t* idx,

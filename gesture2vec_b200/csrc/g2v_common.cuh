@@ -120,6 +120,12 @@ int launch_grad_codebook(const float* dwr, const float* g_loss, float coef_e, in
                          cudaStream_t st);
 int launch_onehot(const int32_t* idx, int64_t N, int K, float* enc, cudaStream_t st);
 
+// ---- g2v_gemm.cu: C[M,N] (+)= alpha * op(A)[M,K] * op(B)[N,K]^T + bias, fp32 in / out, split-fp16 tcgen05 GEMM
+size_t gemm_workspace_bytes(int64_t M, int N, int64_t K, int single_term);
+int launch_gemm_f32(const float* A, int64_t lda, int transA, const float* B, int64_t ldb, int transB, int64_t M, int N,
+                    int64_t K, const float* bias, float* C, int64_t ldc, float alpha, int accumulate, int single_term,
+                    void* ws, cudaStream_t st);
+
 // ---- tensor-core path, implemented in g2v_tc.cu ---------------------------------------------
 bool tc_supported(int K, int D);
 size_t tc_workspace_bytes(int64_t N, int K, int D, int z_dtype);

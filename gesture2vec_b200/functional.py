@@ -273,6 +273,41 @@ def one_hot(idx: torch.Tensor, K: int) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------
+# dense projections on the tensor cores (csrc/g2v_gemm.cu)
+# ------------------------------------------------------------------------------------------------
+def gemm(A: torch.Tensor, B: torch.Tensor, *, bias: Optional[torch.Tensor] = None, transA: bool = False,
+         transB: bool = False, out: Optional[torch.Tensor] = None, alpha: float = 1.0, accumulate: bool = False,
+         fp16: bool = False) -> torch.Tensor:
+    """C = alpha * op(A) @ op(B)^T + bias on the tcgen05 tensor cores at fp32 accuracy (split-fp16 operands).
+
+    A: [M, K] fp32 (or [K, M] with transA), B: [N, K] fp32 -- nn.Linear's weight layout -- (or [K, N] with transB);
+    rows may be strided (stride(1) == 1).  `fp16=True`: one fp16 term per operand (for very long reductions)."""
+    _need_cuda(A, "A")
+    _need_cuda(B, "B")
+    assert A.dtype == torch.float32 and B.dtype == torch.float32 and A.dim() == 2 and B.dim() == 2
+    if A.stride(1) != 1:
+        A = A.contiguous()
+    if B.stride(1) != 1:
+        B = B.contiguous()
+    M, K = (A.shape[1], A.shape[0]) if transA else A.shape
+    N, Kb = (B.shape[1], B.shape[0]) if transB else B.shape
+    assert K == Kb, "reduction lengths differ"
+    dev = A.device
+    lib = _lib.load()
+    flags = (_lib.GEMM_ACCUMULATE if accumulate else 0) | (_lib.GEMM_FP16 if fp16 else 0)
+    with _on(dev):
+        if out is None:
+            assert not accumulate
+            out = torch.empty(M, N, dtype=torch.float32, device=dev)
+        assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype == torch.float32
+        ws = _scratch.get(dev, "gemm", lib.g2v_gemm_workspace_bytes(M, N, K, flags))
+        _lib.check(lib.g2v_gemm_f32(_ptr(A), A.stride(0), int(transA), _ptr(B), B.stride(0), int(transB), M, N, K,
+                                    _ptr(bias), _ptr(out), out.stride(0), float(alpha), flags, _ptr(ws), ws.numel(),
+                                    _stream(dev)), "g2v_gemm_f32")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # autograd
 # ------------------------------------------------------------------------------------------------
 class EmaState:

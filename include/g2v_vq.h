@@ -196,6 +196,26 @@ int g2v_kmeans_update(const float* E_old, const float* packed, int K, int D, flo
  * returns it and callers argmax it (Clustering.py:156, lmdb_data_loader.py:1281). */
 int g2v_onehot(const int32_t* idx, int64_t N, int K, float* enc, void* stream);
 
+/* Dense projection on the tensor cores at fp32 accuracy:  C[M,N] (+)= alpha * op(A) * op(B)^T + bias[N].
+ * Replaces the fp32 nn.Linear / torch.matmul calls next to the search: pre_linear of
+ * Autoencoder_VQVAE_model.VQ_Payam_EMA (:1230) and VectorQuantizerEMA (:1755), and the products of the soft
+ * quantizer VQ_Payam_GSSoft (:1390-1412) and of its backward pass.  Each fp32 operand is split into two fp16
+ * terms and the three significant partial products are folded into ONE tcgen05 GEMM with a 3x longer reduction
+ * (csrc/g2v_gemm.cu): ~2^-21 relative, like an fp32 SGEMM.
+ *   A    fp32, [M, K] row-major with leading dimension lda; transA != 0: stored [K, M] (the reduction runs over rows)
+ *   B    fp32, [N, K] row-major (nn.Linear's weight layout) with ldb; transB != 0: stored [K, N]
+ *   C    fp32 [M, N] with ldc; bias optional ([N])
+ *   flags  G2V_GEMM_ACCUMULATE: C += ... instead of C = ...;  G2V_GEMM_FP16: one fp16 term per operand (2^-11
+ *          per product, unbiased): for reductions over ~10^6 rows (weight gradients), a third of the traffic
+ * A reduction much longer than the output (weight gradients) is split over thread-block pairs and accumulated
+ * with fp32 atomics.  ws: g2v_gemm_workspace_bytes(M, N, K, flags) bytes (the fp16 operand copies). */
+#define G2V_GEMM_ACCUMULATE 1u
+#define G2V_GEMM_FP16 2u
+size_t g2v_gemm_workspace_bytes(int64_t M, int N, int64_t K, unsigned flags);
+int g2v_gemm_f32(const float* A, int64_t lda, int transA, const float* B, int64_t ldb, int transB, int64_t M, int N,
+                 int64_t K, const float* bias, float* C, int64_t ldc, float alpha, unsigned flags, void* ws,
+                 size_t ws_bytes, void* stream);
+
 /* Verification aid, not a product path: the exact-arithmetic nearest code of EVERY row, all products and
  * sums in fp64 (no error bounds, candidate lists or operand rounding shared with g2v_vq_search), first index
  * on exact ties -- what torch.argmin over fp64 distances of DAE_model.py:320-327 would return.  FP64-bound
