@@ -18,6 +18,8 @@ The default run (no --workload / --codes / --rows override) also measures, as su
                        concatenated batch
   sweep                configs[3]: K = 512 .. 16384 at 1 048 576 rows per GPU, fp32 and bf16 rows, tensor roofline
   latency_n128_us      the reference's real batch (128 chunks per step): eager step and CUDA-graph replay
+  soft_quantizer       SURVEY 8f #1: VQ_Payam_GSSoft fwd+bwd (tcgen05 split-fp16 GEMMs + row kernels) vs eager torch
+  vqvae_ema_flavour    the EMA flavour that searches on pre_linear(z), 1 M rows (pre_linear on g2v_gemm_f32)
   eager_cuda_baseline  the reference's op sequence in eager torch on the SAME GPU (cuBLAS path): the factor a
                        Gesture2Vec user with a GPU would see
 One JSON line is printed by rank 0.
@@ -540,6 +542,82 @@ def latency_record(cx: Ctx, g2v, lib) -> dict:
     return rec
 
 
+def soft_record(cx: Ctx, g2v, lib, pk) -> dict:
+    """the soft quantizer VQ_Payam_GSSoft (the layer Autoencoder_VQVAE instantiates), fwd+bwd on
+    131 072 chunks, K=512: this library (split-fp16 tcgen05 GEMMs + row kernels) and the reference's op sequence in
+    eager torch (fp32 cuBLAS, autograd) on the same GPU.  flops: one logical pass per product (split terms not credited)."""
+    dev, K, D, N = cx.dev, 512, D_LATENT, 131072
+    gen = torch.Generator(device=dev).manual_seed(11 + cx.rank)
+    x = torch.tanh(0.8 * torch.randn(N, D, device=dev, generator=gen))
+    gq = torch.randn(N, D, device=dev, generator=gen)
+    layer = g2v.VQVAE_VQ_Payam_GSSoft(K, D, 0.25).to(dev)
+    xs = x.clone().requires_grad_(True)
+
+    def step():
+        xs.grad = None
+        layer.zero_grad(set_to_none=True)
+        loss, q, ppl, p = layer(xs)
+        torch.autograd.backward([loss, q], [torch.ones_like(loss), gq])
+    step()
+    torch.cuda.synchronize()
+    l0 = lib.g2v_launch_count()
+    step()
+    launches = int(lib.g2v_launch_count() - l0)
+    ms = cx.timed(step, 10)
+    flops = 2.0 * N * (3 * D * D + 9 * K * D)
+    rec = {"codes_K": K, "rows_per_gpu": N, "ms_per_step": ms, "value": N * cx.world / (ms * 1e-3), "unit": UNIT,
+           "own_launches_per_step": launches, "algorithmic_tflops": flops / (ms * 1e-3) / 1e12,
+           "frac_of_sustained_bf16_peak": flops / (ms * 1e-3) / 1e12 / pk["bf16_sustained"],
+           "note": "every product is a 3-term split-fp16 GEMM (fp32 accuracy): the tensor pipe does 3x the credited flops"}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    E = layer._embedding.weight.detach().clone().requires_grad_(True)
+    Wm, bm = layer.mean_layer.weight.detach().clone().requires_grad_(True), layer.mean_layer.bias.detach().clone().requires_grad_(True)
+    Wl, bl = layer.logvar_layer.weight.detach().clone().requires_grad_(True), layer.logvar_layer.bias.detach().clone().requires_grad_(True)
+
+    def eager():
+        xe = x.detach().requires_grad_(True)
+        for t in (E, Wm, bm, Wl, bl):
+            t.grad = None
+        m = torch.nn.functional.linear(xe, Wm, bm)
+        lv = torch.nn.functional.linear(m, Wl, bl)
+        d = torch.sum(m ** 2, dim=1, keepdim=True) + torch.sum(E ** 2, dim=1) - 2 * torch.matmul(m, E.t())
+        smooth = 1.0 / torch.exp(lv) ** 2
+        prob = torch.exp(-torch.multiply(d / 400, 0.5 * smooth)) / torch.sqrt(smooth)
+        probs = prob / prob.sum(1).unsqueeze(1)
+        q = torch.matmul(probs, E)
+        loss = torch.nn.functional.mse_loss(q, xe.detach()) + 0.25 * torch.nn.functional.mse_loss(q.detach(), xe)
+        q = xe + (q - xe).detach()
+        torch.autograd.backward([loss, q], [torch.ones_like(loss), gq])
+    ems = cx.timed(eager, 5)
+    rec["eager_cuda"] = {"ms_per_step": ems, "value": N * cx.world / (ems * 1e-3), "unit": UNIT}
+    rec["vs_eager_cuda"] = ems / ms
+    return rec
+
+
+def vqvae_ema_record(cx: Ctx, g2v, lib, pk) -> dict:
+    """The flavour Autoencoder_VQVAE.__init__ constructs at :801 (search and EMA sums on pre_linear(z)): fwd+bwd+EMA
+    at 1 M rows, K=512 -- pre_linear runs on g2v_gemm_f32, not on cuBLAS."""
+    dev, K, D, N = cx.dev, 512, D_LATENT, 1_000_000
+    gen = torch.Generator(device=dev).manual_seed(21 + cx.rank)
+    E = torch.rand(K, D, device=dev, generator=torch.Generator(device=dev).manual_seed(0)) * 2 - 1
+    layer = g2v.VQVAE_VQ_Payam_EMA(K, D, 0.25, 0.85).to(dev).train()
+    with torch.no_grad():
+        layer._embedding.weight.copy_(E)
+    layer.return_encodings = False
+    if cx.world > 1:
+        g2v.enable_data_parallel_ema(layer, overlap=True)
+    zf = torch.tanh(0.8 * torch.randn(N, D, device=dev, generator=gen)).requires_grad_(True)
+    gq = torch.randn(N, D, device=dev, generator=gen)
+
+    def step():
+        zf.grad = None
+        loss, q, ppl, _ = layer(zf)
+        torch.autograd.backward([loss, q], [torch.ones_like(loss), gq])
+    ms = cx.timed(step, 10)
+    return {"codes_K": K, "rows_per_gpu": N, "ms_per_step": ms, "value": N * cx.world / (ms * 1e-3), "unit": UNIT,
+            "pre_linear": "g2v_gemm_f32 (split-fp16 tcgen05 GEMM, 2*N*D*D flop per step)"}
+
+
 def eager_cuda_baseline(cx: Ctx, K_tok: int, K_train: int) -> dict:
     """The reference's own op sequence (DAE_model.py:301-348 hard VQ forward; :396-482 EMA forward + autograd backward)
     restated in eager torch on THIS GPU -- cuBLAS SGEMMs (TF32 off, like the reference's default), materialised
@@ -800,6 +878,8 @@ def main():
         train = [train_record(cx, g2v, lib, 512, 1_000_000, 10, pk), train_record(cx, g2v, lib, 400, 1_000_000, 10, pk)]
         dpc = dp_check(cx, g2v) if world > 1 else None
         sweep = sweep_records(cx, g2v, lib, pk)
+        soft = soft_record(cx, g2v, lib, pk)
+        vq_ema = vqvae_ema_record(cx, g2v, lib, pk)
         lat = latency_record(cx, g2v, lib) if rank == 0 else None
         cx.barrier()
         eager = eager_cuda_baseline(cx, 400, 512)
@@ -807,6 +887,8 @@ def main():
             out["train"] = train
             out["dp_check"] = dpc
             out["sweep"] = sweep
+            out["soft_quantizer"] = soft
+            out["vqvae_ema_flavour"] = vq_ema
             out["latency_n128_us"] = lat
             out["eager_cuda_baseline"] = eager
             out["vs_eager_cuda"] = {"tokenize_k400": value / eager["tokenize"]["value"],

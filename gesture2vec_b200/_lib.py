@@ -42,6 +42,10 @@ SIGNATURES = {
                                   _p, _p, _sz, _p]),
     "g2v_gemm_workspace_bytes": (_sz, [_i64, _i, _i64, _u]),
     "g2v_gemm_f32": (_i, [_p, _i64, _i, _p, _i64, _i, _i64, _i, _i64, _p, _p, _i64, _f, _u, _p, _sz, _p]),
+    "g2v_soft_assign": (_i, [_p, _p, _p, _p, _i64, _i, _i, _p, _p, _p]),
+    "g2v_soft_tail": (_i, [_p, _p, _i64, _i, _i, _f, _p, _p, _p, _p, _p, _p]),
+    "g2v_soft_backward": (_i, [_p, _p, _p, _p, _i64, _i, _p, _p, _p, _p, _p, _p]),
+    "g2v_soft_gx": (_i, [_p, _p, _p, _p, _p, _p, _i64, _p, _p]),
     "g2v_exact_workspace_bytes": (_sz, [_i]),
     "g2v_vq_search_exact": (_i, [_p, _i, _p, _i64, _i, _i, _p, _p, _sz, _p]),
     "g2v_vq_backward": (_i, [_p, _p, _p, _p, _p, _f, _i64, _i, _i, _p, _p]),

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.abspath(os.path.join(HERE, "..", "include"))
 LIB = os.path.join(CSRC, "libg2v_vq.so")
-SOURCES = ["g2v_api.cu", "g2v_simt.cu", "g2v_finalize.cu", "g2v_audit.cu", "g2v_gemm.cu", "g2v_tc.cu"]
+SOURCES = ["g2v_api.cu", "g2v_simt.cu", "g2v_finalize.cu", "g2v_audit.cu", "g2v_gemm.cu", "g2v_soft.cu", "g2v_tc.cu"]
 HEADERS = [os.path.join(CSRC, "g2v_common.cuh"), os.path.join(INCLUDE, "g2v_vq.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

@@ -251,6 +251,36 @@ int g2v_gemm_f32(const float* A, int64_t lda, int transA, const float* B, int64_
                          (cudaStream_t)stream);
 }
 
+int g2v_soft_assign(const float* m, float* dot_d, const float* lv, const float* e2, int64_t N, int K, int D, float* p,
+                    float* colsum, void* stream) {
+  if (bad_shape(N, K, D) || !e2 || !colsum || (N > 0 && (!m || !dot_d || !lv || !p))) return G2V_ERR_INVALID;
+  if ((size_t)K * 8 > 48 * 1024) return G2V_ERR_UNSUPPORTED;        // column sums live in (default-size) shared memory
+  if (N == 0) return G2V_OK;
+  return launch_soft_assign(m, dot_d, lv, e2, N, K, D, p, colsum, (cudaStream_t)stream);
+}
+
+int g2v_soft_tail(const float* x, const float* q, int64_t N, int K, int D, float beta, float* out, double* sse,
+                  const float* colsum, float* loss, float* perplexity, void* stream) {
+  if (bad_shape(N, K, D) || !sse || !colsum || !loss || !perplexity || (N > 0 && (!x || !q || !out))) return G2V_ERR_INVALID;
+  return launch_soft_tail(x, q, N, K, D, beta, out, sse, colsum, loss, perplexity, (cudaStream_t)stream);
+}
+
+int g2v_soft_backward(const float* p, const float* dp, const float* d, const float* lv, int64_t N, int K, float* gd,
+                      float* glv, float* rowsum_gd, float* col_gd, float* col_glv, void* stream) {
+  if (N < 0 || K <= 0 || !col_gd || !col_glv || (N > 0 && (!p || !dp || !d || !lv || !gd || !glv || !rowsum_gd)))
+    return G2V_ERR_INVALID;
+  if ((size_t)K * 8 > 48 * 1024) return G2V_ERR_UNSUPPORTED;
+  if (N == 0) return G2V_OK;
+  return launch_soft_bwd(p, dp, d, lv, N, K, gd, glv, rowsum_gd, col_gd, col_glv, (cudaStream_t)stream);
+}
+
+int g2v_soft_gx(const float* gmw, const float* x, const float* q, const float* g_out, const float* c, const float* a,
+                int64_t n, float* gx, void* stream) {
+  if (n < 0 || !c || !a || (n > 0 && (!gmw || !x || !q || !gx))) return G2V_ERR_INVALID;
+  if (n == 0) return G2V_OK;
+  return launch_soft_gx(gmw, x, q, g_out, c, a, n, gx, (cudaStream_t)stream);
+}
+
 size_t g2v_exact_workspace_bytes(int K) { return K > 0 ? align_up((size_t)K * sizeof(double), 256) : 0; }
 
 int g2v_vq_search_exact(const void* z, int z_dtype, const float* E, int64_t N, int K, int D, int32_t* idx,

@@ -126,6 +126,16 @@ int launch_gemm_f32(const float* A, int64_t lda, int transA, const float* B, int
                     int64_t K, const float* bias, float* C, int64_t ldc, float alpha, int accumulate, int single_term,
                     void* ws, cudaStream_t st);
 
+// ---- g2v_soft.cu: row kernels of the soft quantizer VQ_Payam_GSSoft
+int launch_soft_assign(const float* m, float* dot, const float* lv, const float* e2, int64_t N, int K, int D, float* p,
+                       float* colsum, cudaStream_t st);
+int launch_soft_tail(const float* x, const float* q, int64_t N, int K, int D, float beta, float* out, double* sse,
+                     const float* colsum, float* loss, float* ppl, cudaStream_t st);
+int launch_soft_bwd(const float* p, const float* dp, const float* d, const float* lv, int64_t N, int K, float* gd, float* glv,
+                    float* rowsum_gd, float* col_gd, float* col_glv, cudaStream_t st);
+int launch_soft_gx(const float* gmw, const float* x, const float* q, const float* g_out, const float* c, const float* a,
+                   int64_t n, float* gx, cudaStream_t st);
+
 // ---- tensor-core path, implemented in g2v_tc.cu ---------------------------------------------
 bool tc_supported(int K, int D);
 size_t tc_workspace_bytes(int64_t N, int K, int D, int z_dtype);

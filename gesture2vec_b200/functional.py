@@ -307,6 +307,30 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     return out
 
 
+class _LinearFn(torch.autograd.Function):
+    """y = x W^T + b on g2v_gemm_f32, with the two backward products on it as well."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        ctx.save_for_backward(x, W)
+        ctx.has_bias = b is not None
+        return gemm(x, W.detach(), bias=None if b is None else b.detach())
+
+    @staticmethod
+    def backward(ctx, g):
+        x, W = ctx.saved_tensors
+        g = g.contiguous()
+        gx = gemm(g, W.detach(), transB=True) if ctx.needs_input_grad[0] else None
+        gW = gemm(g, x, transA=True, transB=True) if ctx.needs_input_grad[1] else None
+        gb = g.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return gx, gW, gb
+
+
+def linear(x: torch.Tensor, W: torch.Tensor, b: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """nn.Linear's arithmetic (fp32 in / out) on the tcgen05 GEMM; differentiable."""
+    return _LinearFn.apply(x.contiguous(), W, b)
+
+
 # ------------------------------------------------------------------------------------------------
 # autograd
 # ------------------------------------------------------------------------------------------------

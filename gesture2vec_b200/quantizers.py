@@ -228,9 +228,55 @@ class VQVAE_VQ_Payam_EMA(_HardQuantizerBase):
     _projects = True
 
     def _search_rows(self, flat: torch.Tensor) -> Optional[torch.Tensor]:
-        # plain library GEMM (cuBLAS through torch); no gradient reaches pre_linear
-        return torch.nn.functional.linear(flat, self.pre_linear.weight.detach(),
-                                          self.pre_linear.bias.detach()).contiguous()
+        # pre_linear on the tensor cores at fp32 accuracy (g2v_gemm_f32: split-fp16 tcgen05 GEMM, bias in the
+        # epilogue); no gradient reaches pre_linear
+        return F.gemm(flat, self.pre_linear.weight.detach(), bias=self.pre_linear.bias.detach())
+
+
+class VQVAE_VQ_Payam_GSSoft(nn.Module):
+    """Autoencoder_VQVAE_model.py:1304-1433 -- the soft quantizer `Autoencoder_VQVAE.__init__` ends on (:816-820).
+
+    Same constructor, attributes and state_dict keys (`pre_linear.*` exists and is unused, `_embedding.weight` ~
+    N(0,1), `mean_layer.*`, `logvar_layer.*`), same forward contract; `encodings` is the dense [N, K] matrix of
+    assignment probabilities.  The arithmetic runs in soft.py (tcgen05 GEMMs + the g2v_soft_* row kernels)."""
+
+    def __init__(self, num_embeddings: int, embedding_dim: int, commitment_cost: float):
+        super().__init__()
+        self._embedding_dim = int(embedding_dim)
+        self._num_embeddings = int(num_embeddings)
+        self.pre_linear = nn.Linear(self._embedding_dim, self._embedding_dim)
+        self._embedding = nn.Embedding(self._num_embeddings, self._embedding_dim)
+        self._embedding.weight.data.normal_()
+        self._commitment_cost = float(commitment_cost)
+        self.mean_layer = nn.Linear(self._embedding_dim, self._embedding_dim)
+        self.logvar_layer = nn.Linear(self._embedding_dim, self._num_embeddings)
+
+    def embedding_grad(self, what: bool) -> None:
+        for param in self._embedding.parameters():
+            param.requires_grad = what
+
+    def forward(self, inputs: torch.Tensor):
+        from .soft import soft_quantize
+        if inputs.numel() % self._embedding_dim:
+            raise RuntimeError(
+                f"shape '[-1, {self._embedding_dim}]' is invalid for input of size {inputs.numel()}")
+        src_dev = inputs.device
+        W0 = self._embedding.weight
+        if not inputs.is_cuda:
+            if not W0.is_cuda:
+                raise RuntimeError(
+                    "gesture2vec_b200 quantizers run on a CUDA device only: move the module to a "
+                    "B200 (`.cuda()`); there is no CPU implementation of this path")
+            inputs = inputs.to(W0.device)
+        if inputs.dtype != torch.float32:
+            inputs = inputs.float()
+        flat = inputs.contiguous().view(-1, self._embedding_dim)
+        loss, out, ppl, p = soft_quantize(flat, W0, self.mean_layer.weight, self.mean_layer.bias,
+                                          self.logvar_layer.weight, self.logvar_layer.bias, self._commitment_cost)
+        quantized = out.view(inputs.shape)
+        if src_dev != quantized.device:
+            loss, quantized, ppl, p = (t.to(src_dev) for t in (loss, quantized, ppl, p))
+        return loss, quantized, ppl, p
 
 
 class VectorQuantizerEMA(_HardQuantizerBase):
@@ -255,7 +301,10 @@ class VectorQuantizerEMA(_HardQuantizerBase):
 
     def forward(self, inputs: torch.Tensor):
         rows = torch.hstack((inputs[0], inputs[1]))
-        rows = self.pre_lin(rows)                       # differentiable: grads reach pre_lin here
+        if rows.is_cuda:                                # differentiable: grads reach pre_lin here
+            rows = F.linear(rows.float(), self.pre_lin.weight, self.pre_lin.bias)
+        else:
+            rows = self.pre_lin(rows)                   # CPU input: _run raises or moves it, like the other flavours
         loss, quantized, ppl, enc = self._run(rows)
         quantized = torch.reshape(quantized, (2, quantized.shape[0], -1)).contiguous()
         return loss, quantized, ppl, enc
@@ -264,5 +313,5 @@ class VectorQuantizerEMA(_HardQuantizerBase):
 FLAVOURS = {
     "dae": {"VQ_Payam": DAE_VQ_Payam, "VQ_Payam_EMA": DAE_VQ_Payam_EMA},
     "vqvae": {"VQ_Payam": VQVAE_VQ_Payam, "VQ_Payam_EMA": VQVAE_VQ_Payam_EMA,
-              "VectorQuantizerEMA": VectorQuantizerEMA},
+              "VectorQuantizerEMA": VectorQuantizerEMA, "VQ_Payam_GSSoft": VQVAE_VQ_Payam_GSSoft},
 }

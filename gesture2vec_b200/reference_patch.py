@@ -6,7 +6,7 @@ overwritten by the soft VQ_Payam_GSSoft) and inside ``VQ_Frame.__init__``
 (scripts/model/DAE_model.py:162-176).  Two hooks cover both:
 
   patch_reference()        rebinds model.Autoencoder_VQVAE_model.{VQ_Payam,VQ_Payam_EMA,
-                           VectorQuantizerEMA} and model.DAE_model.{VQ_Payam,VQ_Payam_EMA} to the
+                           VectorQuantizerEMA,VQ_Payam_GSSoft} and model.DAE_model.{VQ_Payam,VQ_Payam_EMA} to the
                            classes of gesture2vec_b200.quantizers, so every later construction
                            (train_autoencoder_VQVAE.init_model, utils/train_utils.load_checkpoint_and_model)
                            gets the CUDA-backed layer with identical state_dict keys.
@@ -66,7 +66,7 @@ def swap_vq_layer(net: torch.nn.Module, kind: str = "VQ_Payam_EMA", flavour: str
     beta = float(old._commitment_cost)
     cls = Q.FLAVOURS[flavour][kind]
     new = cls(K, D, beta, getattr(old, "_decay", decay), getattr(old, "_epsilon", 1e-5)) \
-        if kind != "VQ_Payam" else cls(K, D, beta)
+        if kind not in ("VQ_Payam", "VQ_Payam_GSSoft") else cls(K, D, beta)
     src = old.state_dict()
     dst = new.state_dict()
     for k, v in src.items():

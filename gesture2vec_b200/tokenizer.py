@@ -46,8 +46,8 @@ class GestureTokenizer:
         if getattr(codebook, "_projects", False) and hasattr(codebook, "_search_rows"):
             self._project = codebook._search_rows
         elif hasattr(codebook, "pre_lin") and hasattr(codebook, "_embedding"):
-            self._project = lambda rows, _m=codebook: torch.nn.functional.linear(
-                rows, _m.pre_lin.weight.detach(), _m.pre_lin.bias.detach()).contiguous()
+            from .functional import gemm
+            self._project = lambda rows, _m=codebook: gemm(rows, _m.pre_lin.weight.detach(), bias=_m.pre_lin.bias.detach())
         w = getattr(getattr(codebook, "_embedding", None), "weight", codebook)
         if isinstance(w, np.ndarray):
             w = torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32))

@@ -216,6 +216,27 @@ int g2v_gemm_f32(const float* A, int64_t lda, int transA, const float* B, int64_
                  int64_t K, const float* bias, float* C, int64_t ldc, float alpha, unsigned flags, void* ws,
                  size_t ws_bytes, void* stream);
 
+/* Row kernels of the soft quantizer VQ_Payam_GSSoft (Autoencoder_VQVAE_model.py:1304-1433), the layer
+ * Autoencoder_VQVAE.__init__ instantiates (:816-820).  Its dense products go through g2v_gemm_f32; these do the rest.
+ *
+ * g2v_soft_assign   soft_prob (:1349-1372) fused with the distance assembly (:1393-1397) and smooth (:1399):
+ *                   dot_d [N,K] holds m E^T on entry and d = (|m|^2 + |e|^2) - 2 m.e on exit; p [N,K] receives
+ *                   p~ / sum_k p~, p~ = exp(-(d / 400)(0.5 s)) / sqrt(s), s = 1 / exp(lv)^2; colsum [K] (caller
+ *                   zeroes) accumulates sum_n p for the perplexity.
+ * g2v_soft_tail     out = x + (q - x) (:1424); sse (double, caller zeroes) += sum (q - x)^2; then loss = mse +
+ *                   beta mse and perplexity = exp(-sum avg log(avg + 1e-10)), avg = colsum / N (:1418-1426).
+ * g2v_soft_backward closed-form backward of the soft assignment given dp = dL/dp [N,K]: gd = dL/dd, glv = dL/dlv
+ *                   [N,K], rowsum_gd [N], and the column sums col_gd / col_glv [K] (caller zeroes).
+ * g2v_soft_gx       gx = c[0] gmw + a[0] (x - q) + g_out over n elements (c, a device scalars; g_out optional). */
+int g2v_soft_assign(const float* m, float* dot_d, const float* lv, const float* e2, int64_t N, int K, int D, float* p,
+                    float* colsum, void* stream);
+int g2v_soft_tail(const float* x, const float* q, int64_t N, int K, int D, float beta, float* out, double* sse,
+                  const float* colsum, float* loss, float* perplexity, void* stream);
+int g2v_soft_backward(const float* p, const float* dp, const float* d, const float* lv, int64_t N, int K, float* gd,
+                      float* glv, float* rowsum_gd, float* col_gd, float* col_glv, void* stream);
+int g2v_soft_gx(const float* gmw, const float* x, const float* q, const float* g_out, const float* c, const float* a,
+                int64_t n, float* gx, void* stream);
+
 /* Verification aid, not a product path: the exact-arithmetic nearest code of EVERY row, all products and
  * sums in fp64 (no error bounds, candidate lists or operand rounding shared with g2v_vq_search), first index
  * on exact ties -- what torch.argmin over fp64 distances of DAE_model.py:320-327 would return.  FP64-bound

@@ -117,6 +117,7 @@ def main():
         keys[f"{flavour}.VQ_Payam"] = sorted(mod.VQ_Payam(8, 4, 0.25).state_dict().keys())
         keys[f"{flavour}.VQ_Payam_EMA"] = sorted(mod.VQ_Payam_EMA(8, 4, 0.25, 0.9).state_dict().keys())
     keys["vqvae.VectorQuantizerEMA"] = sorted(vqvae.VectorQuantizerEMA(8, 4, 0.25, 0.9).state_dict().keys())
+    keys["vqvae.VQ_Payam_GSSoft"] = sorted(vqvae.VQ_Payam_GSSoft(8, 4, 0.25).state_dict().keys())
     import json
     with open(os.path.join(HERE, "state_dict_keys.json"), "w") as f:
         json.dump(keys, f, indent=1, sort_keys=True)

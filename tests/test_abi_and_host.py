@@ -106,10 +106,10 @@ def test_modules_construct_with_reference_state_dict_keys():
     keys = json.load(open(os.path.join(HERE, "golden", "state_dict_keys.json")))
     for flavour, classes in g.FLAVOURS.items():
         for cname, cls in classes.items():
-            layer = cls(8, 4, 0.25) if cname == "VQ_Payam" else cls(8, 4, 0.25, 0.9)
+            layer = cls(8, 4, 0.25) if cname in ("VQ_Payam", "VQ_Payam_GSSoft") else cls(8, 4, 0.25, 0.9)
             assert sorted(layer.state_dict().keys()) == keys[f"{flavour}.{cname}"]
             assert layer._num_embeddings == 8 and layer._embedding_dim == 4 and layer._commitment_cost == 0.25
-            if cname != "VQ_Payam":
+            if cname not in ("VQ_Payam", "VQ_Payam_GSSoft"):
                 assert layer._decay == 0.9 and layer._epsilon == 1e-5
                 assert tuple(layer._ema_w.shape) == (8, 4) and tuple(layer._ema_cluster_size.shape) == (8,)
             layer.embedding_grad(False)

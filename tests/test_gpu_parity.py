@@ -206,7 +206,7 @@ def test_state_dict_contract_and_checkpoint_roundtrip():
     keys = json.load(open(os.path.join(HERE, "golden", "state_dict_keys.json")))
     for flavour, classes in g.FLAVOURS.items():
         for cname, cls in classes.items():
-            layer = cls(8, 4, 0.25) if cname == "VQ_Payam" else cls(8, 4, 0.25, 0.9)
+            layer = cls(8, 4, 0.25) if cname in ("VQ_Payam", "VQ_Payam_GSSoft") else cls(8, 4, 0.25, 0.9)
             assert sorted(layer.state_dict().keys()) == keys[f"{flavour}.{cname}"]
     a = g.VQVAE_VQ_Payam_EMA(32, 16, 0.25, 0.85).to(_dev())
     a.train()
