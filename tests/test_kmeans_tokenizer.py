@@ -65,9 +65,63 @@ def test_tokenize_oracle_matches_reference_loop():
     assert aud["hard"] == 0 and aud["mismatch"] == 0, aud
 
 
+def test_kmeans_plusplus_seeding_is_sklearns():
+    """The greedy k-means++ draw, row for row, against sklearn.cluster.kmeans_plusplus with the same RandomState
+    (torch ops on CPU tensors here; the same code runs on the device in KMeans.fit).  The scikit-learn in this
+    image is 1.3+ (first centre by `choice`); the reference's pinned 1.2.2 differs in that one draw (`randint`)."""
+    from sklearn.cluster import kmeans_plusplus as sk_pp
+    from gesture2vec_b200.kmeans import kmeans_plusplus
+    rng = np.random.default_rng(0)
+    for n, d, k in ((2000, 16, 12), (3000, 400, 20), (6000, 40, 64)):
+        X = (rng.standard_normal((n, d)) + rng.integers(0, 5, (n, 1))).astype(np.float32)
+        c_sk, idx_sk = sk_pp(X, k, random_state=np.random.RandomState(0))
+        c, idx = kmeans_plusplus(torch.from_numpy(X), k, np.random.RandomState(0), seeding="sklearn-1.3+")
+        assert np.array_equal(idx, idx_sk) and np.array_equal(c.numpy(), c_sk)
+        # the 1.2 stream: same algorithm, first draw by randint -- a valid, reproducible seeding
+        c2, idx2 = kmeans_plusplus(torch.from_numpy(X), k, np.random.RandomState(0), seeding="sklearn-1.2")
+        c3, idx3 = kmeans_plusplus(torch.from_numpy(X), k, np.random.RandomState(0), seeding="sklearn-1.2")
+        assert np.array_equal(idx2, idx3) and len(set(idx2.tolist())) == k and idx2[0] == np.random.RandomState(0).randint(n)
+
+
 # ---------------------------------------------------------------------------------------------
 # GPU
 # ---------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_kmeans_fit_as_the_reference_calls_it_matches_sklearn():
+    """Clustering.py:718 / train_DAE.py:257: KMeans(n_clusters, max_iter, random_state=0) -- k-means++ restarts from
+    one RandomState stream, best inertia wins.  Same seeds as the scikit-learn in this image -> the same fit."""
+    from sklearn.cluster import KMeans as SkKMeans
+    import gesture2vec_b200 as g2v
+    X, _ = KO.synth_blobs(6000, 40, 24, seed=11)
+    sk = SkKMeans(n_clusters=24, n_init=4, max_iter=100, random_state=0, algorithm="lloyd").fit(X)
+    km = g2v.KMeans(n_clusters=24, n_init=4, max_iter=100, random_state=0, seeding="sklearn-1.3+").fit(X)
+    np.testing.assert_allclose(km.inertia_, sk.inertia_, rtol=1e-4)
+    assert float((km.labels_ == sk.labels_).mean()) > 0.999
+    np.testing.assert_allclose(km.cluster_centers_, sk.cluster_centers_, rtol=1e-3, atol=1e-3)
+    # the lagged, sync-free convergence mode reaches the same fit
+    km2 = g2v.KMeans(n_clusters=24, n_init=4, max_iter=100, random_state=0, seeding="sklearn-1.3+",
+                     relocate_empty=False).fit(X)
+    np.testing.assert_allclose(km2.inertia_, km.inertia_, rtol=1e-5)
+    assert km2.n_iter_ == km.n_iter_ and np.array_equal(km2.labels_, km.labels_)
+
+
+@pytest.mark.gpu
+def test_kmeans_relocates_empty_clusters():
+    """A centre no row is assigned to is moved onto the row farthest from its centre (sklearn's
+    _relocate_empty_clusters_dense), instead of staying empty for ever."""
+    from sklearn.cluster import KMeans as SkKMeans
+    import gesture2vec_b200 as g2v
+    X, init = KO.synth_blobs(3000, 16, 8, seed=3)
+    init = init.copy()
+    init[5] = 1e3                                   # far from every row: empty after the first assignment
+    km = g2v.KMeans(n_clusters=8, init=init, max_iter=50).fit(X)
+    assert np.bincount(km.labels_, minlength=8).min() > 0
+    sk = SkKMeans(n_clusters=8, init=init, n_init=1, max_iter=50, algorithm="lloyd").fit(X)
+    np.testing.assert_allclose(km.inertia_, sk.inertia_, rtol=0.05)     # which far row is taken may differ
+    stay = g2v.KMeans(n_clusters=8, init=init, max_iter=50, relocate_empty=False).fit(X)
+    assert np.bincount(stay.labels_, minlength=8).min() == 0 and stay.inertia_ > km.inertia_
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", list(KM_CASES))
 def test_kmeans_fit_matches_sklearn_golden(name):
