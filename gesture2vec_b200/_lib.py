@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get("G2V_LIB_PATH") or os.path.join(HERE, "csrc", "libg2v_
 F32, BF16, F16 = 0, 1, 2
 ALGO_AUTO, ALGO_SIMT, ALGO_TC, NO_RECHECK = 0, 1, 2, 4
 GEMM_ACCUMULATE, GEMM_FP16 = 1, 2
+DET_CHUNK = 128                    # G2V_DET_CHUNK
 TC_VARIANT_TMEM, TC_VARIANT_FUSED, TC_VARIANT_PREP, TC_VARIANT_PAIR = 1 << 8, 2 << 8, 3 << 8, 4 << 8
 STAT_ROWS, STAT_PAIR_RECHECK, STAT_FULL_RECHECK, STAT_FALLBACK_ROWS = 0, 1, 2, 3
 
@@ -35,6 +36,7 @@ SIGNATURES = {
     "g2v_workspace_bytes": (_sz, [_i64, _i, _i, _i, _u]),
     "g2v_vq_search": (_i, [_p, _i, _p, _p, _i64, _i, _i, _p, _p, _p, _sz, _u, _p]),
     "g2v_vq_apply": (_i, [_p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _i, _p]),
+    "g2v_vq_stats_deterministic": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _p]),
     "g2v_vq_stats_pack": (_i, [_p, _p, _p, _i, _i64, _i, _i, _p, _p]),
     "g2v_vq_stats_finalize": (_i, [_p, _i, _i, _f, _f, _p, _p, _p]),
     "g2v_vq_ema_update": (_i, [_p, _p, _p, _p, _p, _p, _p, _f, _f, _i, _i, _p, _sz, _p]),

@@ -19,6 +19,7 @@ void set_error_detail(const char* fmt, ...) {
 }
 
 int cuda_fail(cudaError_t e, const char* what) {
+  (void)cudaGetLastError();      // a failed launch / call must not stay pending for the caller's next CUDA call
   set_error_detail("%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
   return G2V_ERR_CUDA;
 }
@@ -160,6 +161,16 @@ int g2v_vq_apply(const float* x, const float* zs, const float* E, const int32_t*
   int rc = check_arch();
   if (rc) return rc;
   return launch_apply(x, zs, E, idx, N, K, D, out, sse, counts, dwr, dwr_replicas, (cudaStream_t)stream);
+}
+
+int g2v_vq_stats_deterministic(const float* x, const float* zs, const float* E, const int32_t* order,
+                                const int64_t* seg, const int64_t* chunk_off, int64_t max_chunks, int K, int D,
+                                double* partial, float* dwr, double* sse_code, double* sse, void* stream) {
+  if (K <= 0 || D <= 0 || max_chunks < 0 || !x || !E || !order || !seg || !chunk_off || !partial || !dwr || !sse_code || !sse)
+    return G2V_ERR_INVALID;
+  return launch_stats_deterministic(x, zs, E, order, reinterpret_cast<const long long*>(seg),
+                                    reinterpret_cast<const long long*>(chunk_off), max_chunks, K, D, partial, dwr, sse_code,
+                                    sse, (cudaStream_t)stream);
 }
 
 int g2v_vq_stats_pack(const int32_t* counts, const double* sse, const float* dwr, int dwr_replicas, int64_t N,

@@ -15,6 +15,8 @@
 
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include <float.h>
 #include <math.h>
 
@@ -618,6 +620,80 @@ __global__ void __launch_bounds__(APPLY_WARPS * 32) apply_runs_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// deterministic statistics: no atomics, fixed summation order, fp64 accumulation
+// ------------------------------------------------------------------------------------------
+// The fast row pass accumulates the per-code residual sums with fp32 reductions whose order depends on
+// scheduling, so two runs of the same step agree to a few ulp, not bitwise.  This pair of kernels computes the
+// same statistics reproducibly: the rows come sorted by code (`order`: stable sort, ties by row index; `seg`:
+// first position of every code), each code's segment is cut into chunks of DET_CHUNK consecutive positions,
+// one block sums a chunk's rows one after the other in fp64 (threads = columns; the last column slot is the
+// chunk's sum of squared errors), and a second kernel adds every code's chunk partials in ascending order and
+// rounds once to fp32.
+constexpr int DET_CHUNK = 128;
+
+__global__ void __launch_bounds__(256) det_partial_kernel(const float* __restrict__ x, const float* __restrict__ zs,
+                                                          const float* __restrict__ E, const int* __restrict__ order,
+                                                          const long long* __restrict__ seg,
+                                                          const long long* __restrict__ chunk_off, int K, int D,
+                                                          double* __restrict__ partial) {
+  __shared__ double red[8];
+  const long long total = chunk_off[K];
+  for (long long b = blockIdx.x; b < total; b += gridDim.x) {
+    int lo = 0, hi = K;                                    // the code whose chunk range contains b
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (chunk_off[mid] <= b) lo = mid; else hi = mid;
+    }
+    const int k = lo;
+    const long long p0 = seg[k] + (b - chunk_off[k]) * DET_CHUNK, p1 = min(seg[k + 1], p0 + DET_CHUNK);
+    const float* er = E + (size_t)k * D;
+    double sq = 0.0;
+    for (int j = threadIdx.x; j < D; j += blockDim.x) {
+      const float ev = er[j];
+      double acc = 0.0;
+      for (long long p = p0; p < p1; ++p) {
+        const size_t r = (size_t)order[p] * D + j;
+        const float xv = x[r];
+        acc += (double)((zs ? zs[r] : xv) - ev);
+        const double dd = (double)(ev - xv);
+        sq += dd * dd;
+      }
+      partial[(size_t)b * (D + 1) + j] = acc;
+    }
+    // the chunk's squared error: per-thread sums combined in a fixed order
+    sq = warp_sum(sq);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += red[w];
+      partial[(size_t)b * (D + 1) + D] = t;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) det_reduce_kernel(const double* __restrict__ partial,
+                                                         const long long* __restrict__ chunk_off, int K, int D,
+                                                         float* __restrict__ dwr, double* __restrict__ sse_code) {
+  for (int k = blockIdx.x; k < K; k += gridDim.x) {
+    const long long c0 = chunk_off[k], c1 = chunk_off[k + 1];
+    for (int j = threadIdx.x; j <= D; j += blockDim.x) {
+      double acc = 0.0;
+      for (long long c = c0; c < c1; ++c) acc += partial[(size_t)c * (D + 1) + j];
+      if (j < D) dwr[(size_t)k * D + j] = (float)acc;
+      else sse_code[k] = acc;
+    }
+  }
+}
+
+__global__ void det_sse_kernel(const double* __restrict__ sse_code, int K, double* sse) {
+  double t = 0.0;
+  for (int k = 0; k < K; ++k) t += sse_code[k];            // ascending code order, one thread
+  *sse = t;
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(256) backward_kernel(const float* __restrict__ x, const float* __restrict__ E,
                                                        const int* __restrict__ idx,
@@ -892,6 +968,20 @@ int launch_apply(const float* x, const float* zs, const float* E, const int32_t*
   else
     apply_kernel<false><<<grid, APPLY_WARPS * 32, smem, st>>>(x, zs, E, idx, N, K, D, out, sse, counts, dwr, dwr_replicas, use_hist);
   G2V_LAUNCH_CHECK("apply_kernel");
+  return G2V_OK;
+}
+
+int launch_stats_deterministic(const float* x, const float* zs, const float* E, const int32_t* order, const long long* seg,
+                               const long long* chunk_off, int64_t max_chunks, int K, int D, double* partial, float* dwr,
+                               double* sse_code, double* sse, cudaStream_t st) {
+  const long long cap = (long long)num_sms() * 16;
+  const int g1 = (int)std::max<long long>(1, std::min<long long>(max_chunks, cap));
+  det_partial_kernel<<<g1, 256, 0, st>>>(x, zs, E, order, seg, chunk_off, K, D, partial);
+  G2V_LAUNCH_CHECK("det_partial_kernel");
+  det_reduce_kernel<<<std::min(K, num_sms() * 8), 256, 0, st>>>(partial, chunk_off, K, D, dwr, sse_code);
+  G2V_LAUNCH_CHECK("det_reduce_kernel");
+  det_sse_kernel<<<1, 1, 0, st>>>(sse_code, K, sse);
+  G2V_LAUNCH_CHECK("det_sse_kernel");
   return G2V_OK;
 }
 

@@ -7,6 +7,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 namespace g2v {
 namespace {
 
@@ -277,13 +279,18 @@ int make_map(CUtensorMap* tm, const void* gptr, uint64_t rows, uint64_t cols, ui
   return G2V_OK;
 }
 
-// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device, size): the attribute sticks
-int set_dyn_smem(const void* func, size_t bytes) {
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) only when a launch needs MORE than what the kernel already has on
+// that device.  The attribute belongs to the function (all host threads share it) and a call SETS it, it does not
+// raise it: the table is therefore process-wide and keeps the maximum -- a per-thread table would let a small launch
+// from one thread (e.g. the autograd engine's) lower the limit under a large launch from another.
+inline int set_dyn_smem(const void* func, size_t bytes) {
   struct Ent { const void* f; int dev; size_t bytes; };
-  static thread_local Ent ent[16];
-  static thread_local int n = 0;
+  static Ent ent[32];
+  static int n = 0;
+  static std::mutex mu;
   int dev = 0;
   G2V_CUDA_CHECK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
   for (int i = 0; i < n; ++i)
     if (ent[i].f == func && ent[i].dev == dev) {
       if (ent[i].bytes >= bytes) return G2V_OK;
@@ -292,10 +299,9 @@ int set_dyn_smem(const void* func, size_t bytes) {
       return G2V_OK;
     }
   G2V_CUDA_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  if (n < 16) ent[n++] = Ent{func, dev, bytes};
+  if (n < 32) ent[n++] = Ent{func, dev, bytes};
   return G2V_OK;
 }
-
 
 }  // namespace
 }  // namespace g2v

@@ -189,15 +189,45 @@ def packed_numel(K: int, D: int) -> int:
     return K * D + K + 2
 
 
-def _apply_rows(x, zs, E, idx, out, acc: Optional[_Accum], want_dwr: bool) -> None:
-    """g2v_vq_apply: out = x + (E[idx]-x) and, if `acc`, SSE / counts (/ residual sums) into the accumulators."""
+def _apply_rows(x, zs, E, idx, out, acc: Optional[_Accum], want_dwr: bool, deterministic: bool = False) -> None:
+    """g2v_vq_apply: out = x + (E[idx]-x) and, if `acc`, SSE / counts (/ residual sums) into the accumulators.
+    deterministic: the statistics come from the atomics-free fixed-order pass instead (acc must hold ONE dwr copy)."""
     N, D = x.shape
     K = E.shape[0]
+    if deterministic and acc is not None:
+        assert acc.reps == 1, "deterministic statistics use a single accumulator copy"
+        _deterministic_stats(x, zs, E, idx, acc)
+        if out is not None:
+            _lib.check(_lib.load().g2v_vq_apply(_ptr(x), None, _ptr(E), _ptr(idx), N, K, D, _ptr(out), None, None, None, 0,
+                                                _stream(x.device)), "g2v_vq_apply")
+        return
     dwr = acc.dwr if (acc is not None and want_dwr) else None
     _lib.check(_lib.load().g2v_vq_apply(
         _ptr(x), _ptr(zs), _ptr(E), _ptr(idx), N, K, D, _ptr(out),
         _ptr(acc.sse) if acc is not None else None, _ptr(acc.counts) if acc is not None else None,
         _ptr(dwr), acc.reps if dwr is not None else 0, _stream(x.device)), "g2v_vq_apply")
+
+
+def _deterministic_stats(x, zs, E, idx, acc: _Accum) -> None:
+    """Fill the accumulators reproducibly (g2v_vq_stats_deterministic): rows sorted by code with a stable sort
+    (plumbing: torch.sort / bincount / cumsum), then fixed-order fp64 chunk sums -- no atomics anywhere."""
+    N, D = x.shape
+    K = E.shape[0]
+    dev = x.device
+    idx64 = idx.long()
+    order = torch.sort(idx64, stable=True).indices.to(torch.int32)
+    counts = torch.bincount(idx64, minlength=K)
+    seg = torch.zeros(K + 1, dtype=torch.int64, device=dev)
+    seg[1:] = torch.cumsum(counts, 0)
+    chunk_off = torch.zeros(K + 1, dtype=torch.int64, device=dev)
+    chunk_off[1:] = torch.cumsum((counts + (_lib.DET_CHUNK - 1)) // _lib.DET_CHUNK, 0)
+    max_chunks = N // _lib.DET_CHUNK + K
+    partial = torch.empty(max_chunks * (D + 1), dtype=torch.float64, device=dev)
+    sse_code = torch.empty(K, dtype=torch.float64, device=dev)
+    _lib.check(_lib.load().g2v_vq_stats_deterministic(
+        _ptr(x), _ptr(zs), _ptr(E), _ptr(order), _ptr(seg), _ptr(chunk_off), max_chunks, K, D, _ptr(partial),
+        _ptr(acc.dwr), _ptr(sse_code), _ptr(acc.sse), _stream(dev)), "g2v_vq_stats_deterministic")
+    acc.counts.copy_(counts)
 
 
 def step_finalize(K: int, D: int, packed: torch.Tensor, *, acc: Optional[_Accum] = None, use_dwr: bool = True,
@@ -228,17 +258,20 @@ def step_finalize(K: int, D: int, packed: torch.Tensor, *, acc: Optional[_Accum]
 
 
 def vq_apply(x: torch.Tensor, E: torch.Tensor, idx: torch.Tensor, *, zs: Optional[torch.Tensor] = None,
-             want_out: bool = True, want_stats: bool = True, want_dwr: bool = False
+             want_out: bool = True, want_stats: bool = True, want_dwr: bool = False, deterministic: bool = False
              ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """One pass over the rows: out = x + (E[idx]-x) and, if asked, the packed statistics buffer
-    [dwr (K*D) | counts (K) | sse | rows] (fp32, ready for an all-reduce)."""
+    [dwr (K*D) | counts (K) | sse | rows] (fp32, ready for an all-reduce).  deterministic=True: bit-reproducible
+    statistics (sorted, fixed-order fp64 sums instead of fp32 atomics)."""
     N, D = x.shape
     K = E.shape[0]
     dev = x.device
     with _on(dev):
         out = torch.empty_like(x) if want_out else None
-        acc = _accum(dev, K, D, dwr_replicas(N, K, D) if want_dwr else 0) if want_stats else None
-        _apply_rows(x, zs, E, idx, out, acc, want_dwr)
+        det = deterministic and want_stats and N > 0
+        acc = _accum(dev, K, D, 1 if det else (dwr_replicas(N, K, D) if want_dwr else 0)) if want_stats else None
+        _apply_rows(x, zs, E, idx, out, acc, want_dwr or det, det)
+        want_dwr = want_dwr or det
         packed = None
         if want_stats:
             packed = torch.empty(packed_numel(K, D), dtype=torch.float32, device=dev)
@@ -357,7 +390,7 @@ class _QuantizeFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x2d, E, zs, cb, beta, coef_codebook, want_dwr, reduce_fn, grad_scale, flags, ema, idx_given):
+    def forward(ctx, x2d, E, zs, cb, beta, coef_codebook, want_dwr, reduce_fn, grad_scale, flags, ema, idx_given, det):
         dev = x2d.device
         N, D = x2d.shape
         K = E.shape[0]
@@ -369,8 +402,9 @@ class _QuantizeFn(torch.autograd.Function):
                 packed.zero_()
                 acc = None
             else:
-                acc = _accum(dev, K, D, dwr_replicas(N, K, D) if want_dwr else 0)
-                _apply_rows(x2d, zs, E, idx, out, acc, want_dwr)
+                want_dwr = want_dwr or det
+                acc = _accum(dev, K, D, 1 if det else (dwr_replicas(N, K, D) if want_dwr else 0))
+                _apply_rows(x2d, zs, E, idx, out, acc, want_dwr, det)
             kw = dict(coefs=(coef_codebook, beta), res=torch.empty(2, dtype=torch.float32, device=dev))
             E_bwd = E
             if ema is not None:
@@ -434,20 +468,20 @@ class _QuantizeFn(torch.autograd.Function):
                 _lib.check(lib.g2v_vq_grad_codebook(_ptr(packed), _ptr(g_loss),
                                                     2.0 * ctx.coef_codebook * ctx.grad_scale / M if M else 0.0,
                                                     K, D, _ptr(gE), st), "g2v_vq_grad_codebook")
-        return gx, gE, None, None, None, None, None, None, None, None, None, None
+        return gx, gE, None, None, None, None, None, None, None, None, None, None, None
 
 
 def quantize(x2d, E, *, zs=None, cb=None, beta=0.25, coef_codebook=1.0, want_dwr=False,
              reduce_fn=None, grad_scale=1.0, flags=_lib.ALGO_AUTO, ema: Optional[EmaState] = None,
-             idx: Optional[torch.Tensor] = None):
-    """The whole layer on [N, D] rows.  `idx`: int32 code ids to use instead of searching (rows tokenised
+             idx: Optional[torch.Tensor] = None, deterministic: bool = False):
+    """The whole layer on [N, D] rows.  deterministic: bit-reproducible statistics (see vq_apply).  `idx`: int32 code ids to use instead of searching (rows tokenised
     earlier; also how the parity tests evaluate the downstream arithmetic at the reference's indices)."""
     if idx is not None:
         idx = idx.to(device=x2d.device, dtype=torch.int32).contiguous()
         if idx.numel() != x2d.shape[0]:
             raise RuntimeError("one code id per row expected")
     return _QuantizeFn.apply(x2d, E, zs, cb, float(beta), float(coef_codebook), bool(want_dwr),
-                             reduce_fn, float(grad_scale), int(flags), ema, idx)
+                             reduce_fn, float(grad_scale), int(flags), ema, idx, bool(deterministic))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -51,6 +51,9 @@ class _HardQuantizerBase(nn.Module):
         # EMA state updated in place (fixed addresses: a captured CUDA graph of the training step advances the
         # state on every replay).  The backward pass then reads the old codebook from a private copy, so at most
         # one forward may be pending its backward.  Default: fresh tensors per step, like the reference.
+        # bit-reproducible statistics (EMA sums, codebook gradient, loss): sorted fixed-order fp64 sums instead of
+        # fp32 atomics -- the same bits from run to run, at the cost of a sort and a second pass over the rows
+        self.deterministic: bool = False
         self.ema_inplace: bool = False
         self._E_prev: Optional[torch.Tensor] = None
 
@@ -121,7 +124,8 @@ class _HardQuantizerBase(nn.Module):
             loss, out, ppl, idx, packed = F.quantize(
                 flat, E_arg, zs=zs, cb=cb, beta=self._commitment_cost,
                 coef_codebook=0.0 if self._ema else 1.0, want_dwr=want_dwr, reduce_fn=reduce_fn,
-                grad_scale=self.grad_scale, flags=self.search_flags, ema=ema, idx=indices)
+                grad_scale=self.grad_scale, flags=self.search_flags, ema=ema, idx=indices,
+                deterministic=self.deterministic)
             self.last_indices = idx
             quantized = out.view(inputs.shape)
             enc = F.one_hot(idx, self._num_embeddings) if self.return_encodings else idx.long().unsqueeze(1)

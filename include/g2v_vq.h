@@ -125,6 +125,17 @@ int g2v_vq_apply(const float* x, const float* zs, const float* E, const int32_t*
                  int64_t N, int K, int D, float* out, double* sse, int32_t* counts,
                  float* dwr, int dwr_replicas, void* stream);
 
+/* Reproducible statistics (SURVEY.md 7 "Atomics determinism"): the residual sums dwr [K,D] and the squared error
+ * of g2v_vq_apply WITHOUT atomics -- rows sorted by code (order: stable, ties by row index; seg [K+1]: first
+ * position of each code; chunk_off [K+1]: prefix sum of ceil(count_k / G2V_DET_CHUNK)), every chunk of
+ * consecutive positions summed row after row in fp64, every code's chunks added in ascending order, one rounding to
+ * fp32.  Bit-identical from run to run; ~1e-7 relative to the exact sums.  partial: double [max_chunks, D+1]
+ * scratch, max_chunks >= chunk_off[K] (N / G2V_DET_CHUNK + K always suffices); sse_code: double [K] scratch. */
+#define G2V_DET_CHUNK 128
+int g2v_vq_stats_deterministic(const float* x, const float* zs, const float* E, const int32_t* order,
+                                const int64_t* seg, const int64_t* chunk_off, int64_t max_chunks, int K, int D,
+                                double* partial, float* dwr, double* sse_code, double* sse, void* stream);
+
 /* Pack the per-step statistics into ONE fp32 buffer for the data-parallel all-reduce:
  * packed = [ dwr (K*D) | counts (K) | sse (1) | rows (1) ], K*D+K+2 floats.  The dwr_replicas
  * copies written by g2v_vq_apply are summed into packed[0 .. K*D) (dwr may be NULL: zeros). */

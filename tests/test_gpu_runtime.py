@@ -142,3 +142,36 @@ def test_tokenizers_apply_the_projection_of_the_vqvae_flavour():
     # and the raw codebook (no projection) differs, which is what the old tokenizer silently returned
     raw = g.tokenize(x, layer._embedding.weight.detach()).long()
     assert not torch.equal(raw, want)
+
+
+def test_deterministic_statistics_are_bit_reproducible_and_tight():
+    """layer.deterministic = True: atomics-free, fixed-order fp64 sums -- two runs give the same bits (the default
+    fp32-atomics pass does not promise that), and the sums are within 1e-6 of fp64 (default pass: 1e-4)."""
+    import gesture2vec_b200 as g
+    K, D, N = 400, 400, 200_000
+    E = torch.randn(K, D, device=DEV, generator=torch.Generator(device=DEV).manual_seed(0))
+    w = 1.0 / torch.arange(1, K + 1, device=DEV, dtype=torch.float64) ** 1.1
+    code = torch.multinomial(w / w.sum(), N, replacement=True, generator=torch.Generator(device=DEV).manual_seed(1))
+    z = (E[code] + 0.1 * torch.randn(N, D, device=DEV, generator=torch.Generator(device=DEV).manual_seed(2))).contiguous()
+    idx = g.tokenize(z, E)
+    runs = [g.vq_apply(z, E, idx, want_out=True, want_stats=True, want_dwr=True, deterministic=True) for _ in range(3)]
+    for out, packed in runs[1:]:
+        assert torch.equal(packed, runs[0][1]) and torch.equal(out, runs[0][0])
+    packed = runs[0][1]
+    lay = g.packed_layout(K, D)
+    counts = packed[lay["counts"][0]:lay["counts"][1]]
+    assert torch.equal(counts.long(), torch.bincount(idx.long(), minlength=K))
+    ref = torch.zeros(K, D, device=DEV, dtype=torch.float64).index_add_(0, idx.long(), z.double() - E.double()[idx.long()])
+    got = packed[:K * D].view(K, D).double()
+    scale = ref.abs().amax(dim=1, keepdim=True).clamp_min(1e-12)
+    assert float(((got - ref).abs() / scale).max()) < 1e-6
+    sse = ((E[idx.long()] - z).double() ** 2).sum()
+    assert abs(float(packed[lay["sse"]]) - float(sse)) <= 1e-6 * float(sse)
+    # through the module: two identically initialised layers stay bit-identical over EMA steps
+    a, b = _layer(g, DEV, 512, 400), _layer(g, DEV, 512, 400)
+    a.deterministic = b.deterministic = True
+    for s in range(3):
+        x = torch.from_numpy(O.synth_latents("gru", 4096, 400, seed=30 + s)).to(DEV)
+        ra, rb = a(x), b(x)
+        assert all(torch.equal(u, v) for u, v in zip(ra, rb))
+        assert all(torch.equal(u, v) for u, v in zip(_state(a), _state(b)))
