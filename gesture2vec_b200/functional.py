@@ -390,7 +390,8 @@ class _QuantizeFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x2d, E, zs, cb, beta, coef_codebook, want_dwr, reduce_fn, grad_scale, flags, ema, idx_given, det):
+    def forward(ctx, x2d, E, zs, cb, beta, coef_codebook, want_dwr, reduce_fn, grad_scale, flags, ema, idx_given, det,
+                dw_transform):
         dev = x2d.device
         N, D = x2d.shape
         K = E.shape[0]
@@ -416,8 +417,25 @@ class _QuantizeFn(torch.autograd.Function):
                     ema.E_new = torch.empty_like(E)
                 kw.update(update=UPDATE_EMA, cs_in=ema.cs_in, cs_out=ema.cs_out, w_in=ema.w_in, w_out=ema.w_out,
                           E_old=E, E_new=ema.E_new, E_prev=ema.E_prev, decay=ema.decay, eps=ema.eps, cb=cb)
-            if reduce_fn is None:
+            def project_sums():
+                # the EMA sums are taken over pre_linear(x): sum_n (W x_n + b) = W (sum_n x_n) + count b, from the
+                # raw residual sums of the row pass; K x D x D work on g2v_gemm_f32 instead of N x D x D
+                if dw_transform is None:
+                    return
+                Wp, bp = dw_transform
+                KD = K * D
+                cnt = packed[KD:KD + K].unsqueeze(1)
+                dwr = packed[:KD].view(K, D)
+                S = torch.addcmul(dwr, cnt, E)                            # raw sums of the rows of each code
+                dwp = gemm(S, Wp).addcmul_(cnt, bp.unsqueeze(0))          # sums of the projected rows
+                dwr.copy_(dwp.addcmul_(cnt, E, value=-1.0))               # back to the residual form the finalise takes
+
+            if reduce_fn is None and dw_transform is None:
                 res = step_finalize(K, D, packed, acc=acc, use_dwr=want_dwr, rows_local=N, **kw)
+            elif reduce_fn is None:
+                step_finalize(K, D, packed, acc=acc, use_dwr=want_dwr, rows_local=N)
+                project_sums()
+                res = step_finalize(K, D, packed, **kw)
             else:
                 # data-parallel: pack, ONE sum all-reduce of the packed statistics, then the identical finalise
                 # on every rank.  With a side stream (StatsAllReduce(overlap=True)) the exchange and the
@@ -426,12 +444,14 @@ class _QuantizeFn(torch.autograd.Function):
                 side = getattr(reduce_fn, "stream", None)
                 if side is None or ema is None:
                     reduce_fn(packed)
+                    project_sums()
                     res = step_finalize(K, D, packed, **kw)
                 else:
                     main = torch.cuda.current_stream(dev)
                     side.wait_stream(main)
                     with torch.cuda.stream(side):
                         reduce_fn(packed)
+                        project_sums()
                         res = step_finalize(K, D, packed, **kw)
                         ema.pending = torch.cuda.Event()
                         ema.pending.record(side)
@@ -468,12 +488,12 @@ class _QuantizeFn(torch.autograd.Function):
                 _lib.check(lib.g2v_vq_grad_codebook(_ptr(packed), _ptr(g_loss),
                                                     2.0 * ctx.coef_codebook * ctx.grad_scale / M if M else 0.0,
                                                     K, D, _ptr(gE), st), "g2v_vq_grad_codebook")
-        return gx, gE, None, None, None, None, None, None, None, None, None, None, None
+        return gx, gE, None, None, None, None, None, None, None, None, None, None, None, None
 
 
 def quantize(x2d, E, *, zs=None, cb=None, beta=0.25, coef_codebook=1.0, want_dwr=False,
              reduce_fn=None, grad_scale=1.0, flags=_lib.ALGO_AUTO, ema: Optional[EmaState] = None,
-             idx: Optional[torch.Tensor] = None, deterministic: bool = False):
+             idx: Optional[torch.Tensor] = None, deterministic: bool = False, dw_transform=None):
     """The whole layer on [N, D] rows.  deterministic: bit-reproducible statistics (see vq_apply).  `idx`: int32 code ids to use instead of searching (rows tokenised
     earlier; also how the parity tests evaluate the downstream arithmetic at the reference's indices)."""
     if idx is not None:
@@ -481,7 +501,7 @@ def quantize(x2d, E, *, zs=None, cb=None, beta=0.25, coef_codebook=1.0, want_dwr
         if idx.numel() != x2d.shape[0]:
             raise RuntimeError("one code id per row expected")
     return _QuantizeFn.apply(x2d, E, zs, cb, float(beta), float(coef_codebook), bool(want_dwr),
-                             reduce_fn, float(grad_scale), int(flags), ema, idx, bool(deterministic))
+                             reduce_fn, float(grad_scale), int(flags), ema, idx, bool(deterministic), dw_transform)
 
 
 # ------------------------------------------------------------------------------------------------

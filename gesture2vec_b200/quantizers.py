@@ -88,6 +88,10 @@ class _HardQuantizerBase(nn.Module):
         """Rows the search (and the EMA sums) run on, if different from the raw rows."""
         return None
 
+    def _fold(self, dev: torch.device):
+        """(E_fold, cb_fold, W_proj, b_proj) when the flavour's projection is folded into the codebook, else None."""
+        return None
+
     def _run(self, inputs: torch.Tensor, indices: Optional[torch.Tensor] = None):
         if inputs.numel() % self._embedding_dim:
             raise RuntimeError(
@@ -105,8 +109,18 @@ class _HardQuantizerBase(nn.Module):
         flat = inputs.contiguous().view(-1, self._embedding_dim)          # a1: inputs.view(-1, D)
         with F._on(flat.device):
             W, cb = self._codebook(flat.device)
+            fold = self._fold(flat.device)
+            zs, dw_transform = None, None
             with torch.no_grad():
-                zs = self._search_rows(flat.detach())
+                if fold is None:
+                    zs = self._search_rows(flat.detach())
+                else:
+                    # the projection lives in the codebook: search the RAW rows (zero-extended to the folded width)
+                    E_fold, cb_fold, Wp, bp = fold
+                    dw_transform = (Wp, bp)
+                    if indices is None:
+                        indices = F.vq_search(torch.nn.functional.pad(flat.detach(), (0, E_fold.shape[1] - flat.shape[1])),
+                                              E_fold, cb_fold, flags=self.search_flags)
             training_ema = self._ema and self.training
             want_dwr = training_ema or (not self._ema and W.requires_grad and torch.is_grad_enabled())
             reduce_fn = self.stats_reduce if training_ema else None
@@ -125,7 +139,7 @@ class _HardQuantizerBase(nn.Module):
                 flat, E_arg, zs=zs, cb=cb, beta=self._commitment_cost,
                 coef_codebook=0.0 if self._ema else 1.0, want_dwr=want_dwr, reduce_fn=reduce_fn,
                 grad_scale=self.grad_scale, flags=self.search_flags, ema=ema, idx=indices,
-                deterministic=self.deterministic)
+                deterministic=self.deterministic, dw_transform=dw_transform if training_ema else None)
             self.last_indices = idx
             quantized = out.view(inputs.shape)
             enc = F.one_hot(idx, self._num_embeddings) if self.return_encodings else idx.long().unsqueeze(1)
@@ -151,7 +165,12 @@ class _HardQuantizerBase(nn.Module):
         flat = inputs.contiguous().view(-1, self._embedding_dim)
         with F._on(flat.device):
             W, cb = self._codebook(flat.device)
+            fold = self._fold(flat.device)
             with torch.no_grad():
+                if fold is not None:
+                    E_fold, cb_fold, _, _ = fold
+                    return F.vq_search(torch.nn.functional.pad(flat.float(), (0, E_fold.shape[1] - flat.shape[1])),
+                                       E_fold, cb_fold, flags=self.search_flags)
                 zs = self._search_rows(flat.float() if self._projects else flat)
             return F.vq_search(flat if zs is None else zs, W.detach(), cb, flags=self.search_flags)
 
@@ -230,6 +249,39 @@ class VQVAE_VQ_Payam_EMA(_HardQuantizerBase):
         self._epsilon = epsilon
 
     _projects = True
+    #: fold pre_linear into the codebook (see _fold); False: project every row with g2v_gemm_f32 first
+    fold_projection: bool = True
+    _FOLD_PAD = 4           # extra codebook columns: the offset term + zeros up to a 16-byte row pitch
+
+    def _fold(self, dev: torch.device):
+        """pre_linear is linear, so  argmin_k |W z + b - e_k|^2 = argmin_k ( c_k - 2 z . (W^T e_k) ),
+        c_k = |e_k|^2 - 2 b.e_k  (|W z + b|^2 is constant over k).  With e'_k = W^T e_k and one extra coordinate
+        t_k = sqrt(c_k + C - |e'_k|^2)  (C >= 0 makes every radicand non-negative; a constant shift of all
+        distances) the folded code  e~_k = [e'_k, t_k, 0, 0, 0]  satisfies  |[z,0] - e~_k|^2 = |z|^2 + c_k + C - 2 z.e'_k,
+        i.e. the SAME argmin from the RAW rows against a [K, D+4] codebook: no N x D x D projection, no projected
+        copy of the rows.  The fold is K x D x D work (fp64, rounded once to fp32) whenever E, W or b change; the
+        exact search then returns the exact argmin for that fp32 codebook, ~1e-4 absolute in the distances away
+        from the reference's own fp32 chain -- far inside the near-tie tolerance.  The EMA sums over the projected
+        rows follow from the raw sums: sum_n (W x_n + b) = W (sum_n x_n) + count b (functional.quantize)."""
+        if not self.fold_projection:
+            return None
+        Wemb, Wp, bp = self._embedding.weight, self.pre_linear.weight, self.pre_linear.bias
+        key = (Wemb.data_ptr(), Wemb._version, Wp.data_ptr(), Wp._version, bp.data_ptr(), bp._version, str(dev))
+        if getattr(self, "_fold_key", None) != key:
+            with torch.no_grad():
+                E64, W64, b64 = Wemb.detach().double(), Wp.detach().double(), bp.detach().double()
+                K, D = E64.shape
+                ef = (E64 @ W64).float()                                       # rows W^T e_k
+                c = (E64 * E64).sum(1) - 2.0 * (E64 @ b64)
+                g = c - (ef.double() ** 2).sum(1)
+                C = torch.clamp(-g.min(), min=0.0)
+                E_fold = torch.zeros(K, D + self._FOLD_PAD, dtype=torch.float32, device=dev)
+                E_fold[:, :D] = ef
+                E_fold[:, D] = torch.sqrt(g + C).float()
+                self._fold_E = E_fold
+                self._fold_cb = F.prepare_codebook(E_fold, getattr(self, "_fold_cb", None))
+                self._fold_key = key
+        return self._fold_E, self._fold_cb, Wp.detach(), bp.detach()
 
     def _search_rows(self, flat: torch.Tensor) -> Optional[torch.Tensor]:
         # pre_linear on the tensor cores at fp32 accuracy (g2v_gemm_f32: split-fp16 tcgen05 GEMM, bias in the

@@ -43,7 +43,9 @@ class GestureTokenizer:
         # searches pre_linear(z), :1230; VectorQuantizerEMA its pre_lin, :1755): the ids must be those of
         # module.forward, so the rows go through the module's own projection first
         self._project = None
-        if getattr(codebook, "_projects", False) and hasattr(codebook, "_search_rows"):
+        self._module = None
+        if getattr(codebook, "_projects", False) and hasattr(codebook, "tokenize"):
+            self._module = codebook            # its tokenize() searches the raw rows against the folded codebook
             self._project = codebook._search_rows
         elif hasattr(codebook, "pre_lin") and hasattr(codebook, "_embedding"):
             from .functional import gemm
@@ -68,6 +70,8 @@ class GestureTokenizer:
             return np.zeros(0, dtype=np.int64)
         if isinstance(rows, torch.Tensor) and rows.is_cuda:
             r = rows if rows.dtype in (torch.float32, torch.bfloat16, torch.float16) else rows.float()
+            if self._module is not None:
+                return self._module.tokenize(r).cpu().numpy().astype(np.int64)
             if self._project is not None:
                 with torch.no_grad():
                     r = self._project(r.float().contiguous())
@@ -81,6 +85,9 @@ class GestureTokenizer:
             out = np.empty(t.shape[0], dtype=np.int64)
             for r0 in range(0, t.shape[0], self.host_chunk_rows):
                 blk = t[r0:r0 + self.host_chunk_rows].to(self.E.device, non_blocking=True)
+                if self._module is not None:
+                    out[r0:r0 + blk.shape[0]] = self._module.tokenize(blk).cpu().numpy()
+                    continue
                 with torch.no_grad():
                     blk = self._project(blk.float().contiguous())
                 out[r0:r0 + blk.shape[0]] = vq_search(blk.contiguous(), self.E, self.cb).cpu().numpy()
