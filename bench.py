@@ -19,7 +19,7 @@ The default run (no --workload / --codes / --rows override) also measures, as su
   sweep                configs[3]: K = 512 .. 16384 at 1 048 576 rows per GPU, fp32 and bf16 rows, tensor roofline
   latency_n128_us      the reference's real batch (128 chunks per step): eager step and CUDA-graph replay
   soft_quantizer       SURVEY 8f #1: VQ_Payam_GSSoft fwd+bwd (tcgen05 split-fp16 GEMMs + row kernels) vs eager torch
-  vqvae_ema_flavour    the EMA flavour that searches on pre_linear(z), 1 M rows (pre_linear on g2v_gemm_f32)
+  vqvae_ema_flavour    the EMA flavour that searches on pre_linear(z), 1 M rows (pre_linear folded into the codebook)
   eager_cuda_baseline  the reference's op sequence in eager torch on the SAME GPU (cuBLAS path): the factor a
                        Gesture2Vec user with a GPU would see
 One JSON line is printed by rank 0.
@@ -596,7 +596,7 @@ def soft_record(cx: Ctx, g2v, lib, pk) -> dict:
 
 def vqvae_ema_record(cx: Ctx, g2v, lib, pk) -> dict:
     """The flavour Autoencoder_VQVAE.__init__ constructs at :801 (search and EMA sums on pre_linear(z)): fwd+bwd+EMA
-    at 1 M rows, K=512 -- pre_linear runs on g2v_gemm_f32, not on cuBLAS."""
+    at 1 M rows, K=512 -- pre_linear is folded into the codebook (no N x D x D projection at all)."""
     dev, K, D, N = cx.dev, 512, D_LATENT, 1_000_000
     gen = torch.Generator(device=dev).manual_seed(21 + cx.rank)
     E = torch.rand(K, D, device=dev, generator=torch.Generator(device=dev).manual_seed(0)) * 2 - 1
@@ -615,7 +615,7 @@ def vqvae_ema_record(cx: Ctx, g2v, lib, pk) -> dict:
         torch.autograd.backward([loss, q], [torch.ones_like(loss), gq])
     ms = cx.timed(step, 10)
     return {"codes_K": K, "rows_per_gpu": N, "ms_per_step": ms, "value": N * cx.world / (ms * 1e-3), "unit": UNIT,
-            "pre_linear": "g2v_gemm_f32 (split-fp16 tcgen05 GEMM, 2*N*D*D flop per step)"}
+            "pre_linear": "folded into a [K, D+4] codebook (K*D*D work per step); the raw rows are searched"}
 
 
 def eager_cuda_baseline(cx: Ctx, K_tok: int, K_train: int) -> dict:

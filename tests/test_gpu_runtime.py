@@ -175,3 +175,39 @@ def test_deterministic_statistics_are_bit_reproducible_and_tight():
         ra, rb = a(x), b(x)
         assert all(torch.equal(u, v) for u, v in zip(ra, rb))
         assert all(torch.equal(u, v) for u, v in zip(_state(a), _state(b)))
+
+
+def test_pre_linear_fold_matches_the_explicit_projection():
+    """Autoencoder_VQVAE_model.VQ_Payam_EMA searches on pre_linear(z) (:1230).  Default here: pre_linear folded into a
+    [K, D+4] codebook and the RAW rows searched; `fold_projection = False`: every row projected first (g2v_gemm_f32).
+    Same indices (near-ties aside), same loss / perplexity / EMA state, over 65 659 rows and two EMA steps."""
+    import gesture2vec_b200 as g
+    import gpu_synth as S
+    K, D, N = 512, 400, 65536 + 123
+    a = _layer(g, DEV, K, D, cls="VQVAE_VQ_Payam_EMA", seed=7)
+    b = _layer(g, DEV, K, D, cls="VQVAE_VQ_Payam_EMA", seed=7)
+    b.load_state_dict(a.state_dict())
+    b.fold_projection = False
+    assert a.fold_projection and a._fold(DEV) is not None and b._fold(DEV) is None
+    gq = torch.randn(N, D, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1))
+    for s in range(2):
+        x = torch.from_numpy(O.synth_latents("gru", N, D, seed=40 + s)).to(DEV)
+        zs = b._search_rows(x)                                           # the projected rows the reference searches
+        E = b._embedding.weight.detach().clone()
+        ia, ib = a.tokenize(x), b.tokenize(x)
+        aud = S.audit(zs, E, ia, ib)                                     # EPS_TIE: the reference's own fp32 noise floor
+        assert aud["hard"] == 0 and aud["mismatch"] <= N // 2000, aud
+        outs = []
+        for layer, ids in ((a, ib), (b, ib)):                            # same indices: compare the arithmetic downstream
+            xi = x.clone().requires_grad_(True)
+            loss, q, ppl, enc = layer.forward_with_indices(xi, ids)
+            (loss * 2.0 + (q * gq).sum()).backward()
+            outs.append((loss.detach(), q.detach(), ppl, xi.grad))
+        for u, v in zip(*outs):
+            _close(u, v, f"step {s}")
+        for u, v in zip(_state(a), _state(b)):
+            _close(u, v, f"state {s}")
+    tok = g.GestureTokenizer(a)
+    x = torch.from_numpy(O.synth_latents("gru", 5000, D, seed=50)).to(DEV)
+    assert np.array_equal(tok.encode_rows(x), a.tokenize(x).cpu().numpy())
+    assert np.array_equal(tok.encode_rows(x.cpu().numpy()), a.tokenize(x).cpu().numpy())
