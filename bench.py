@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--codes", type=int, default=400, help="codebook size K (GENEA 400, Trinity 512)")
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--algo", default="auto", choices=["auto", "simt", "tc"])
-    ap.add_argument("--variant", default="auto", choices=["auto", "tmem", "fused", "prep", "pair"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "tmem", "fused", "prep"])
     ap.add_argument("--extras", default="auto", choices=["auto", "none", "all"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -684,8 +684,7 @@ def main():
 
     K, D, N = a.codes, D_LATENT, a.rows
     flags = {"auto": _lib.ALGO_AUTO, "simt": _lib.ALGO_SIMT, "tc": _lib.ALGO_TC}[a.algo]
-    flags |= {"auto": 0, "tmem": _lib.TC_VARIANT_TMEM, "fused": _lib.TC_VARIANT_FUSED, "prep": _lib.TC_VARIANT_PREP,
-              "pair": _lib.TC_VARIANT_PAIR}[a.variant]
+    flags |= {"auto": 0, "tmem": _lib.TC_VARIANT_TMEM, "fused": _lib.TC_VARIANT_FUSED, "prep": _lib.TC_VARIANT_PREP}[a.variant]
     default_run = (a.workload == "tokenize" and K == 400 and N == 1_000_000 and a.dtype == "f32" and a.algo == "auto"
                    and a.variant == "auto")
     extras = a.extras == "all" or (a.extras == "auto" and default_run)

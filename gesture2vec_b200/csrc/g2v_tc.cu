@@ -815,7 +815,6 @@ constexpr int TME_ZCOLS = 32;           // fp32 columns per staging slot (128 by
 constexpr int TME_ZSLOT = TM * TME_ZCOLS * 4;   // 16384
 constexpr int TME_MAX_BST = 16;
 constexpr int kTmeDefaultABufs = 1;   // see plan_tmem()
-constexpr int kPairDefault = 0;       // tc_pair_kernel as the automatic choice for few code tiles (G2V_TC_PAIR=0|1|2 overrides)
 
 struct TmeParams {
   long long N;
@@ -1275,8 +1274,6 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
   if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
-#include "g2v_tc_pair.cuh"
-
 // ------------------------------------------------------------------------------------------
 // row preparation: fp16 operand rows + per-row constants
 // ------------------------------------------------------------------------------------------
@@ -1575,7 +1572,7 @@ inline size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 
 // Experiment knobs, read from the environment ONCE per process (-1 = not set).  None of them changes results.
 struct Tuning {
-  int tmem_mode, pair_mode, a_bufs, bstages, zslots, fused, cg, tmem16;
+  int tmem_mode, a_bufs, bstages, zslots, fused, cg, tmem16;
   unsigned dbg_flags;          // -DG2V_TRACE=1 builds only
   long long* trace;            // -DG2V_TRACE=1 builds only: device buffer the role timeline is written to
 };
@@ -1584,7 +1581,6 @@ const Tuning& tuning() {
     auto geti = [](const char* name) { const char* e = getenv(name); return e ? atoi(e) : -1; };
     Tuning u;
     u.tmem_mode = geti("G2V_TC_TMEM");
-    u.pair_mode = geti("G2V_TC_PAIR");
     u.a_bufs = geti("G2V_TC_ABUFS");
     u.bstages = geti("G2V_TC_BSTAGES");
     u.zslots = geti("G2V_TC_ZSLOTS");
@@ -1718,54 +1714,6 @@ int launch_tmem(TmeParams& R, const ZT* z, const __half* e16, int Kp, cudaStream
   return G2V_OK;
 }
 
-// "pair" variant (tc_pair_kernel): the geometry of plan_tmem with ONE A buffer in tensor memory, the second A
-// buffer in shared memory, one-panel codebook stages and a short row ring behind L2 prefetches.
-bool plan_pair(const void* z, int z_dtype, int64_t N, int K, int D, TmeParams* R) {
-  if (!plan_tmem(z, z_dtype, N, K, D, 1, R)) return false;
-  R->b_stage = (uint32_t)round_up((R->ntile / 2) * (KC + R->n_tail * KT) * 2, 1024);
-  int nb = 4;
-  if (tuning().bstages >= 0) nb = std::max(2, std::min(PAIR_MAX_BST, tuning().bstages));
-  int nz = 6;
-  if (tuning().zslots >= 0) nz = std::max(2, std::min(TME_MAX_ZSLOTS, tuning().zslots));
-  while (nz > 2 && pair_plan(R->n_full, R->n_tail, nb, R->b_stage, nz, R->Kpad).total + 1024 > 227 * 1024) --nz;
-  while (nb > 2 && pair_plan(R->n_full, R->n_tail, nb, R->b_stage, nz, R->Kpad).total + 1024 > 227 * 1024) --nb;
-  R->nb = nb; R->nz = nz;
-  return nz >= 3 && pair_plan(R->n_full, R->n_tail, nb, R->b_stage, nz, R->Kpad).total + 1024 <= 227 * 1024;
-}
-
-template <typename ZT>
-int launch_pair(TmeParams& R, const ZT* z, const __half* e16, int Kp, cudaStream_t st) {
-  alignas(64) CUtensorMap tmZ, tmZt, tmB, tmBt, tmBl, tmBlt;
-  int rc;
-  constexpr bool z32 = sizeof(ZT) == 4;
-  if ((rc = make_map(&tmZ, z, (uint64_t)R.N, (uint64_t)R.D, z32 ? TME_ZCOLS : KC, TM, CU_TENSOR_MAP_SWIZZLE_128B, z32))) return rc;
-  if ((rc = make_map(&tmZt, z, (uint64_t)R.N, (uint64_t)R.D, KT, TM, CU_TENSOR_MAP_SWIZZLE_NONE, z32))) return rc;
-  const uint32_t brow = (uint32_t)R.ntile / 2, blast = (uint32_t)R.n_last / 2;
-  if ((rc = make_map(&tmB, e16, (uint64_t)Kp, (uint64_t)R.Dp, KC, brow, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = make_map(&tmBt, e16, (uint64_t)Kp, (uint64_t)R.Dp, KT, brow, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
-  if ((rc = make_map(&tmBl, e16, (uint64_t)Kp, (uint64_t)R.Dp, KC, blast, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = make_map(&tmBlt, e16, (uint64_t)Kp, (uint64_t)R.Dp, KT, blast, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
-  const size_t smem = pair_plan(R.n_full, R.n_tail, R.nb, R.b_stage, R.nz, R.Kpad).total + 1024;
-  { const int rc_attr = set_dyn_smem(reinterpret_cast<const void*>(&tc_pair_kernel<ZT>), smem); if (rc_attr) return rc_attr; }
-  const int max_groups = num_sms() / 2;
-  const int groups = R.n_row_tiles < max_groups ? R.n_row_tiles : max_groups;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(groups * 2);
-  cfg.blockDim = dim3(TME_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  G2V_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_pair_kernel<ZT>, tmZ, tmZt, tmB, tmBt, tmBl, tmBlt, R));
-  G2V_LAUNCH_CHECK("tc_pair_kernel");
-  return G2V_OK;
-}
-
 template <typename ZT>
 int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, int K, int D, int32_t* idx,
            unsigned long long* stats, void* ws, unsigned flags, cudaStream_t st) {
@@ -1783,25 +1731,6 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
   const float* e2 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_e2_offset());
   const __half* e16 = reinterpret_cast<const __half*>(reinterpret_cast<const char*>(cb) + cb_e16_offset(K));
 
-  {   // few code tiles: CTA pairs with a double-buffered A operand (tensor memory + shared memory)
-    TmeParams R;
-    const int pmode = tuning().pair_mode >= 0 ? tuning().pair_mode : kPairDefault;
-    const bool want = variant == G2V_TC_VARIANT_PAIR || (variant == G2V_TC_VARIANT_AUTO && pmode != 0);
-    if (want && plan_pair(z, z_dtype, N, K, D, &R) && (variant == G2V_TC_VARIANT_PAIR || pmode == 2 || R.n_ntiles <= 4)) {
-      R.hdr = hdr; R.e2 = e2; R.idx = idx;
-      R.ntab = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_tab_offset());
-      R.pair_list = pairs; R.full_list = fulls; R.chain_list = chains; R.counters = counters; R.flags = flags;
-      R.trace = nullptr;
-      G2V_CUDA_CHECK(cudaMemsetAsync(counters, 0, 256 + kRerankArriveBytes, st));
-      cudaEvent_t pev0, pev1;
-      profile_take(&pev0, &pev1);
-      if (pev0) G2V_CUDA_CHECK(cudaEventRecord(pev0, st));
-      const int rc = launch_pair<ZT>(R, z, e16, Kp, st);
-      if (rc) return rc;
-      if (pev1) G2V_CUDA_CHECK(cudaEventRecord(pev1, st));
-      return run_recheck(z, z_dtype, E, cb, N, K, D, pairs, chains, fulls, counters, base + w.scratch, idx, stats, flags, st);
-    }
-  }
   {   // fp32 rows, few code tiles: A operand in tensor memory, CTA pairs (G2V_TC_TMEM=0 switches the variant off,
       // =2 forces it for any K)
     TmeParams R;

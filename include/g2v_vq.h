@@ -58,7 +58,6 @@ extern "C" {
 #define G2V_TC_VARIANT_TMEM (1u << 8)   /* tc_tmem_kernel: rows -> fp16 A operand in tensor memory, CTA pairs */
 #define G2V_TC_VARIANT_FUSED (2u << 8)  /* tc_search_kernel<1,true>: fp32 rows converted in-kernel, single CTA */
 #define G2V_TC_VARIANT_PREP (3u << 8)   /* row_prep_kernel + tc_search_kernel<.,false>: fp16 rows in shared memory */
-#define G2V_TC_VARIANT_PAIR (4u << 8)   /* tc_pair_kernel: as TMEM with a second A buffer in shared memory */
 
 /* slots of the optional int64 search_stats[8] output */
 #define G2V_STAT_ROWS 0         /* rows searched                                      */

@@ -26,8 +26,7 @@ def _g():
 
 def _variants(L):
     return {"auto": L.ALGO_AUTO, "simt": L.ALGO_SIMT, "tmem": L.ALGO_TC | L.TC_VARIANT_TMEM,
-            "fused": L.ALGO_TC | L.TC_VARIANT_FUSED, "prep": L.ALGO_TC | L.TC_VARIANT_PREP,
-            "pair": L.ALGO_TC | L.TC_VARIANT_PAIR}
+            "fused": L.ALGO_TC | L.TC_VARIANT_FUSED, "prep": L.ALGO_TC | L.TC_VARIANT_PREP}
 
 
 @pytest.mark.parametrize("N,K,D,dtype", [(777, 400, 400, torch.float32), (130, 512, 400, torch.bfloat16),
@@ -105,7 +104,7 @@ def test_full_row_audit_every_variant(lk, ck, K):
     for dtype in (torch.bfloat16, torch.float16):                      # 16-bit rows: their own exact answer
         z16 = z[:32768].to(dtype).contiguous()
         ex16 = g.vq_search_exact(z16, E)
-        for name in ("auto", "prep", "simt", "pair"):
+        for name in ("auto", "prep", "simt"):
             idx = g.vq_search(z16, E, cb, flags=_variants(L)[name])
             a = S.audit(z16.float(), E, idx, ex16, eps_tie=2.0 ** -40)
             assert a["hard"] == 0, (name, str(dtype), a)

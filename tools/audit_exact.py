@@ -37,8 +37,7 @@ def main():
     dev = torch.device("cuda:0")
     D = 400
     variants = {"auto": L.ALGO_AUTO, "simt": L.ALGO_SIMT, "tmem": L.ALGO_TC | L.TC_VARIANT_TMEM,
-                "fused": L.ALGO_TC | L.TC_VARIANT_FUSED, "prep": L.ALGO_TC | L.TC_VARIANT_PREP,
-            "pair": L.ALGO_TC | L.TC_VARIANT_PAIR}
+                "fused": L.ALGO_TC | L.TC_VARIANT_FUSED, "prep": L.ALGO_TC | L.TC_VARIANT_PREP}
     lines = []
 
     def log(rec):
@@ -61,7 +60,7 @@ def main():
         cb = g.prepare_codebook(E)
         names = list(variants) if K <= 2048 else ["auto", "prep", "simt"]
         for name in names:
-            if name in ("tmem", "pair") and K > 576:
+            if name == "tmem" and K > 576:
                 continue
             stats = torch.zeros(8, dtype=torch.int64, device=dev)
             idx = g.vq_search(z, E, cb, flags=variants[name], stats=stats)
@@ -75,9 +74,7 @@ def main():
         for dt in (torch.bfloat16, torch.float16):
             z16 = z[:n16].to(dt).contiguous()
             ex16 = g.vq_search_exact(z16, E)
-            for name in ("auto", "prep", "simt", "pair"):
-                if name == "pair" and K > 576:
-                    continue
+            for name in ("auto", "prep", "simt"):
                 idx = g.vq_search(z16, E, cb, flags=variants[name])
                 r = S.audit(z16.float(), E, idx, ex16, eps_tie=2.0 ** -40)
                 r.update(latents=lk, codebook=ck, K=K, dtype=str(dt).replace("torch.", ""), variant=name)

@@ -24,8 +24,7 @@ def main():
     dev = torch.device("cuda:0")
     gen = torch.Generator(device=dev).manual_seed(0)
     variants = {"auto": L.ALGO_AUTO, "simt": L.ALGO_SIMT, "tmem": L.ALGO_TC | L.TC_VARIANT_TMEM,
-                "fused": L.ALGO_TC | L.TC_VARIANT_FUSED, "prep": L.ALGO_TC | L.TC_VARIANT_PREP,
-            "pair": L.ALGO_TC | L.TC_VARIANT_PAIR}
+                "fused": L.ALGO_TC | L.TC_VARIANT_FUSED, "prep": L.ALGO_TC | L.TC_VARIANT_PREP}
     n_checked = 0
     for (N, K, D) in ((600, 400, 400), (257, 512, 400), (300, 1000, 104), (130, 80, 40)):
         E = torch.randn(K, D, device=dev, generator=gen)
