@@ -179,8 +179,12 @@ def test_modules_match_reference_golden(name):
             assert layer._embedding.weight.grad is None
             assert layer.pre_linear.weight.grad is None
             np.testing.assert_allclose(layer._ema_cluster_size.cpu().numpy(), gold[f"s{s}_cs"], rtol=1e-5, atol=1e-9)
-            _rows_close(layer._ema_w, gold, f"s{s}_ema_w", gold["krows"], 1e-5, 1e-6)
-            _rows_close(layer._embedding.weight, gold, f"s{s}_E", gold["krows"], 2e-5, 1e-6)
+            # the vqvae flavour takes its EMA sums over pre_linear(x): the reference adds the fp32-rounded
+            # projections row by row, the fold projects the per-code sums (W sum(x) + count b) -- two orders of
+            # the same fp32 sum, a few 1e-6 apart in absolute terms on elements that cancel to ~1e-2
+            folded = r["flavour"] == "vqvae"
+            _rows_close(layer._ema_w, gold, f"s{s}_ema_w", gold["krows"], 1e-5, 4e-6 if folded else 1e-6)
+            _rows_close(layer._embedding.weight, gold, f"s{s}_E", gold["krows"], 2e-5, 4e-6 if folded else 1e-6)
     if r["ema"]:
         layer.eval()
         before = [t.detach().clone() for t in (layer._embedding.weight, layer._ema_w, layer._ema_cluster_size)]
