@@ -163,6 +163,13 @@ int g2v_vq_apply(const float* x, const float* zs, const float* E, const int32_t*
   return launch_apply(x, zs, E, idx, N, K, D, out, sse, counts, dwr, dwr_replicas, (cudaStream_t)stream);
 }
 
+int g2v_pad_rows(const float* x, int64_t N, int D, int Dp, float* out, void* stream) {
+  if (N < 0 || D <= 0 || Dp < D || (D % 4) || (Dp % 4) || (N > 0 && (!x || !out))) return G2V_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) return G2V_ERR_ALIGN;
+  if (N == 0) return G2V_OK;
+  return launch_pad_rows(x, N, D, Dp, out, (cudaStream_t)stream);
+}
+
 int g2v_vq_stats_deterministic(const float* x, const float* zs, const float* E, const int32_t* order,
                                 const int64_t* seg, const int64_t* chunk_off, int64_t max_chunks, int K, int D,
                                 double* partial, float* dwr, double* sse_code, double* sse, void* stream) {

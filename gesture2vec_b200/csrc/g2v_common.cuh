@@ -100,6 +100,7 @@ int launch_full_recheck(const void* z, int z_dtype, const float* E, const void* 
                         bool overflow_only, cudaStream_t st);
 int launch_apply(const float* x, const float* zs, const float* E, const int32_t* idx, int64_t N, int K,
                  int D, float* out, double* sse, int32_t* counts, float* dwr, int dwr_replicas, cudaStream_t st);
+int launch_pad_rows(const float* x, int64_t N, int D, int Dp, float* out, cudaStream_t st);
 // deterministic (atomics-free, fixed-order, fp64-accumulated) residual sums and squared error from rows sorted by code
 int launch_stats_deterministic(const float* x, const float* zs, const float* E, const int32_t* order, const long long* seg,
                                const long long* chunk_off, int64_t max_chunks, int K, int D, double* partial, float* dwr,

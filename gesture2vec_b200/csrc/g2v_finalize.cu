@@ -395,7 +395,9 @@ int launch_fin(FinParams& P, cudaStream_t st) {
   long long want = 1;
   if (P.mode != 0 || P.cb) want = (P.Kp + FIN_WARPS - 1) / FIN_WARPS;
   if (P.do_pack) {
-    const long long pack_blocks = ((long long)P.K * P.D / 4 + FIN_THREADS * 4 - 1) / (FIN_THREADS * 4);
+    // one float4 column of the replicas per thread: the pack pass reads and re-zeroes reps x K x D floats, and with
+    // too few threads that is the whole cost of the launch (58 us at 64 blocks, K=512, 8 replicas)
+    const long long pack_blocks = ((long long)P.K * P.D / 4 + FIN_THREADS - 1) / FIN_THREADS;
     if (pack_blocks > want) want = pack_blocks;
   }
   const long long cap = std::min<long long>(max_coop_grid(), 2LL * num_sms());

@@ -620,6 +620,19 @@ __global__ void __launch_bounds__(APPLY_WARPS * 32) apply_runs_kernel(
   }
 }
 
+// rows [N, D] -> [N, Dp] with zeros in the extra columns (the raw rows a folded codebook is searched with)
+__global__ void __launch_bounds__(256) pad_rows_kernel(const float* __restrict__ x, long long N, int D, int Dp,
+                                                       float* __restrict__ out) {
+  const int nq = Dp >> 2, dq = D >> 2;                     // D % 4 == 0, Dp % 4 == 0
+  const long long total = N * nq;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / nq;
+    const int c = (int)(i - r * nq);
+    const float4 v = c < dq ? __ldcs(reinterpret_cast<const float4*>(x + (size_t)r * D) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    __stcs(reinterpret_cast<float4*>(out + (size_t)r * Dp) + c, v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // deterministic statistics: no atomics, fixed summation order, fp64 accumulation
 // ------------------------------------------------------------------------------------------
@@ -968,6 +981,12 @@ int launch_apply(const float* x, const float* zs, const float* E, const int32_t*
   else
     apply_kernel<false><<<grid, APPLY_WARPS * 32, smem, st>>>(x, zs, E, idx, N, K, D, out, sse, counts, dwr, dwr_replicas, use_hist);
   G2V_LAUNCH_CHECK("apply_kernel");
+  return G2V_OK;
+}
+
+int launch_pad_rows(const float* x, int64_t N, int D, int Dp, float* out, cudaStream_t st) {
+  pad_rows_kernel<<<grid_for(N * (Dp / 4), 256 * 4, 16), 256, 0, st>>>(x, N, D, Dp, out);
+  G2V_LAUNCH_CHECK("pad_rows_kernel");
   return G2V_OK;
 }
 

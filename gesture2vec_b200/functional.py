@@ -185,6 +185,17 @@ def vq_search_exact(z: torch.Tensor, E: torch.Tensor) -> torch.Tensor:
     return idx
 
 
+def pad_rows(x: torch.Tensor, Dp: int) -> torch.Tensor:
+    """[N, D] fp32 rows -> [N, Dp] with zeros in the extra columns (g2v_pad_rows)."""
+    N, D = x.shape
+    if D % 4 or Dp % 4 or x.dtype != torch.float32 or not x.is_contiguous() or (x.data_ptr() & 15):
+        return torch.nn.functional.pad(x.float(), (0, Dp - D)).contiguous()
+    with _on(x.device):
+        out = torch.empty(N, Dp, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().g2v_pad_rows(_ptr(x), N, D, Dp, _ptr(out), _stream(x.device)), "g2v_pad_rows")
+    return out
+
+
 def packed_numel(K: int, D: int) -> int:
     return K * D + K + 2
 

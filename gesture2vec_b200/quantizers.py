@@ -119,8 +119,8 @@ class _HardQuantizerBase(nn.Module):
                     E_fold, cb_fold, Wp, bp = fold
                     dw_transform = (Wp, bp)
                     if indices is None:
-                        indices = F.vq_search(torch.nn.functional.pad(flat.detach(), (0, E_fold.shape[1] - flat.shape[1])),
-                                              E_fold, cb_fold, flags=self.search_flags)
+                        indices = F.vq_search(F.pad_rows(flat.detach(), E_fold.shape[1]), E_fold, cb_fold,
+                                              flags=self.search_flags)
             training_ema = self._ema and self.training
             want_dwr = training_ema or (not self._ema and W.requires_grad and torch.is_grad_enabled())
             reduce_fn = self.stats_reduce if training_ema else None
@@ -169,8 +169,8 @@ class _HardQuantizerBase(nn.Module):
             with torch.no_grad():
                 if fold is not None:
                     E_fold, cb_fold, _, _ = fold
-                    return F.vq_search(torch.nn.functional.pad(flat.float(), (0, E_fold.shape[1] - flat.shape[1])),
-                                       E_fold, cb_fold, flags=self.search_flags)
+                    return F.vq_search(F.pad_rows(flat.float().contiguous(), E_fold.shape[1]), E_fold, cb_fold,
+                                       flags=self.search_flags)
                 zs = self._search_rows(flat.float() if self._projects else flat)
             return F.vq_search(flat if zs is None else zs, W.detach(), cb, flags=self.search_flags)
 
@@ -269,10 +269,12 @@ class VQVAE_VQ_Payam_EMA(_HardQuantizerBase):
         key = (Wemb.data_ptr(), Wemb._version, Wp.data_ptr(), Wp._version, bp.data_ptr(), bp._version, str(dev))
         if getattr(self, "_fold_key", None) != key:
             with torch.no_grad():
-                E64, W64, b64 = Wemb.detach().double(), Wp.detach().double(), bp.detach().double()
+                E64, b64 = Wemb.detach().double(), bp.detach().double()
                 K, D = E64.shape
-                ef = (E64 @ W64).float()                                       # rows W^T e_k
-                c = (E64 * E64).sum(1) - 2.0 * (E64 @ b64)
+                # rows W^T e_k: K x D x D on the split-fp16 tensor-core GEMM (2^-21 relative; an fp64 cuBLAS matmul of
+                # this size measured 19 ms on the B200 boxes of this pool, longer than the whole 1 M-row step)
+                ef = F.gemm(Wemb.detach(), Wp.detach(), transB=True)
+                c = (E64 * E64).sum(1) - 2.0 * (E64 * b64.unsqueeze(0)).sum(1)
                 g = c - (ef.double() ** 2).sum(1)
                 C = torch.clamp(-g.min(), min=0.0)
                 E_fold = torch.zeros(K, D + self._FOLD_PAD, dtype=torch.float32, device=dev)

@@ -124,6 +124,11 @@ int g2v_vq_apply(const float* x, const float* zs, const float* E, const int32_t*
                  int64_t N, int K, int D, float* out, double* sse, int32_t* counts,
                  float* dwr, int dwr_replicas, void* stream);
 
+/* out [N, Dp] = [x | 0]: the raw rows widened to the width of a folded codebook (quantizers.py
+ * VQVAE_VQ_Payam_EMA._fold: pre_linear, Autoencoder_VQVAE_model.py:1230, folded into [K, D+4] codes).  D, Dp
+ * multiples of 4, 16-byte aligned buffers. */
+int g2v_pad_rows(const float* x, int64_t N, int D, int Dp, float* out, void* stream);
+
 /* Reproducible statistics (SURVEY.md 7 "Atomics determinism"): the residual sums dwr [K,D] and the squared error
  * of g2v_vq_apply WITHOUT atomics -- rows sorted by code (order: stable, ties by row index; seg [K+1]: first
  * position of each code; chunk_off [K+1]: prefix sum of ceil(count_k / G2V_DET_CHUNK)), every chunk of
