@@ -27,6 +27,8 @@ namespace {
 constexpr float kU32 = 5.9604645e-8f;  // 2^-24, fp32 unit roundoff
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// row streams (read once): evict-first, so they do not push the codebook rows the same kernel gathers out of L1 / L2
+__device__ __forceinline__ float4 lds4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
@@ -449,7 +451,7 @@ __global__ void __launch_bounds__(APPLY_WARPS * 32) apply_kernel(
     float* drow = dwr ? dwr + (size_t)k * D : nullptr;
     if (VEC) {
       for (int c = lane * 4; c < D; c += 128) {
-        float4 xv = ldg4(xr + c), ev = ldg4(er + c);
+        float4 xv = lds4(xr + c), ev = ldg4(er + c);
         float4 d = make_float4(ev.x - xv.x, ev.y - xv.y, ev.z - xv.z, ev.w - xv.w);
         acc = fmaf(d.x, d.x, acc); acc = fmaf(d.y, d.y, acc);
         acc = fmaf(d.z, d.z, acc); acc = fmaf(d.w, d.w, acc);
@@ -459,7 +461,7 @@ __global__ void __launch_bounds__(APPLY_WARPS * 32) apply_kernel(
         }
         if (drow) {
           if (zr) {
-            float4 zv = ldg4(zr + c);
+            float4 zv = lds4(zr + c);
             red_add_v4(drow + c, zv.x - ev.x, zv.y - ev.y, zv.z - ev.z, zv.w - ev.w);
           } else {
             red_add_v4(drow + c, -d.x, -d.y, -d.z, -d.w);
@@ -554,7 +556,7 @@ __global__ void __launch_bounds__(APPLY_WARPS * 32) apply_runs_kernel(
       const unsigned ki = __shfl_sync(0xffffffffu, key, i);
       const float* r = src + (size_t)(base + (ki & 31u)) * D;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = (lane + 32 * u < nq) ? ldg4(r + 4 * (lane + 32 * u)) : zero4;
+      for (int u = 0; u < 4; ++u) v[u] = (lane + 32 * u < nq) ? lds4(r + 4 * (lane + 32 * u)) : zero4;
     };
     auto flush = [&]() {
       float* drow = dwr + (size_t)cur * D;
@@ -725,8 +727,8 @@ __global__ void __launch_bounds__(256) backward_kernel(const float* __restrict__
     float* o = g_x + (size_t)row * D;
     if (VEC) {
       for (int j = lane * 4; j < D; j += 128) {
-        float4 xv = ldg4(xr + j), ev = ldg4(er + j);
-        float4 g = gr ? ldg4(gr + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 xv = lds4(xr + j), ev = ldg4(er + j);
+        float4 g = gr ? lds4(gr + j) : make_float4(0.f, 0.f, 0.f, 0.f);
         float4 r = make_float4(fmaf(c, xv.x - ev.x, g.x), fmaf(c, xv.y - ev.y, g.y),
                                fmaf(c, xv.z - ev.z, g.z), fmaf(c, xv.w - ev.w, g.w));
         __stcs(reinterpret_cast<float4*>(o + j), r);
