@@ -16,6 +16,8 @@ LIB_PATH = os.environ.get("G2V_LIB_PATH") or os.path.join(HERE, "csrc", "libg2v_
 # dtype / flag codes (mirror include/g2v_vq.h)
 F32, BF16, F16 = 0, 1, 2
 ALGO_AUTO, ALGO_SIMT, ALGO_TC, NO_RECHECK = 0, 1, 2, 4
+ALGO_MASK = 3
+ERR_UNSUPPORTED = -7
 GEMM_ACCUMULATE, GEMM_FP16 = 1, 2
 DET_CHUNK = 128                    # G2V_DET_CHUNK
 TC_VARIANT_TMEM, TC_VARIANT_FUSED, TC_VARIANT_PREP = 1 << 8, 2 << 8, 3 << 8
@@ -35,6 +37,7 @@ SIGNATURES = {
     "g2v_search_path": (_i, [_i, _i, _u]),
     "g2v_workspace_bytes": (_sz, [_i64, _i, _i, _i, _u]),
     "g2v_vq_search": (_i, [_p, _i, _p, _p, _i64, _i, _i, _p, _p, _p, _sz, _u, _p]),
+    "g2v_vq_search_wide": (_i, [_p, _i, _i, _p, _p, _i64, _i, _i, _p, _p, _p, _sz, _u, _p]),
     "g2v_vq_apply": (_i, [_p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _i, _p]),
     "g2v_pad_rows": (_i, [_p, _i64, _i, _i, _p, _p]),
     "g2v_vq_stats_deterministic": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _p]),

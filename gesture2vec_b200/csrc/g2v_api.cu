@@ -154,6 +154,21 @@ int g2v_vq_search(const void* z, int z_dtype, const float* E, const void* cb, in
                             reinterpret_cast<int32_t*>(ws), idx, stats, st);
 }
 
+int g2v_vq_search_wide(const void* z, int z_dtype, int Dz, const float* E, const void* cb, int64_t N, int K, int D,
+                       int32_t* idx, int64_t* search_stats, void* ws, size_t ws_bytes, unsigned flags, void* stream) {
+  if (bad_shape(N, K, D) || Dz <= 0 || Dz > D || !E || !cb || (N > 0 && (!z || !idx))) return G2V_ERR_INVALID;
+  if (Dz == D) return g2v_vq_search(z, z_dtype, E, cb, N, K, D, idx, search_stats, ws, ws_bytes, flags, stream);
+  if (z_dtype != G2V_F32 && z_dtype != G2V_BF16 && z_dtype != G2V_F16) return G2V_ERR_DTYPE;
+  if (N == 0) return G2V_OK;
+  int rc = check_arch();
+  if (rc) return rc;
+  if (!tc_supported(K, D)) return G2V_ERR_UNSUPPORTED;
+  if (ws_bytes < g2v_workspace_bytes(N, K, D, z_dtype, G2V_ALGO_TC) || !ws) return G2V_ERR_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(ws) & 255) return G2V_ERR_ALIGN;
+  return launch_search_tc(z, z_dtype, E, cb, N, K, D, idx, reinterpret_cast<unsigned long long*>(search_stats),
+                          reinterpret_cast<char*>(ws) + 256, ws_bytes - 256, flags, (cudaStream_t)stream, Dz);
+}
+
 int g2v_vq_apply(const float* x, const float* zs, const float* E, const int32_t* idx, int64_t N, int K, int D,
                  float* out, double* sse, int32_t* counts, float* dwr, int dwr_replicas, void* stream) {
   if (bad_shape(N, K, D) || !E || (N > 0 && (!x || !idx)) || (dwr && dwr_replicas < 1)) return G2V_ERR_INVALID;

@@ -95,7 +95,7 @@ int launch_search_simt(const void* z, int z_dtype, const float* E, const void* c
 // take a per-row fp64 kernel, the rest a batched fp32+fp64 kernel; overflow_only = the caller has already
 // handled the first kFull64Cap rows itself.
 constexpr int kFull64Cap = 4096;
-int launch_full_recheck(const void* z, int z_dtype, const float* E, const void* cb, int K, int D, const int32_t* list,
+int launch_full_recheck(const void* z, int z_dtype, const float* E, const void* cb, int K, int D, int Dz, const int32_t* list,
                         const int32_t* count, int64_t max_rows, int32_t* idx, unsigned long long* stats,
                         bool overflow_only, cudaStream_t st);
 int launch_apply(const float* x, const float* zs, const float* E, const int32_t* idx, int64_t N, int K,
@@ -146,6 +146,6 @@ bool tc_supported(int K, int D);
 size_t tc_workspace_bytes(int64_t N, int K, int D, int z_dtype);
 int launch_search_tc(const void* z, int z_dtype, const float* E, const void* cb, int64_t N, int K, int D,
                      int32_t* idx, unsigned long long* stats, void* ws, size_t ws_bytes, unsigned flags,
-                     cudaStream_t st);
+                     cudaStream_t st, int Dz = 0);   // Dz: columns of the rows in memory (0 = D)
 
 }  // namespace g2v

@@ -281,7 +281,7 @@ template <typename ZT, bool VEC, int FR_ROWS, int NP>
 __global__ void __launch_bounds__(FR_THREADS) full_recheck_kernel(
     const ZT* __restrict__ z, const float* __restrict__ E, const float* __restrict__ e2,
     const float* __restrict__ ntab, int K, int D, const int* __restrict__ list,
-    const int* __restrict__ count, int skip, int* __restrict__ idx_out, unsigned long long* stats) {
+    const int* __restrict__ count, int skip, int* __restrict__ idx_out, unsigned long long* stats, int Dz) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* zs = reinterpret_cast<float*>(smem_raw);                 // [FR_ROWS][Dp4]
   const int Dp4 = (D + 3) & ~3;
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(FR_THREADS) full_recheck_kernel(
     __syncthreads();
     for (int i = threadIdx.x; i < FR_ROWS * Dp4; i += blockDim.x) {
       const int r = i / Dp4, j = i - r * Dp4;
-      zs[i] = (rows[r] >= 0 && j < D) ? to_f32(z[(size_t)rows[r] * D + j]) : 0.f;
+      zs[i] = (rows[r] >= 0 && j < Dz) ? to_f32(z[(size_t)rows[r] * Dz + j]) : 0.f;
     }
     __syncthreads();
     for (int r = warp; r < FR_ROWS; r += NW) {              // row norms for the fp32 error bound
@@ -809,7 +809,7 @@ inline int grid_for(long long work_items, int per_block, int cap_mult) {
 // case: a few hundred rows per million); anything beyond goes to the batched fp32+fp64 kernel above.
 
 template <typename ZT>
-__global__ void __launch_bounds__(256) full64_kernel(const ZT* __restrict__ z, const float* __restrict__ E, int K, int D,
+__global__ void __launch_bounds__(256) full64_kernel(const ZT* __restrict__ z, const float* __restrict__ E, int K, int D, int Dz,
                                                      const int* __restrict__ list, const int* __restrict__ count,
                                                      int* __restrict__ idx_out, unsigned long long* stats) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -823,7 +823,7 @@ __global__ void __launch_bounds__(256) full64_kernel(const ZT* __restrict__ z, c
   for (int e = blockIdx.x; e < n; e += gridDim.x) {
     const int row = list[e];
     __syncthreads();
-    for (int j = threadIdx.x; j < Dp; j += blockDim.x) zs[j] = j < D ? to_f32(z[(size_t)row * D + j]) : 0.f;
+    for (int j = threadIdx.x; j < Dp; j += blockDim.x) zs[j] = j < Dz ? to_f32(z[(size_t)row * Dz + j]) : 0.f;
     __syncthreads();
     double best = INFINITY;
     int besti = 0x7fffffff;
@@ -872,7 +872,7 @@ __global__ void __launch_bounds__(256) full64_kernel(const ZT* __restrict__ z, c
 }
 
 template <typename ZT, bool VEC, int R, int NP>
-static int launch_full_recheck_v(const ZT* z, const float* E, const void* cb, int K, int D, const int32_t* list,
+static int launch_full_recheck_v(const ZT* z, const float* E, const void* cb, int K, int D, int Dz, const int32_t* list,
                                  const int32_t* count, int64_t max_rows, int32_t* idx,
                                  unsigned long long* stats, cudaStream_t st) {
   const size_t smem = (size_t)R * ((D + 3) / 4 * 4) * sizeof(float);
@@ -883,13 +883,13 @@ static int launch_full_recheck_v(const ZT* z, const float* E, const void* cb, in
   const float* e2 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_e2_offset());
   if (smem > 40 * 1024)
     G2V_CUDA_CHECK(cudaFuncSetAttribute(full_recheck_kernel<ZT, VEC, R, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  full_recheck_kernel<ZT, VEC, R, NP><<<grid, FR_THREADS, smem, st>>>(z, E, e2, ntab, K, D, list, count, kFull64Cap, idx, stats);
+  full_recheck_kernel<ZT, VEC, R, NP><<<grid, FR_THREADS, smem, st>>>(z, E, e2, ntab, K, D, list, count, kFull64Cap, idx, stats, Dz);
   G2V_LAUNCH_CHECK("full_recheck_kernel");
   return G2V_OK;
 }
 
 template <typename ZT>
-static int launch_full_recheck_t(const ZT* z, const float* E, const void* cb, int K, int D, const int32_t* list,
+static int launch_full_recheck_t(const ZT* z, const float* E, const void* cb, int K, int D, int Dz, const int32_t* list,
                                  const int32_t* count, int64_t max_rows, int32_t* idx,
                                  unsigned long long* stats, bool overflow_only, cudaStream_t st) {
   if (overflow_only) {
@@ -898,25 +898,25 @@ static int launch_full_recheck_t(const ZT* z, const float* E, const void* cb, in
     const long long cap = max_rows < kFull64Cap ? max_rows : kFull64Cap;
     const long long lim = (long long)num_sms() * 8;
     const int g = (int)(cap < 1 ? 1 : (cap < lim ? cap : lim));
-    full64_kernel<ZT><<<g, 256, (size_t)((D + 31) / 32 * 32) * sizeof(float), st>>>(z, E, K, D, list, count, idx, stats);
+    full64_kernel<ZT><<<g, 256, (size_t)((D + 31) / 32 * 32) * sizeof(float), st>>>(z, E, K, D, Dz, list, count, idx, stats);
     G2V_LAUNCH_CHECK("full64_kernel");
     if (max_rows <= kFull64Cap) return G2V_OK;               // nothing can be left for the batched kernel
   }
   const bool vec = (D % 4 == 0) && aligned16(E);
   // small codebooks: 8 rows per CTA (more CTAs in flight, 4 partial sums -> tight fp32 bound);
   // large codebooks: 16 rows per CTA so each codebook row fetched from L2 serves more latents
-  if (!vec) return launch_full_recheck_v<ZT, false, 8, 1>(z, E, cb, K, D, list, count, max_rows, idx, stats, st);
-  if (K <= 2048) return launch_full_recheck_v<ZT, true, 8, 4>(z, E, cb, K, D, list, count, max_rows, idx, stats, st);
-  return launch_full_recheck_v<ZT, true, 16, 1>(z, E, cb, K, D, list, count, max_rows, idx, stats, st);
+  if (!vec) return launch_full_recheck_v<ZT, false, 8, 1>(z, E, cb, K, D, Dz, list, count, max_rows, idx, stats, st);
+  if (K <= 2048) return launch_full_recheck_v<ZT, true, 8, 4>(z, E, cb, K, D, Dz, list, count, max_rows, idx, stats, st);
+  return launch_full_recheck_v<ZT, true, 16, 1>(z, E, cb, K, D, Dz, list, count, max_rows, idx, stats, st);
 }
 
-int launch_full_recheck(const void* z, int z_dtype, const float* E, const void* cb, int K, int D, const int32_t* list,
+int launch_full_recheck(const void* z, int z_dtype, const float* E, const void* cb, int K, int D, int Dz, const int32_t* list,
                         const int32_t* count, int64_t max_rows, int32_t* idx, unsigned long long* stats,
                         bool overflow_only, cudaStream_t st) {
   switch (z_dtype) {
-    case G2V_F32: return launch_full_recheck_t(reinterpret_cast<const float*>(z), E, cb, K, D, list, count, max_rows, idx, stats, overflow_only, st);
-    case G2V_F16: return launch_full_recheck_t(reinterpret_cast<const __half*>(z), E, cb, K, D, list, count, max_rows, idx, stats, overflow_only, st);
-    case G2V_BF16: return launch_full_recheck_t(reinterpret_cast<const __nv_bfloat16*>(z), E, cb, K, D, list, count, max_rows, idx, stats, overflow_only, st);
+    case G2V_F32: return launch_full_recheck_t(reinterpret_cast<const float*>(z), E, cb, K, D, Dz, list, count, max_rows, idx, stats, overflow_only, st);
+    case G2V_F16: return launch_full_recheck_t(reinterpret_cast<const __half*>(z), E, cb, K, D, Dz, list, count, max_rows, idx, stats, overflow_only, st);
+    case G2V_BF16: return launch_full_recheck_t(reinterpret_cast<const __nv_bfloat16*>(z), E, cb, K, D, Dz, list, count, max_rows, idx, stats, overflow_only, st);
     default: return G2V_ERR_DTYPE;
   }
 }
@@ -946,7 +946,7 @@ static int launch_search_simt_t(const ZT* z, int z_dtype, const float* E, const 
   }
   G2V_LAUNCH_CHECK("search_simt_kernel");
   if (pev1) G2V_CUDA_CHECK(cudaEventRecord(pev1, st));
-  return launch_full_recheck_t(z, E, cb, K, D, full_list, full_count, N, idx, stats, false, st);
+  return launch_full_recheck_t(z, E, cb, K, D, D, full_list, full_count, N, idx, stats, false, st);
 }
 
 // fp32 search of all rows; `full_list` (N ints) and `full_count` (1 int) are scratch

@@ -819,6 +819,7 @@ constexpr int kTmeDefaultABufs = 1;   // see plan_tmem()
 struct TmeParams {
   long long N;
   int K, D, Dp;
+  int Dz;                         // columns of the rows in memory (<= D; the TMA zero-fills the rest of the operand)
   int n_full, n_tail, n_chunks;   // K panels of the A operand: 64 columns, then 16-column tails
   int ntile, n_ntiles, n_last;    // codes per accumulator stage; code tiles; codes of the last tile (multiple of 16)
   int a_bufs, acc_col0;           // A operand buffers in TMEM (1 or 2); first accumulator column in TMEM
@@ -1328,16 +1329,17 @@ __global__ void __launch_bounds__(256) row_prep_kernel(const ZT* __restrict__ z,
 // exact re-rank of the two or three candidate codes of each listed row (one warp per entry, fp64);
 // all loads of an entry are issued before the first use.  Lowest index wins exact ties.
 template <typename ZT>
-__device__ __forceinline__ void pair_entries(const ZT* __restrict__ z, const float* __restrict__ E, int D,
+__device__ __forceinline__ void pair_entries(const ZT* __restrict__ z, const float* __restrict__ E, int D, int Dz,
                                              const int* __restrict__ pair_list, int n, int* __restrict__ idx) {
   const int lane = threadIdx.x & 31;
   const int wstride = (gridDim.x * blockDim.x) >> 5;
   constexpr int U = 2;                                   // 2 x 128 columns per pass (registers -> occupancy)
-  const bool vec = (D % 4 == 0) && sizeof(ZT) == 4 && ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(E)) & 15) == 0;
+  // rows have Dz <= D columns (zero beyond: a folded codebook is wider than the rows it is searched with)
+  const bool vec = (D % 4 == 0) && (Dz % 4 == 0) && sizeof(ZT) == 4 && ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(E)) & 15) == 0;
   for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n; e += wstride) {
     const int4 ent = reinterpret_cast<const int4*>(pair_list)[e];
     const int row = ent.x, a = ent.y, b = ent.z, c = ent.w;
-    const ZT* zr = z + (size_t)row * D;
+    const ZT* zr = z + (size_t)row * Dz;
     const float* ea = E + (size_t)a * D;
     const float* eb = E + (size_t)b * D;
     const float* ec = E + (size_t)(c >= 0 ? c : a) * D;
@@ -1350,7 +1352,7 @@ __device__ __forceinline__ void pair_entries(const ZT* __restrict__ z, const flo
         for (int u = 0; u < U; ++u) {
           const int j = j0 + 128 * u;
           if (j < D) {
-            zv[u] = __ldg(reinterpret_cast<const float4*>(zf + j));
+            zv[u] = j < Dz ? __ldg(reinterpret_cast<const float4*>(zf + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
             av[u] = __ldg(reinterpret_cast<const float4*>(ea + j));
             bv[u] = __ldg(reinterpret_cast<const float4*>(eb + j));
             cv[u] = (c >= 0) ? __ldg(reinterpret_cast<const float4*>(ec + j)) : av[u];
@@ -1376,7 +1378,7 @@ __device__ __forceinline__ void pair_entries(const ZT* __restrict__ z, const flo
       }
     } else {
       for (int j = lane; j < D; j += 32) {
-        const double zv = (double)ld_f32(zr + j);
+        const double zv = j < Dz ? (double)ld_f32(zr + j) : 0.0;
         const double xa = zv - (double)__ldg(ea + j), xb = zv - (double)__ldg(eb + j), xc = zv - (double)__ldg(ec + j);
         da = fma(xa, xa, da);
         db = fma(xb, xb, db);
@@ -1404,14 +1406,14 @@ __device__ __forceinline__ void pair_entries(const ZT* __restrict__ z, const flo
 // BLOCK = false: one warp per entry.  BLOCK = true (large K: a chain is K / 32 codes): one CTA per entry, the
 // warps split the chain and combine through shared memory.
 template <typename ZT, bool BLOCK>
-__device__ __forceinline__ void chain_entries(const ZT* __restrict__ z, const float* __restrict__ E, int K, int D,
+__device__ __forceinline__ void chain_entries(const ZT* __restrict__ z, const float* __restrict__ E, int K, int D, int Dz,
                                               const int* __restrict__ chain_list, int n, int* __restrict__ idx,
                                               double* sh_v, int* sh_i) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wstride = BLOCK ? (int)gridDim.x : (int)((gridDim.x * blockDim.x) >> 5);
   for (int e = BLOCK ? (int)blockIdx.x : (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); e < n; e += wstride) {
     const int4 ent = reinterpret_cast<const int4*>(chain_list)[e];
-    const ZT* zr = z + (size_t)ent.x * D;
+    const ZT* zr = z + (size_t)ent.x * Dz;
     double best = INFINITY;
     int besti = 0x7fffffff;
     const int nchain = (K - ent.y + 31) / 32;
@@ -1425,7 +1427,7 @@ __device__ __forceinline__ void chain_entries(const ZT* __restrict__ z, const fl
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int j = j0 + 32 * u;
-          zv[u] = j < D ? ld_f32(zr + j) : 0.f;
+          zv[u] = j < Dz ? ld_f32(zr + j) : 0.f;
           ev[u] = j < D ? __ldg(er + j) : 0.f;
         }
 #pragma unroll
@@ -1467,7 +1469,7 @@ constexpr size_t kRerankScratchBytes = (size_t)kFull64Cap * kRerankMaxSlices * s
 constexpr size_t kRerankArriveBytes = (size_t)kFull64Cap * sizeof(int);
 
 template <typename ZT>
-__global__ void __launch_bounds__(256, 4) rerank_kernel(const ZT* __restrict__ z, const float* __restrict__ E, int K, int D,
+__global__ void __launch_bounds__(256, 4) rerank_kernel(const ZT* __restrict__ z, const float* __restrict__ E, int K, int D, int Dz,
                                                      const int* __restrict__ pair_list, const int* __restrict__ chain_list,
                                                      const int* __restrict__ full_list, const int* __restrict__ counters,
                                                      int slices, RerankSlot* scratch, int* arrive, int* __restrict__ idx,
@@ -1488,7 +1490,7 @@ __global__ void __launch_bounds__(256, 4) rerank_kernel(const ZT* __restrict__ z
     const int row = full_list[e];
     const int k0 = sl * per, k1 = min(K, k0 + per);
     __syncthreads();
-    for (int j = threadIdx.x; j < Dp; j += blockDim.x) zs[j] = j < D ? ld_f32(z + (size_t)row * D + j) : 0.f;
+    for (int j = threadIdx.x; j < Dp; j += blockDim.x) zs[j] = j < Dz ? ld_f32(z + (size_t)row * Dz + j) : 0.f;
     __syncthreads();
     double best = INFINITY;
     int besti = 0x7fffffff;
@@ -1555,9 +1557,9 @@ __global__ void __launch_bounds__(256, 4) rerank_kernel(const ZT* __restrict__ z
     }
   }
   // ---- chains, then candidate pairs / triples ----
-  if (K >= 2048) chain_entries<ZT, true>(z, E, K, D, chain_list, n_chain, idx, bv, bi);
-  else chain_entries<ZT, false>(z, E, K, D, chain_list, n_chain, idx, bv, bi);
-  pair_entries<ZT>(z, E, D, pair_list, n_pair, idx);
+  if (K >= 2048) chain_entries<ZT, true>(z, E, K, D, Dz, chain_list, n_chain, idx, bv, bi);
+  else chain_entries<ZT, false>(z, E, K, D, Dz, chain_list, n_chain, idx, bv, bi);
+  pair_entries<ZT>(z, E, D, Dz, pair_list, n_pair, idx);
   if (stats && blockIdx.x == 0 && threadIdx.x == 0) {
     atomicAdd(stats + G2V_STAT_PAIR_RECHECK, (unsigned long long)(n_pair + n_chain));
     atomicAdd(stats + G2V_STAT_FALLBACK_ROWS, (unsigned long long)counters[1]);
@@ -1618,7 +1620,7 @@ TcWs tc_ws(int64_t N, int D) {
 // exact re-rank of the rows the fast pass could not certify (candidate list, chain list, whole rows).
 // `counters` is followed by the arrive counters (zero on entry, left zero) and `scratch` by tc_ws().
 template <typename ZT>
-int run_recheck(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, int K, int D, int* pairs, int* chains,
+int run_recheck(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, int K, int D, int Dz, int* pairs, int* chains,
                 int* fulls, int* counters, void* scratch, int32_t* idx, unsigned long long* stats, unsigned flags,
                 cudaStream_t st) {
   if (flags & G2V_NO_RECHECK) return G2V_OK;
@@ -1633,20 +1635,20 @@ int run_recheck(const ZT* z, int z_dtype, const float* E, const void* cb, int64_
   // a small grid (a fixed 4-CTAs-per-SM grid costs ~25 us of launch + drain for a 128-row step)
   const long long want = (N + 7) / 8, cap = (long long)num_sms() * 4;
   const int rgrid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
-  rerank_kernel<ZT><<<rgrid, 256, smem, st>>>(z, E, K, D, pairs, chains, fulls, counters, slices,
+  rerank_kernel<ZT><<<rgrid, 256, smem, st>>>(z, E, K, D, Dz, pairs, chains, fulls, counters, slices,
                                                      reinterpret_cast<RerankSlot*>(scratch), arrive, idx, stats);
   G2V_LAUNCH_CHECK("rerank_kernel");
-  return launch_full_recheck(z, z_dtype, E, cb, K, D, fulls, counters + 1, N, idx, stats, true, st);
+  return launch_full_recheck(z, z_dtype, E, cb, K, D, Dz, fulls, counters + 1, N, idx, stats, true, st);
 }
 
 // "tmem" variant: geometry, or false if the shape does not qualify (fp32 rows read through TMA: D % 4 == 0
 // and a 16-byte aligned base; more than one 128-row tile so that a CTA pair has work).
-bool plan_tmem(const void* z, int z_dtype, int64_t N, int K, int D, int a_bufs, TmeParams* R) {
+bool plan_tmem(const void* z, int z_dtype, int64_t N, int K, int D, int Dz, int a_bufs, TmeParams* R) {
   const int Dp = round_up(D, 16);
   // rows are read through TMA: 16-byte aligned base and row pitch (G2V_TC_TMEM16=0 keeps 16-bit rows on the
   // row_prep + shared-memory-operand path)
   if (z_dtype != G2V_F32 && tuning().tmem16 == 0) return false;
-  if (D % (z_dtype == G2V_F32 ? 4 : 8) != 0 || (reinterpret_cast<uintptr_t>(z) & 15) != 0) return false;
+  if (Dz % (z_dtype == G2V_F32 ? 4 : 8) != 0 || (reinterpret_cast<uintptr_t>(z) & 15) != 0) return false;
   if (N <= TM || Dp > kMaxDp || Dp < KC) return false;
   // a_bufs == 2: the fp16 rows of the next tile are converted while the MMAs still read this one's; what is
   // left of tensor memory holds two (then much narrower) accumulator stages
@@ -1662,7 +1664,7 @@ bool plan_tmem(const void* z, int z_dtype, int64_t N, int K, int D, int a_bufs, 
     if (n < best_n || (n == best_n && pad < best_pad)) { best_nt = nt; best_n = n; best_pad = pad; best_last = last; }
   }
   if (best_nt == 0) return false;
-  R->N = N; R->K = K; R->D = D; R->Dp = Dp;
+  R->N = N; R->K = K; R->D = D; R->Dp = Dp; R->Dz = Dz;
   R->n_full = Dp / KC; R->n_tail = (Dp % KC) / KT; R->n_chunks = R->n_full + R->n_tail;
   if (R->n_chunks > MAX_CHUNKS) return false;
   R->ntile = best_nt; R->n_ntiles = best_n; R->n_last = best_last; R->Kpad = best_pad;
@@ -1686,8 +1688,8 @@ int launch_tmem(TmeParams& R, const ZT* z, const __half* e16, int Kp, cudaStream
   alignas(64) CUtensorMap tmZ, tmZt, tmB, tmBt, tmBl, tmBlt;
   int rc;
   constexpr bool z32 = sizeof(ZT) == 4;
-  if ((rc = make_map(&tmZ, z, (uint64_t)R.N, (uint64_t)R.D, z32 ? TME_ZCOLS : KC, TM, CU_TENSOR_MAP_SWIZZLE_128B, z32))) return rc;
-  if ((rc = make_map(&tmZt, z, (uint64_t)R.N, (uint64_t)R.D, KT, TM, CU_TENSOR_MAP_SWIZZLE_NONE, z32))) return rc;
+  if ((rc = make_map(&tmZ, z, (uint64_t)R.N, (uint64_t)R.Dz, z32 ? TME_ZCOLS : KC, TM, CU_TENSOR_MAP_SWIZZLE_128B, z32))) return rc;
+  if ((rc = make_map(&tmZt, z, (uint64_t)R.N, (uint64_t)R.Dz, KT, TM, CU_TENSOR_MAP_SWIZZLE_NONE, z32))) return rc;
   const uint32_t brow = (uint32_t)R.ntile / 2, blast = (uint32_t)R.n_last / 2;
   if ((rc = make_map(&tmB, e16, (uint64_t)Kp, (uint64_t)R.Dp, KC, brow, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map(&tmBt, e16, (uint64_t)Kp, (uint64_t)R.Dp, KT, brow, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
@@ -1715,7 +1717,7 @@ int launch_tmem(TmeParams& R, const ZT* z, const __half* e16, int Kp, cudaStream
 }
 
 template <typename ZT>
-int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, int K, int D, int32_t* idx,
+int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, int K, int D, int Dz, int32_t* idx,
            unsigned long long* stats, void* ws, unsigned flags, cudaStream_t st) {
   const int Dp = round_up(D, 16), Kp = round_up(K, 256);
   const unsigned variant = flags & G2V_TC_VARIANT_MASK;      // test / benchmark aid: pin the sweep kernel
@@ -1739,13 +1741,13 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
     else if (variant != G2V_TC_VARIANT_AUTO) mode = 0;
     // fp32 rows: any K (measured, 1 M rows: K=2048 1.77 vs 2.18 ms for row_prep + tc_search_kernel, K=16384 equal);
     // 16-bit rows: up to 16 code tiles, beyond that the cheaper 16-bit row_prep + 256-code stages win
-    bool use = mode != 0 && plan_tmem(z, z_dtype, N, K, D, 1, &R) &&
+    bool use = mode != 0 && plan_tmem(z, z_dtype, N, K, D, Dz, 1, &R) &&
                (mode == 2 || R.n_ntiles <= (z_dtype == G2V_F32 ? (1 << 30) : 16));
     if (use) {      // G2V_TC_ABUFS=1|2: single / double A operand buffer
       int a_bufs = kTmeDefaultABufs;
       if (tuning().a_bufs >= 0) a_bufs = tuning().a_bufs == 2 ? 2 : 1;
       TmeParams R2;
-      if (a_bufs == 2 && plan_tmem(z, z_dtype, N, K, D, 2, &R2)) R = R2;
+      if (a_bufs == 2 && plan_tmem(z, z_dtype, N, K, D, Dz, 2, &R2)) R = R2;
     }
     if (use) {
       R.hdr = hdr; R.e2 = e2; R.idx = idx;
@@ -1760,8 +1762,12 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
       const int rc = launch_tmem<ZT>(R, z, e16, Kp, st);
       if (rc) return rc;
       if (pev1) G2V_CUDA_CHECK(cudaEventRecord(pev1, st));
-      return run_recheck(z, z_dtype, E, cb, N, K, D, pairs, chains, fulls, counters, base + w.scratch, idx, stats, flags, st);
+      return run_recheck(z, z_dtype, E, cb, N, K, D, Dz, pairs, chains, fulls, counters, base + w.scratch, idx, stats, flags, st);
     }
+  }
+  if (Dz != D) {
+    set_error_detail("rows narrower than the codebook (Dz=%d, D=%d) are only searched by tc_tmem_kernel", Dz, D);
+    return G2V_ERR_UNSUPPORTED;
   }
   TcParams P;
   P.N = N; P.K = K; P.D = D; P.Dp = Dp;
@@ -1880,7 +1886,7 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
   G2V_LAUNCH_CHECK("tc_search_kernel");
   if (pev1) G2V_CUDA_CHECK(cudaEventRecord(pev1, st));
 
-  return run_recheck(z, z_dtype, E, cb, N, K, D, pairs, chains, fulls, counters, base + w.scratch, idx, stats, flags, st);
+  return run_recheck(z, z_dtype, E, cb, N, K, D, Dz, pairs, chains, fulls, counters, base + w.scratch, idx, stats, flags, st);
 }
 
 }  // namespace
@@ -1900,13 +1906,14 @@ size_t tc_workspace_bytes(int64_t N, int K, int D, int z_dtype) {
 
 int launch_search_tc(const void* z, int z_dtype, const float* E, const void* cb, int64_t N, int K, int D,
                      int32_t* idx, unsigned long long* stats, void* ws, size_t ws_bytes, unsigned flags,
-                     cudaStream_t st) {
+                     cudaStream_t st, int Dz) {
+  if (Dz <= 0) Dz = D;
   if (!tc_supported(K, D)) return G2V_ERR_UNSUPPORTED;
   if (ws_bytes < tc_ws(N, D).total) return G2V_ERR_WORKSPACE;
   switch (z_dtype) {
-    case G2V_F32: return run_tc(reinterpret_cast<const float*>(z), z_dtype, E, cb, N, K, D, idx, stats, ws, flags, st);
-    case G2V_F16: return run_tc(reinterpret_cast<const __half*>(z), z_dtype, E, cb, N, K, D, idx, stats, ws, flags, st);
-    case G2V_BF16: return run_tc(reinterpret_cast<const __nv_bfloat16*>(z), z_dtype, E, cb, N, K, D, idx, stats, ws, flags, st);
+    case G2V_F32: return run_tc(reinterpret_cast<const float*>(z), z_dtype, E, cb, N, K, D, Dz, idx, stats, ws, flags, st);
+    case G2V_F16: return run_tc(reinterpret_cast<const __half*>(z), z_dtype, E, cb, N, K, D, Dz, idx, stats, ws, flags, st);
+    case G2V_BF16: return run_tc(reinterpret_cast<const __nv_bfloat16*>(z), z_dtype, E, cb, N, K, D, Dz, idx, stats, ws, flags, st);
     default: return G2V_ERR_DTYPE;
   }
 }

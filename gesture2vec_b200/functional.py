@@ -166,6 +166,32 @@ def vq_search(z: torch.Tensor, E: torch.Tensor, cb: Optional[torch.Tensor] = Non
     return idx
 
 
+def vq_search_wide(z: torch.Tensor, E: torch.Tensor, cb: torch.Tensor, *, flags: int = _lib.ALGO_AUTO,
+                   stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Nearest code of rows that are NARROWER than the codebook (z [N, Dz], E [K, D], Dz <= D; the rows count as
+    [z | 0]): how a codebook with a projection folded in is searched with the raw rows.  The tensor-core sweep reads
+    the rows through TMA and lets it zero-fill the missing columns (g2v_vq_search_wide); shapes it does not cover
+    get a widened copy of the rows (g2v_pad_rows) and the ordinary search."""
+    _need_cuda(z, "z")
+    N, Dz = z.shape
+    K, D = E.shape
+    if Dz == D:
+        return vq_search(z, E, cb, flags=flags, stats=stats)
+    lib = _lib.load()
+    if z.dtype in _DT and z.is_contiguous() and N > 0:
+        dt = _DT[z.dtype]
+        with _on(z.device):
+            idx = torch.empty(N, dtype=torch.int32, device=z.device)
+            ws = _scratch.get(z.device, "search", lib.g2v_workspace_bytes(N, K, D, dt, _lib.ALGO_TC))
+            rc = lib.g2v_vq_search_wide(_ptr(z), dt, Dz, _ptr(E), _ptr(cb), N, K, D, _ptr(idx), _ptr(stats), _ptr(ws),
+                                        ws.numel(), flags & ~_lib.ALGO_MASK, _stream(z.device))
+        if rc == 0:
+            return idx
+        if rc != _lib.ERR_UNSUPPORTED:
+            _lib.check(rc, "g2v_vq_search_wide")
+    return vq_search(pad_rows(z.float().contiguous(), D), E, cb, flags=flags, stats=stats)
+
+
 def vq_search_exact(z: torch.Tensor, E: torch.Tensor) -> torch.Tensor:
     """Verification aid: exact-arithmetic (fp64) nearest code of every row, first index on ties (int32).
     Slow by design (FP64-bound); shares nothing with the fast search paths."""

@@ -115,12 +115,11 @@ class _HardQuantizerBase(nn.Module):
                 if fold is None:
                     zs = self._search_rows(flat.detach())
                 else:
-                    # the projection lives in the codebook: search the RAW rows (zero-extended to the folded width)
+                    # the projection lives in the codebook: search the RAW rows (the TMA zero-fills the extra columns)
                     E_fold, cb_fold, Wp, bp = fold
                     dw_transform = (Wp, bp)
                     if indices is None:
-                        indices = F.vq_search(F.pad_rows(flat.detach(), E_fold.shape[1]), E_fold, cb_fold,
-                                              flags=self.search_flags)
+                        indices = F.vq_search_wide(flat.detach(), E_fold, cb_fold, flags=self.search_flags)
             training_ema = self._ema and self.training
             want_dwr = training_ema or (not self._ema and W.requires_grad and torch.is_grad_enabled())
             reduce_fn = self.stats_reduce if training_ema else None
@@ -169,8 +168,7 @@ class _HardQuantizerBase(nn.Module):
             with torch.no_grad():
                 if fold is not None:
                     E_fold, cb_fold, _, _ = fold
-                    return F.vq_search(F.pad_rows(flat.float().contiguous(), E_fold.shape[1]), E_fold, cb_fold,
-                                       flags=self.search_flags)
+                    return F.vq_search_wide(flat, E_fold, cb_fold, flags=self.search_flags)
                 zs = self._search_rows(flat.float() if self._projects else flat)
             return F.vq_search(flat if zs is None else zs, W.detach(), cb, flags=self.search_flags)
 

@@ -106,6 +106,15 @@ int g2v_vq_search(const void* z, int z_dtype, const float* E, const void* cb,
                   int64_t N, int K, int D, int32_t* idx, int64_t* search_stats,
                   void* ws, size_t ws_bytes, unsigned flags, void* stream);
 
+/* g2v_vq_search for rows that are NARROWER than the codebook: z is [N, Dz] with Dz <= D and counts as [z | 0].
+ * This is how a codebook with a linear projection folded in (quantizers.py VQVAE_VQ_Payam_EMA._fold: pre_linear of
+ * Autoencoder_VQVAE_model.py:1230 becomes D+4 code columns) is searched with the RAW rows: the TMA loads of the
+ * tensor-core sweep zero-fill the missing operand columns, so no widened copy of the rows is made.  Covered by the
+ * tcgen05 sweep that reads the rows through TMA (Dz % 4 == 0 for fp32, % 8 for 16-bit rows, 16-byte aligned, N > 128);
+ * G2V_ERR_UNSUPPORTED otherwise (the caller widens the rows with g2v_pad_rows and calls g2v_vq_search). */
+int g2v_vq_search_wide(const void* z, int z_dtype, int Dz, const float* E, const void* cb, int64_t N, int K, int D,
+                       int32_t* idx, int64_t* search_stats, void* ws, size_t ws_bytes, unsigned flags, void* stream);
+
 /* Gather + straight-through value + loss/EMA statistics in one pass over the rows.
  * Replaces the one-hot GEMM gather, both mse_loss reductions, the STE add, the
  * column sums of the one-hot and encodings^T @ flat_input

@@ -153,3 +153,23 @@ def test_unaligned_and_odd_shapes_hypothesis():
             assert a["hard"] == 0, (N, K, D, off, dt, flags, a)
 
     run()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("N,K,D,extra", [(70000, 512, 400, 4), (300, 400, 400, 4), (1000, 1024, 200, 16), (100, 64, 40, 4)])
+def test_narrow_rows_against_a_wider_codebook(N, K, D, extra, dtype):
+    """g2v_vq_search_wide: rows [N, D] searched against a [K, D + extra] codebook as [z | 0] -- the folded-projection
+    search.  Every row against the fp64 checker on explicitly widened rows; shapes the TMA sweep does not cover (tiny N,
+    tiny D) take the widened-copy fallback and must agree too."""
+    g, L = _g()
+    gen = torch.Generator(device=DEV).manual_seed(N + K)
+    E = torch.randn(K, D + extra, device=DEV, generator=gen)
+    E[:, D + 1:] = 0.0                                     # the fold uses ONE extra column; the rest is alignment padding
+    z = torch.randn(N, D, device=DEV, generator=gen).to(dtype)
+    cb = g.prepare_codebook(E)
+    stats = torch.zeros(8, dtype=torch.int64, device=DEV)
+    idx = g.vq_search_wide(z, E, cb, stats=stats)
+    zw = torch.nn.functional.pad(z.float(), (0, extra)).contiguous()
+    exact = g.vq_search_exact(zw, E)
+    a = S.audit(zw, E, idx, exact, eps_tie=2.0 ** -40)
+    assert a["hard"] == 0, (a, stats.cpu().tolist())
