@@ -178,6 +178,12 @@ int g2v_vq_apply(const float* x, const float* zs, const float* E, const int32_t*
   return launch_apply(x, zs, E, idx, N, K, D, out, sse, counts, dwr, dwr_replicas, (cudaStream_t)stream);
 }
 
+int g2v_fold_projection(const float* E, const float* W, const float* b, int K, int D, int ld_out, float* out, double* g,
+                        void* stream) {
+  if (K <= 0 || D <= 0 || ld_out < D || !E || !W || !b || !out || !g || (size_t)D * 4 > 48 * 1024) return G2V_ERR_INVALID;
+  return launch_fold_rows(E, W, b, K, D, ld_out, out, g, (cudaStream_t)stream);
+}
+
 int g2v_pad_rows(const float* x, int64_t N, int D, int Dp, float* out, void* stream) {
   if (N < 0 || D <= 0 || Dp < D || (D % 4) || (Dp % 4) || (N > 0 && (!x || !out))) return G2V_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) return G2V_ERR_ALIGN;

@@ -115,6 +115,8 @@ int launch_step_finalize(int32_t* counts, double* sse, float* dwr, int dwr_repli
                          int mode, const float* cs_in, float* cs_out, const float* w_in, float* w_out,
                          const float* E_old, float* E_new, float* E_prev, float decay, float eps, double* shift2,
                          void* cb, const float* E_cb, cudaStream_t st);
+int launch_fold_rows(const float* E, const float* W, const float* b, int K, int D, int ld_out, float* out, double* g,
+                     cudaStream_t st);
 // g2v_audit.cu: exact fp64 argmin of every row (verification aid); ws holds K doubles
 int launch_search_exact64(const void* z, int z_dtype, const float* E, int64_t N, int K, int D, int32_t* idx, void* ws,
                           cudaStream_t st);

@@ -373,6 +373,34 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const FinParams P
   }
 }
 
+// Fold a linear projection into a codebook (quantizers.py VQVAE_VQ_Payam_EMA._fold): for code k
+//   out[k, 0..D)  = fp32( sum_i E[k,i] W[i,j] )                      -- W^T e_k, accumulated in fp64, rounded once
+//   g[k]          = |e_k|^2 - 2 b.e_k - |out[k, 0..D)|^2   (fp64)    -- what the extra coordinate has to carry
+// One block per code; threads stride the output columns (W rows are read coalesced, E[k,i] is a broadcast).
+__global__ void __launch_bounds__(128) fold_rows_kernel(const float* __restrict__ E, const float* __restrict__ W,
+                                                        const float* __restrict__ b, int D, int ld_out,
+                                                        float* __restrict__ out, double* __restrict__ g) {
+  __shared__ double sh[4];
+  extern __shared__ float er[];                 // the code row
+  const int k = blockIdx.x;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) er[i] = E[(size_t)k * D + i];
+  __syncthreads();
+  double n2 = 0.0;
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    double acc = 0.0;
+    for (int i = 0; i < D; ++i) acc = fma((double)er[i], (double)W[(size_t)i * D + j], acc);
+    const float f = (float)acc;
+    out[(size_t)k * ld_out + j] = f;
+    n2 += (double)f * (double)f;
+  }
+  double c = 0.0;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) c += (double)er[i] * ((double)er[i] - 2.0 * (double)b[i]);
+  double v = warp_sum_d(c - n2);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) g[k] = sh[0] + sh[1] + sh[2] + sh[3];
+}
+
 // largest cooperative grid of finalize_kernel on the current device (cached per thread and device)
 int max_coop_grid() {
   static thread_local int cached_dev = -1, cached = 0;
@@ -417,6 +445,13 @@ FinParams fin_blank(int K, int D) {
 }
 
 }  // namespace
+
+int launch_fold_rows(const float* E, const float* W, const float* b, int K, int D, int ld_out, float* out, double* g,
+                     cudaStream_t st) {
+  fold_rows_kernel<<<K, 128, (size_t)D * sizeof(float), st>>>(E, W, b, D, ld_out, out, g);
+  G2V_LAUNCH_CHECK("fold_rows_kernel");
+  return G2V_OK;
+}
 
 // ------------------------------------------------------------------------------------------
 // launchers

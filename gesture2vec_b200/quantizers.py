@@ -267,16 +267,14 @@ class VQVAE_VQ_Payam_EMA(_HardQuantizerBase):
         key = (Wemb.data_ptr(), Wemb._version, Wp.data_ptr(), Wp._version, bp.data_ptr(), bp._version, str(dev))
         if getattr(self, "_fold_key", None) != key:
             with torch.no_grad():
-                E64, b64 = Wemb.detach().double(), bp.detach().double()
-                K, D = E64.shape
-                # rows W^T e_k: K x D x D on the split-fp16 tensor-core GEMM (2^-21 relative; an fp64 cuBLAS matmul of
-                # this size measured 19 ms on the B200 boxes of this pool, longer than the whole 1 M-row step)
-                ef = F.gemm(Wemb.detach(), Wp.detach(), transB=True)
-                c = (E64 * E64).sum(1) - 2.0 * (E64 * b64.unsqueeze(0)).sum(1)
-                g = c - (ef.double() ** 2).sum(1)
-                C = torch.clamp(-g.min(), min=0.0)
+                K, D = Wemb.shape
                 E_fold = torch.zeros(K, D + self._FOLD_PAD, dtype=torch.float32, device=dev)
-                E_fold[:, :D] = ef
+                g = torch.empty(K, dtype=torch.float64, device=dev)
+                # rows W^T e_k in fp64, rounded once, and g_k = c_k - |W^T e_k|^2 (g2v_fold_projection: K x D x D work)
+                _lib.check(_lib.load().g2v_fold_projection(
+                    F._ptr(Wemb.detach()), F._ptr(Wp.detach().contiguous()), F._ptr(bp.detach().contiguous()), K, D,
+                    D + self._FOLD_PAD, F._ptr(E_fold), F._ptr(g), F._stream(dev)), "g2v_fold_projection")
+                C = torch.clamp(-g.min(), min=0.0)
                 E_fold[:, D] = torch.sqrt(g + C).float()
                 self._fold_E = E_fold
                 self._fold_cb = F.prepare_codebook(E_fold, getattr(self, "_fold_cb", None))

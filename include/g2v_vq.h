@@ -133,6 +133,13 @@ int g2v_vq_apply(const float* x, const float* zs, const float* E, const int32_t*
                  int64_t N, int K, int D, float* out, double* sse, int32_t* counts,
                  float* dwr, int dwr_replicas, void* stream);
 
+/* Fold the linear layer in front of a search into the codebook (pre_linear, Autoencoder_VQVAE_model.py:1230):
+ * argmin_k |W z + b - e_k|^2 = argmin_k (c_k - 2 z.(W^T e_k)), c_k = |e_k|^2 - 2 b.e_k.  Writes out[k, 0..D) =
+ * W^T e_k (fp64 accumulation, one rounding; W is nn.Linear's [D_out, D_in] weight read as rows i, columns j) and
+ * g[k] = c_k - |out[k, 0..D)|^2 in fp64; the caller completes the folded code with the coordinate sqrt(g[k] + C). */
+int g2v_fold_projection(const float* E, const float* W, const float* b, int K, int D, int ld_out, float* out, double* g,
+                        void* stream);
+
 /* out [N, Dp] = [x | 0]: the raw rows widened to the width of a folded codebook (quantizers.py
  * VQVAE_VQ_Payam_EMA._fold: pre_linear, Autoencoder_VQVAE_model.py:1230, folded into [K, D+4] codes).  D, Dp
  * multiples of 4, 16-byte aligned buffers. */

@@ -26,6 +26,8 @@ stats = torch.zeros(8, dtype=torch.int64, device=dev)
 print("pad ms", timed(lambda: torch.nn.functional.pad(x, (0, 4))))
 xp = torch.nn.functional.pad(x, (0, 4))
 print("folded search ms", timed(lambda: F.vq_search(xp, E_fold, cb_fold, stats=stats)), "stats", stats.tolist())
+print("wide search (no copy) ms", timed(lambda: F.vq_search_wide(x, E_fold, cb_fold)))
+print("own pad kernel ms", timed(lambda: F.pad_rows(x, D + 4)))
 E = layer._embedding.weight.detach()
 zs = F.gemm(x, Wp, bias=bp)
 stats.zero_()
@@ -41,6 +43,19 @@ def step():
     xs.grad = None
     loss, q, ppl, _ = layer(xs)
     torch.autograd.backward([loss, q], [torch.ones_like(loss), gq])
+ids = layer.tokenize(x)
+def step_given():
+    xs.grad = None
+    loss, q, ppl, _ = layer.forward_with_indices(xs, ids)
+    torch.autograd.backward([loss, q], [torch.ones_like(loss), gq])
+def fwd_only():
+    with torch.no_grad():
+        layer(x)
 for fold in (True, False):
     layer.fold_projection = fold
-    print("step ms fold=%s" % fold, timed(step, 5))
+    print("step ms fold=%s" % fold, timed(step, 5), "| with indices given", timed(step_given, 5), "| forward only", timed(fwd_only, 5))
+import cProfile, pstats
+layer.fold_projection = True
+torch.cuda.synchronize()
+pr = cProfile.Profile(); pr.enable(); step(); torch.cuda.synchronize(); pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
