@@ -15,13 +15,13 @@ LIB_PATH = os.environ.get("G2V_LIB_PATH") or os.path.join(HERE, "csrc", "libg2v_
 
 # dtype / flag codes (mirror include/g2v_vq.h)
 F32, BF16, F16 = 0, 1, 2
-ALGO_AUTO, ALGO_SIMT, ALGO_TC, NO_RECHECK = 0, 1, 2, 4
+ALGO_AUTO, ALGO_SIMT, ALGO_TC, NO_RECHECK, NO_REFINE = 0, 1, 2, 4, 8
 ALGO_MASK = 3
 ERR_UNSUPPORTED = -7
 GEMM_ACCUMULATE, GEMM_FP16 = 1, 2
 DET_CHUNK = 128                    # G2V_DET_CHUNK
 TC_VARIANT_TMEM, TC_VARIANT_FUSED, TC_VARIANT_PREP = 1 << 8, 2 << 8, 3 << 8
-STAT_ROWS, STAT_PAIR_RECHECK, STAT_FULL_RECHECK, STAT_FALLBACK_ROWS = 0, 1, 2, 3
+STAT_ROWS, STAT_PAIR_RECHECK, STAT_FULL_RECHECK, STAT_FALLBACK_ROWS, STAT_REFINE_ROWS, STAT_REFINE_EXACT = 0, 1, 2, 3, 4, 5
 
 _p, _i, _i64, _f, _sz, _u = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t, C.c_uint
 

@@ -28,11 +28,14 @@ struct CbHeader {
   float e2max;      // max_k ||e_k||^2
   float e2min;      // min_k ||e_k||^2
   float amax;       // max |e_kj|
-  float scale_e;    // power of two the fp16 copy was multiplied by (brings amax into [256,512))
+  float scale_e;    // power of two the fp16 copy was multiplied by (brings amax into [16384,32768))
   int K, D, Kp, Dp;
   int magic;
-  float sfrac;      // max_k ||e_k - fp16(e_k*scale_e)/scale_e|| / ||e_k||: measured residual of the fp16 copy
-  int pad[54];
+  // measured rounding residual of the fp16 copy, r_k = e_k - fp16(e_k*scale_e)/scale_e, split by where the
+  // scaled element landed:  ||r_k|| <= sfrac ||e_k|| + rsub
+  float sfrac;      // max_k ||r_k restricted to fp16-normal elements|| / ||e_k||   (<= 2^-12)
+  float rsub;       // max_k ||r_k restricted to fp16-subnormal elements||          (absolute: <= sqrt(D) 2^-25 / scale_e)
+  int pad[53];
 };
 static_assert(sizeof(CbHeader) == 256, "CbHeader must be 256 bytes");
 constexpr int kCbMagic = 0x67327632;  // "g2v2"
@@ -93,11 +96,11 @@ int launch_search_simt(const void* z, int z_dtype, const float* E, const void* c
                        unsigned long long* stats, cudaStream_t st);
 // exact fp64 argmin of the rows in list[0 .. *count) (count <= max_rows).  The first kFull64Cap listed rows
 // take a per-row fp64 kernel, the rest a batched fp32+fp64 kernel; overflow_only = the caller has already
-// handled the first kFull64Cap rows itself.
+// handled the first `handled` rows itself.
 constexpr int kFull64Cap = 4096;
 int launch_full_recheck(const void* z, int z_dtype, const float* E, const void* cb, int K, int D, int Dz, const int32_t* list,
                         const int32_t* count, int64_t max_rows, int32_t* idx, unsigned long long* stats,
-                        bool overflow_only, cudaStream_t st);
+                        bool overflow_only, cudaStream_t st, int64_t handled = kFull64Cap);
 int launch_apply(const float* x, const float* zs, const float* E, const int32_t* idx, int64_t N, int K,
                  int D, float* out, double* sse, int32_t* counts, float* dwr, int dwr_replicas, cudaStream_t st);
 int launch_pad_rows(const float* x, int64_t N, int D, int Dp, float* out, cudaStream_t st);
@@ -132,6 +135,10 @@ size_t gemm_workspace_bytes(int64_t M, int N, int64_t K, int single_term);
 int launch_gemm_f32(const float* A, int64_t lda, int transA, const float* B, int64_t ldb, int transB, int64_t M, int N,
                     int64_t K, const float* bias, float* C, int64_t ldc, float alpha, int accumulate, int single_term,
                     void* ws, cudaStream_t st);
+
+// operands already in the fp16 layout (row-major [rows, kp16], kp16 % 64 == 0), row count on the device
+int launch_gemm_prepared(const __half* A16, const int* m_dev, long long m_cap, const __half* B16, int N, long long kp16,
+                         float* C, long long ldc, cudaStream_t st);
 
 // ---- g2v_soft.cu: row kernels of the soft quantizer VQ_Payam_GSSoft
 int launch_soft_assign(const float* m, float* dot, const float* lv, const float* e2, int64_t N, int K, int D, float* p,

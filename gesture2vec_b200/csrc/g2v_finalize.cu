@@ -294,8 +294,10 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const FinParams P
   float sc = 1.f;
   if (amax > 0.f && isfinite(amax)) {
     int e;
-    frexpf(amax, &e);              // amax = m * 2^e, m in [0.5,1)  ->  amax * 2^(9-e) in [256,512)
-    sc = ldexpf(1.f, 9 - e);
+    // amax = m * 2^e, m in [0.5,1)  ->  amax * 2^(15-e) in [16384,32768): the top of the fp16 range, so that codes
+    // 2^20 and more below the largest entry (live codes next to dead EMA codes) still land on normal numbers
+    frexpf(amax, &e);
+    sc = ldexpf(1.f, 15 - e);
   }
   const float inv = 1.f / sc;      // power of two: exact
   if (blockIdx.x == 0 && warp == 0) {
@@ -322,7 +324,7 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const FinParams P
   const bool vec_c = (D % 4 == 0) && P.Dp <= 512 && al16(P.E_cb);
   for (int k = blockIdx.x * FIN_WARPS + warp; k < P.Kp; k += gridDim.x * FIN_WARPS) {
     __half* o = e16 + (size_t)k * P.Dp;
-    float s2 = 0.f, n2 = 0.f;
+    float s2 = 0.f, n2 = 0.f, u2 = 0.f;                    // residual^2 on normal / norm^2 / residual^2 on subnormal elements
     if (vec_c) {                                           // float4 in, 4 x fp16 (8 bytes) out; Dp % 16 == 0
       const int nq = D >> 2, nqp = P.Dp >> 2;
       float4 v[4];
@@ -343,7 +345,8 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const FinParams P
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const float r = vv[t] - back[t] * inv;
-            s2 = fmaf(r, r, s2);
+            if (fabsf(vv[t] * sc) >= 6.1035156e-5f) s2 = fmaf(r, r, s2);
+            else u2 = fmaf(r, r, u2);
             n2 = fmaf(vv[t], vv[t], n2);
           }
           uint2 pk2;
@@ -357,7 +360,8 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const FinParams P
         const float v = (k < K && j < D) ? __ldcg(P.E_cb + (size_t)k * D + j) : 0.f;
         const __half h = __float2half_rn(v * sc);
         const float r = v - __half2float(h) * inv;
-        s2 = fmaf(r, r, s2);
+        if (fabsf(v * sc) >= 6.1035156e-5f) s2 = fmaf(r, r, s2);
+        else u2 = fmaf(r, r, u2);
         n2 = fmaf(v, v, n2);
         o[j] = h;
       }
@@ -366,10 +370,14 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const FinParams P
     for (int off = 16; off > 0; off >>= 1) {
       s2 += __shfl_xor_sync(0xffffffffu, s2, off);
       n2 += __shfl_xor_sync(0xffffffffu, n2, off);
+      u2 += __shfl_xor_sync(0xffffffffu, u2, off);
     }
-    // residual relative to the code's own norm, so one scalar bounds every code: ||r_e,k|| <= sfrac ||e_k||
-    if (lane == 0 && k < K && n2 > 0.f)
+    // normal elements round relative to themselves, so their residual scales with the code's own norm; what
+    // lands on fp16 subnormals rounds on a fixed grid and is bounded absolutely:  ||r_e,k|| <= sfrac ||e_k|| + rsub
+    if (lane == 0 && k < K && n2 > 0.f) {
       atomicMax(reinterpret_cast<int*>(&hdr->sfrac), __float_as_int(sqrtf(s2 / n2) * 1.001f));
+      if (u2 > 0.f) atomicMax(reinterpret_cast<int*>(&hdr->rsub), __float_as_int(sqrtf(u2) * 1.001f));
+    }
   }
 }
 

@@ -147,6 +147,7 @@ struct GemmParams {
   long long ldc;
   float alpha;
   int atomic;                       // split-K: accumulate with red.add into a zeroed / pre-filled C
+  const int* m_dev;                 // optional: the row count lives on the device (min(*m_dev, M) rows are multiplied)
 };
 
 template <int DUMMY>
@@ -184,11 +185,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const long long per_split = (P.n_panels + P.split_k - 1) / P.split_k;
+  // a device-side row count shrinks the tile range (the operand buffers are sized for P.M rows)
+  const long long M = P.m_dev ? min((long long)max(__ldg(P.m_dev), 0), P.M) : P.M;
+  const long long n_tiles = P.m_dev ? ((M + 2 * GM_TM - 1) / (2 * GM_TM)) * P.tiles_n * P.split_k : P.n_tiles;
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
     uint32_t s = 0, ph = 0;
-    for (long long t = pair; t < P.n_tiles; t += n_pairs) {
+    for (long long t = pair; t < n_tiles; t += n_pairs) {
       const int ks = (int)(t % P.split_k);
       const long long tn = (t / P.split_k) % P.tiles_n, tm = t / ((long long)P.split_k * P.tiles_n);
       const long long p0 = ks * per_split, p1 = min(P.n_panels, p0 + per_split);
@@ -210,7 +214,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (leader) {
       uint32_t s = 0, ph = 0, it = 0;
       const uint32_t idesc = umma_idesc(2 * GM_TM, P.BN);
-      for (long long t = pair; t < P.n_tiles; t += n_pairs, ++it) {
+      for (long long t = pair; t < n_tiles; t += n_pairs, ++it) {
         const int ks = (int)(t % P.split_k);
         const long long p0 = ks * per_split, p1 = min(P.n_panels, p0 + per_split);
         const uint32_t as = it & 1u, around = it >> 1;
@@ -238,9 +242,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // =========================== epilogue: 4 warps, thread = row ===========================
     const int q = warp & 3;                       // TMEM lane quarter this warp may access (warps 2..5 -> 2,3,0,1)
-    const float inv = P.alpha / (pow2_scale(*P.amax_a) * pow2_scale(*P.amax_b));
+    const float inv = P.amax_a ? P.alpha / (pow2_scale(*P.amax_a) * pow2_scale(*P.amax_b)) : P.alpha;
     uint32_t it = 0;
-    for (long long t = pair; t < P.n_tiles; t += n_pairs, ++it) {
+    for (long long t = pair; t < n_tiles; t += n_pairs, ++it) {
       const int ks = (int)(t % P.split_k);
       const long long tn = (t / P.split_k) % P.tiles_n, tm = t / ((long long)P.split_k * P.tiles_n);
       const uint32_t as = it & 1u, around = it >> 1;
@@ -255,7 +259,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t v[16];
         tc_ld16(taddr + (uint32_t)c, v);
         tc_wait_ld();
-        if (row < P.M) {
+        if (row < M) {
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             const int col = col0 + c + 4 * j4;
@@ -369,10 +373,52 @@ int launch_gemm_f32(const float* A, int64_t lda, int transA, const float* B, int
   P.M = M; P.N = N; P.BN = BN; P.n_panels = n_panels; P.tiles_n = tiles_n; P.split_k = split_k;
   P.n_tiles = out_tiles * split_k;
   P.amax_a = amax_a; P.amax_b = amax_b; P.bias = bias; P.C = C; P.ldc = ldc; P.alpha = alpha; P.atomic = atomic;
+  P.m_dev = nullptr;
   const uint32_t b_stage = (uint32_t)(BN / 2) * GM_KC * 2;
   const size_t smem = (size_t)GM_STAGES * (GM_A_STAGE + ((b_stage + 1023u) & ~1023u)) + 8 * (2 * GM_STAGES + 4) + 16 + 1024;
   if ((rc = set_dyn_smem(reinterpret_cast<const void*>(&tc_gemm_kernel<0>), smem))) return rc;
   const long long pairs = std::min<long long>(n_pairs_max, P.n_tiles);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(pairs * 2));
+  cfg.blockDim = dim3(GM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  G2V_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<0>, tmA, tmB, P));
+  G2V_LAUNCH_CHECK("tc_gemm_kernel");
+  return G2V_OK;
+}
+
+// The product of two operands that are ALREADY in the kernel's fp16 layout (row-major [rows, kp16], kp16 a multiple
+// of 64, 256-byte aligned bases): C[m, n] = sum_j A16[m, j] B16[n, j], raw fp32 accumulators, for the first
+// min(*m_dev, m_cap) rows of A16.  The exact re-rank of the search uses it (g2v_tc.cu, refine pass): the row count
+// is produced on the device by the kernel before it, so the tile range is resolved inside the kernel.
+int launch_gemm_prepared(const __half* A16, const int* m_dev, long long m_cap, const __half* B16, int N, long long kp16,
+                         float* C, long long ldc, cudaStream_t st) {
+  const int sms = num_sms();
+  int tiles_n = (N + 255) / 256;
+  int BN = (int)(((long long)(N + tiles_n - 1) / tiles_n + 15) / 16 * 16);
+  if (BN < 16) BN = 16;
+  const long long tiles_m = (m_cap + 2 * GM_TM - 1) / (2 * GM_TM);
+  alignas(64) CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_map(&tmA, A16, (uint64_t)m_cap, (uint64_t)kp16, GM_KC, GM_TM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map(&tmB, B16, (uint64_t)N, (uint64_t)kp16, GM_KC, (uint32_t)(BN / 2), CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  GemmParams P;
+  P.M = m_cap; P.N = N; P.BN = BN; P.n_panels = kp16 / GM_KC; P.tiles_n = tiles_n; P.split_k = 1;
+  P.n_tiles = tiles_m * tiles_n;
+  P.amax_a = nullptr; P.amax_b = nullptr; P.bias = nullptr; P.C = C; P.ldc = ldc; P.alpha = 1.f; P.atomic = 0;
+  P.m_dev = m_dev;
+  const uint32_t b_stage = (uint32_t)(BN / 2) * GM_KC * 2;
+  const size_t smem = (size_t)GM_STAGES * (GM_A_STAGE + ((b_stage + 1023u) & ~1023u)) + 8 * (2 * GM_STAGES + 4) + 16 + 1024;
+  if ((rc = set_dyn_smem(reinterpret_cast<const void*>(&tc_gemm_kernel<0>), smem))) return rc;
+  const long long pairs = std::max<long long>(1, std::min<long long>(sms / 2, P.n_tiles));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(pairs * 2));
   cfg.blockDim = dim3(GM_THREADS);

@@ -874,16 +874,16 @@ __global__ void __launch_bounds__(256) full64_kernel(const ZT* __restrict__ z, c
 template <typename ZT, bool VEC, int R, int NP>
 static int launch_full_recheck_v(const ZT* z, const float* E, const void* cb, int K, int D, int Dz, const int32_t* list,
                                  const int32_t* count, int64_t max_rows, int32_t* idx,
-                                 unsigned long long* stats, cudaStream_t st) {
+                                 unsigned long long* stats, cudaStream_t st, int64_t handled) {
   const size_t smem = (size_t)R * ((D + 3) / 4 * 4) * sizeof(float);
-  long long batches = (max_rows + R - 1) / R;
+  long long batches = (max_rows - handled + R - 1) / R;
   long long cap = (long long)num_sms() * 4;
   const int grid = (int)(batches < 1 ? 1 : (batches < cap ? batches : cap));
   const float* ntab = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_tab_offset());
   const float* e2 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_e2_offset());
   if (smem > 40 * 1024)
     G2V_CUDA_CHECK(cudaFuncSetAttribute(full_recheck_kernel<ZT, VEC, R, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  full_recheck_kernel<ZT, VEC, R, NP><<<grid, FR_THREADS, smem, st>>>(z, E, e2, ntab, K, D, list, count, kFull64Cap, idx, stats, Dz);
+  full_recheck_kernel<ZT, VEC, R, NP><<<grid, FR_THREADS, smem, st>>>(z, E, e2, ntab, K, D, list, count, (int)handled, idx, stats, Dz);
   G2V_LAUNCH_CHECK("full_recheck_kernel");
   return G2V_OK;
 }
@@ -891,10 +891,11 @@ static int launch_full_recheck_v(const ZT* z, const float* E, const void* cb, in
 template <typename ZT>
 static int launch_full_recheck_t(const ZT* z, const float* E, const void* cb, int K, int D, int Dz, const int32_t* list,
                                  const int32_t* count, int64_t max_rows, int32_t* idx,
-                                 unsigned long long* stats, bool overflow_only, cudaStream_t st) {
+                                 unsigned long long* stats, bool overflow_only, cudaStream_t st, int64_t handled) {
   if (overflow_only) {
-    if (max_rows <= kFull64Cap) return G2V_OK;
+    if (max_rows <= handled) return G2V_OK;
   } else {
+    handled = kFull64Cap;
     const long long cap = max_rows < kFull64Cap ? max_rows : kFull64Cap;
     const long long lim = (long long)num_sms() * 8;
     const int g = (int)(cap < 1 ? 1 : (cap < lim ? cap : lim));
@@ -905,18 +906,18 @@ static int launch_full_recheck_t(const ZT* z, const float* E, const void* cb, in
   const bool vec = (D % 4 == 0) && aligned16(E);
   // small codebooks: 8 rows per CTA (more CTAs in flight, 4 partial sums -> tight fp32 bound);
   // large codebooks: 16 rows per CTA so each codebook row fetched from L2 serves more latents
-  if (!vec) return launch_full_recheck_v<ZT, false, 8, 1>(z, E, cb, K, D, Dz, list, count, max_rows, idx, stats, st);
-  if (K <= 2048) return launch_full_recheck_v<ZT, true, 8, 4>(z, E, cb, K, D, Dz, list, count, max_rows, idx, stats, st);
-  return launch_full_recheck_v<ZT, true, 16, 1>(z, E, cb, K, D, Dz, list, count, max_rows, idx, stats, st);
+  if (!vec) return launch_full_recheck_v<ZT, false, 8, 1>(z, E, cb, K, D, Dz, list, count, max_rows, idx, stats, st, handled);
+  if (K <= 2048) return launch_full_recheck_v<ZT, true, 8, 4>(z, E, cb, K, D, Dz, list, count, max_rows, idx, stats, st, handled);
+  return launch_full_recheck_v<ZT, true, 16, 1>(z, E, cb, K, D, Dz, list, count, max_rows, idx, stats, st, handled);
 }
 
 int launch_full_recheck(const void* z, int z_dtype, const float* E, const void* cb, int K, int D, int Dz, const int32_t* list,
                         const int32_t* count, int64_t max_rows, int32_t* idx, unsigned long long* stats,
-                        bool overflow_only, cudaStream_t st) {
+                        bool overflow_only, cudaStream_t st, int64_t handled) {
   switch (z_dtype) {
-    case G2V_F32: return launch_full_recheck_t(reinterpret_cast<const float*>(z), E, cb, K, D, Dz, list, count, max_rows, idx, stats, overflow_only, st);
-    case G2V_F16: return launch_full_recheck_t(reinterpret_cast<const __half*>(z), E, cb, K, D, Dz, list, count, max_rows, idx, stats, overflow_only, st);
-    case G2V_BF16: return launch_full_recheck_t(reinterpret_cast<const __nv_bfloat16*>(z), E, cb, K, D, Dz, list, count, max_rows, idx, stats, overflow_only, st);
+    case G2V_F32: return launch_full_recheck_t(reinterpret_cast<const float*>(z), E, cb, K, D, Dz, list, count, max_rows, idx, stats, overflow_only, st, handled);
+    case G2V_F16: return launch_full_recheck_t(reinterpret_cast<const __half*>(z), E, cb, K, D, Dz, list, count, max_rows, idx, stats, overflow_only, st, handled);
+    case G2V_BF16: return launch_full_recheck_t(reinterpret_cast<const __nv_bfloat16*>(z), E, cb, K, D, Dz, list, count, max_rows, idx, stats, overflow_only, st, handled);
     default: return G2V_ERR_DTYPE;
   }
 }
@@ -946,7 +947,7 @@ static int launch_search_simt_t(const ZT* z, int z_dtype, const float* E, const 
   }
   G2V_LAUNCH_CHECK("search_simt_kernel");
   if (pev1) G2V_CUDA_CHECK(cudaEventRecord(pev1, st));
-  return launch_full_recheck_t(z, E, cb, K, D, D, full_list, full_count, N, idx, stats, false, st);
+  return launch_full_recheck_t(z, E, cb, K, D, D, full_list, full_count, N, idx, stats, false, st, kFull64Cap);
 }
 
 // fp32 search of all rows; `full_list` (N ints) and `full_count` (1 int) are scratch

@@ -315,19 +315,19 @@ __device__ __forceinline__ void finish_row(const Cand& c1, const Cand& c2, const
 
 // Per-row constants from ||z||^2 and the squared norm of the fp16 rounding residual of the row.
 //   |dot_hat - dot| for a code of norm c:
-//     operand rounding (Cauchy-Schwarz on the measured residuals; ||r_e|| <= sfrac c):
-//          |r_z| c + |z| sfrac c + |r_z| sfrac c
+//     operand rounding (Cauchy-Schwarz on the measured residuals; ||r_e|| <= sfrac c + rsub):
+//          |r_z| c + (|z| + |r_z|) (sfrac c + rsub)
 //     tensor-core accumulation: (2^-19 alignment + one fp32 rounding per K step) |z| c
-//   = a1 c.  The epilogue evaluates it at the largest code norm that can still win the row.
+//   = a1 c + a0.  The epilogue evaluates it at the largest code norm that can still win the row.
 //   Fixed-point range: keys of codes that can still win lie in [-|z|^2, (|z| + c_min)^2]; anything
 //   larger saturates in the epilogue.
-__device__ __forceinline__ RowInfo make_rowinfo(float z2, float r2, float inv_scale_z, float sfrac, float e2min,
+__device__ __forceinline__ RowInfo make_rowinfo(float z2, float r2, float inv_scale_z, float sfrac, float rsub, float e2min,
                                                 float scale_e, int n_ksteps) {
   const float znorm = sqrtf(z2) * 1.0001f, rnorm = sqrtf(r2) * 1.0001f;
   const float acc = 1.9073486e-6f + (float)(n_ksteps + 2) * 1.1920929e-7f;
   RowInfo ri;
   ri.a1 = rnorm * (1.f + sfrac) + znorm * (sfrac + acc);
-  ri.a0 = 0.f;
+  ri.a0 = (znorm + rnorm) * rsub;
   ri.znorm = znorm;
   ri.z2 = z2;
   const float cmin = sqrtf(e2min);
@@ -562,7 +562,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int et = threadIdx.x - EPI_WARP0 * 32;     // 0..255
     uint32_t* xrow = xch + (size_t)r * 12;           // hand-off slot of this row (half 1 -> half 0)
     uint32_t it = 0, ti = 0;
-    const float h_sfrac = FUSED ? P.hdr->sfrac : 0.f, h_e2min = FUSED ? P.hdr->e2min : 0.f,
+    const float h_sfrac = FUSED ? P.hdr->sfrac : 0.f, h_rsub = FUSED ? P.hdr->rsub : 0.f, h_e2min = FUSED ? P.hdr->e2min : 0.f,
                 h_scale_e = FUSED ? P.hdr->scale_e : 1.f;
     for (int tile = group; tile < P.n_row_tiles; tile += n_groups, ++ti) {
       const long long row = ((long long)tile * CG + cta_rank) * TM + r;
@@ -572,7 +572,7 @@ tc_search_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // statistics of this tile's rows come from the converter warps (same CTA)
         mbar_wait(bar_rsfull(ti % RS_RING), (ti / RS_RING) & 1u);
         const float2 st = rowstat[(ti % RS_RING) * TM + r];
-        ri = make_rowinfo(st.x, st.y, 1.f, h_sfrac, h_e2min, h_scale_e, P.n_ksteps);
+        ri = make_rowinfo(st.x, st.y, 1.f, h_sfrac, h_rsub, h_e2min, h_scale_e, P.n_ksteps);
       } else {
         ri = valid ? P.rowinfo[row] : RowInfo{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       }
@@ -1075,7 +1075,7 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
       mbar_wait(bar_rsfull(ti % RS_RING), (ti / RS_RING) & 1u);
       float key_cS, key_S;
       {
-        const RowInfo r0 = make_rowinfo(rowstat[(ti % RS_RING) * TM + r].x, 0.f, 1.f, 0.f, P.hdr->e2min, P.hdr->scale_e, P.n_ksteps);
+        const RowInfo r0 = make_rowinfo(rowstat[(ti % RS_RING) * TM + r].x, 0.f, 1.f, 0.f, 0.f, P.hdr->e2min, P.hdr->scale_e, P.n_ksteps);
         key_cS = r0.cS; key_S = r0.S;
       }
       uint32_t m1[16], m2[16];
@@ -1122,7 +1122,7 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
         const long long row = ((long long)tile * 2 + cta_rank) * TM + r;
         const bool valid = row < P.N;
         const float2 st = rowstat[(ti % RS_RING) * TM + r];
-        const RowInfo ri = make_rowinfo(st.x, st.y, 1.f, P.hdr->sfrac, P.hdr->e2min, P.hdr->scale_e, P.n_ksteps);
+        const RowInfo ri = make_rowinfo(st.x, st.y, 1.f, P.hdr->sfrac, P.hdr->rsub, P.hdr->e2min, P.hdr->scale_e, P.n_ksteps);
         finish_row(c1, c2, c3, k4, ri, row, valid, P.K, P.ntab, P.flags, P.idx, P.pair_list, P.chain_list, P.full_list, P.counters);
       }
       asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
@@ -1321,81 +1321,96 @@ __global__ void __launch_bounds__(256) row_prep_kernel(const ZT* __restrict__ z,
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, off);
   if (lane == 0) {
-    const RowInfo ri = make_rowinfo(s2, r2, inv, hdr->sfrac, hdr->e2min, hdr->scale_e, n_ksteps);
+    const RowInfo ri = make_rowinfo(s2, r2, inv, hdr->sfrac, hdr->rsub, hdr->e2min, hdr->scale_e, n_ksteps);
     rowinfo[row] = ri;
   }
 }
 
-// exact re-rank of the two or three candidate codes of each listed row (one warp per entry, fp64);
-// all loads of an entry are issued before the first use.  Lowest index wins exact ties.
-template <typename ZT>
+// exact re-rank of the two or three candidate codes of each listed row (fp64).  LPE lanes share an entry, so a
+// warp keeps 32 / LPE entries in flight: the pass is bound by the latency of the row fetch (random rows, long
+// gone from L2), not by arithmetic.  The third code is only read when there is one.  Lowest index wins exact ties.
+template <typename ZT, int LPE>
 __device__ __forceinline__ void pair_entries(const ZT* __restrict__ z, const float* __restrict__ E, int D, int Dz,
                                              const int* __restrict__ pair_list, int n, int* __restrict__ idx) {
-  const int lane = threadIdx.x & 31;
-  const int wstride = (gridDim.x * blockDim.x) >> 5;
-  constexpr int U = 2;                                   // 2 x 128 columns per pass (registers -> occupancy)
+  constexpr int EPW = 32 / LPE;                          // entries per warp
+  constexpr int U = 2;                                   // float4 columns in flight per array (registers -> occupancy)
+  const int lane = threadIdx.x & 31, sub = lane / LPE, sl = lane % LPE;
+  const int wstride = (int)((gridDim.x * blockDim.x) >> 5);
   // rows have Dz <= D columns (zero beyond: a folded codebook is wider than the rows it is searched with)
   const bool vec = (D % 4 == 0) && (Dz % 4 == 0) && sizeof(ZT) == 4 && ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(E)) & 15) == 0;
-  for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n; e += wstride) {
-    const int4 ent = reinterpret_cast<const int4*>(pair_list)[e];
+  for (int e0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * EPW; e0 < n; e0 += wstride * EPW) {
+    const int e = e0 + sub;
+    const bool live = e < n;
+    const int4 ent = live ? reinterpret_cast<const int4*>(pair_list)[e] : make_int4(0, 0, 0, -1);
     const int row = ent.x, a = ent.y, b = ent.z, c = ent.w;
+    const bool has_c = c >= 0;
     const ZT* zr = z + (size_t)row * Dz;
     const float* ea = E + (size_t)a * D;
     const float* eb = E + (size_t)b * D;
-    const float* ec = E + (size_t)(c >= 0 ? c : a) * D;
+    const float* ec = E + (size_t)(has_c ? c : a) * D;
     double da = 0.0, db = 0.0, dc = 0.0;
-    if (vec) {
-      const float* zf = reinterpret_cast<const float*>(zr);
-      for (int j0 = lane * 4; j0 < D; j0 += 128 * U) {
-        float4 zv[U], av[U], bv[U], cv[U];
+    if (live) {
+      if (vec) {
+        const float* zf = reinterpret_cast<const float*>(zr);
+        for (int j0 = sl * 4; j0 < D; j0 += LPE * 4 * U) {
+          float4 zv[U], av[U], bv[U], cv[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int j = j0 + 128 * u;
-          if (j < D) {
-            zv[u] = j < Dz ? __ldg(reinterpret_cast<const float4*>(zf + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            av[u] = __ldg(reinterpret_cast<const float4*>(ea + j));
-            bv[u] = __ldg(reinterpret_cast<const float4*>(eb + j));
-            cv[u] = (c >= 0) ? __ldg(reinterpret_cast<const float4*>(ec + j)) : av[u];
-          } else {
+          for (int u = 0; u < U; ++u) {
+            const int j = j0 + LPE * 4 * u;
             zv[u] = av[u] = bv[u] = cv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < D) {
+              if (j < Dz) zv[u] = __ldg(reinterpret_cast<const float4*>(zf + j));
+              av[u] = __ldg(reinterpret_cast<const float4*>(ea + j));
+              bv[u] = __ldg(reinterpret_cast<const float4*>(eb + j));
+              if (has_c) cv[u] = __ldg(reinterpret_cast<const float4*>(ec + j));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const float zz[4] = {zv[u].x, zv[u].y, zv[u].z, zv[u].w};
+            const float aa[4] = {av[u].x, av[u].y, av[u].z, av[u].w};
+            const float bb[4] = {bv[u].x, bv[u].y, bv[u].z, bv[u].w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const double zd = (double)zz[t];
+              const double xa = zd - (double)aa[t], xb = zd - (double)bb[t];
+              da = fma(xa, xa, da);
+              db = fma(xb, xb, db);
+            }
+            if (has_c) {
+              const float cc[4] = {cv[u].x, cv[u].y, cv[u].z, cv[u].w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const double xc = (double)zz[t] - (double)cc[t];
+                dc = fma(xc, xc, dc);
+              }
+            }
           }
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const float zz[4] = {zv[u].x, zv[u].y, zv[u].z, zv[u].w};
-          const float aa[4] = {av[u].x, av[u].y, av[u].z, av[u].w};
-          const float bb[4] = {bv[u].x, bv[u].y, bv[u].z, bv[u].w};
-          const float cc[4] = {cv[u].x, cv[u].y, cv[u].z, cv[u].w};
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const double xa = (double)zz[t] - (double)aa[t], xb = (double)zz[t] - (double)bb[t];
-            const double xc = (double)zz[t] - (double)cc[t];
-            da = fma(xa, xa, da);
-            db = fma(xb, xb, db);
+      } else {
+        for (int j = sl; j < D; j += LPE) {
+          const double zv = j < Dz ? (double)ld_f32(zr + j) : 0.0;
+          const double xa = zv - (double)__ldg(ea + j), xb = zv - (double)__ldg(eb + j);
+          da = fma(xa, xa, da);
+          db = fma(xb, xb, db);
+          if (has_c) {
+            const double xc = zv - (double)__ldg(ec + j);
             dc = fma(xc, xc, dc);
           }
         }
       }
-    } else {
-      for (int j = lane; j < D; j += 32) {
-        const double zv = j < Dz ? (double)ld_f32(zr + j) : 0.0;
-        const double xa = zv - (double)__ldg(ea + j), xb = zv - (double)__ldg(eb + j), xc = zv - (double)__ldg(ec + j);
-        da = fma(xa, xa, da);
-        db = fma(xb, xb, db);
-        dc = fma(xc, xc, dc);
-      }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = LPE / 2; o > 0; o >>= 1) {
       da += __shfl_xor_sync(0xffffffffu, da, o);
       db += __shfl_xor_sync(0xffffffffu, db, o);
       dc += __shfl_xor_sync(0xffffffffu, dc, o);
     }
-    if (lane == 0) {
+    if (live && sl == 0) {
       int best = a;
       double dbest = da;
       if (db < dbest || (db == dbest && b < best)) { best = b; dbest = db; }
-      if (c >= 0 && (dc < dbest || (dc == dbest && c < best))) { best = c; dbest = dc; }
+      if (has_c && (dc < dbest || (dc == dbest && c < best))) { best = c; dbest = dc; }
       idx[row] = best;
     }
   }
@@ -1455,6 +1470,254 @@ __device__ __forceinline__ void chain_entries(const ZT* __restrict__ z, const fl
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// refine pass: the listed WHOLE rows, a second time on the tensor cores at fp32 accuracy
+// ------------------------------------------------------------------------------------------
+// A whole-row re-rank costs K x D fp64 operations; one row in a hundred ends up there (K = 400, iid rows) and
+// those rows were most of the re-rank time (and ALL of the step for a degenerate EMA codebook, where most rows
+// are uncertain at fp16 accuracy).  The listed rows therefore take a second tensor-core pass first:
+//   refine_prep_kernel   gathers the listed rows and the codes, each scaled by its OWN power of two (largest
+//                        entry in [256, 512)), split into fp16 hi + lo terms laid out for the 3-term product
+//                        (g2v_gemm.cu):  A' = [hi | lo | hi],  B' = [hi | hi | lo]
+//   tc_gemm_kernel       dots[i, k] = A'_i . B'_k for the listed rows (row count read on the device)
+//   rerank_kernel        per listed row: d^_k = e2_k - 2 dots[i, k] / (s_i t_k); every code whose lower bound
+//                        d^_k - err_k does not exceed min_k (d^_k + err_k) is evaluated exactly in fp64
+//                        (usually one or two codes), lowest index winning exact ties.
+// Error of one dot product, relative to |z| |e_k| (u = 2^-11, fp16 unit roundoff; x = scaled entry, |x| < 512):
+//   hi = rn(x), lo = rn(x - hi):  |lo| <= u |x| + 2^-25,  |x - hi - lo| <= u^2 |x| + 2^-25   (2^-25: fp16 subnormal grid)
+//   with the largest entry >= 256 the 2^-25 terms add < 2.6e-9 to either ratio:  lam = 4.8829e-4,  rho = 2.411e-7
+//   dropped lo.lo term + residuals:  lam^2 + 2 rho + rho^2 <= 7.3e-7
+//   tensor-core accumulation (same model as the first pass): 1.003 (2^-19 + (k-steps + 2) 2^-23)
+// The comparison itself runs in fp32: e2_k carries one rounding (2^-24 e2_k), the fma and the +-err one each.
+struct RefineRow {
+  float inv_s;      // 1 / s_i  (power of two)
+  float znorm;      // upper bound of |z_i|
+  float pad0, pad1;
+};
+
+constexpr int64_t kRefineMinRows = 32768;          // below this a step is launch-bound: keep the two-launch re-rank
+// The listed rows take the pass when there is enough fp64 work to save (rows x codes): three dependent launches
+// cost ~35 us, K x D fp64 operations per row cost ~0.25 ns per code.  Evaluated on the device by every kernel
+// involved, from the same counter, so that they agree.  Below the threshold fewer than kFull64Cap rows are listed
+// (K >= 64), i.e. rerank_kernel's own fp64 path covers all of them.
+constexpr long long kRefineMinWork = 131072;
+__device__ __forceinline__ int refine_count(int listed, int K, int cap) {
+  const int n = min(max(listed, 0), cap);
+  return (long long)n * K >= kRefineMinWork ? n : 0;
+}
+constexpr size_t kRefineBudget = (size_t)4 << 30;  // bytes of workspace the pass may claim (of 180 GB)
+
+struct RefineWs {
+  long long cap;        // listed rows the pass can take (0 = pass disabled); the rest goes to the batched fp32+fp64 kernel
+  int kp, ldc;          // fp16 per operand segment (D rounded up to 64), row pitch of the dots
+  size_t invt, rows, A, B, C, total;      // offsets relative to the start of the refine region
+};
+inline size_t al256r(size_t v) { return (v + 255) / 256 * 256; }
+RefineWs refine_ws(int64_t N, int K, int D) {
+  RefineWs r = {};
+  if (N < kRefineMinRows || D > 512 || K < 64) return r;
+  r.kp = round_up(D, 64);
+  r.ldc = round_up(K, 4);
+  const size_t per_row = sizeof(RefineRow) + (size_t)3 * r.kp * 2 + (size_t)r.ldc * 4;
+  long long cap = (long long)(kRefineBudget / per_row);
+  if (cap > N) cap = N;
+  cap = cap / 256 * 256;
+  if (cap < 256) return r;
+  r.cap = cap;
+  r.invt = 0;
+  r.rows = r.invt + al256r((size_t)K * 4);
+  r.A = r.rows + al256r((size_t)cap * sizeof(RefineRow));
+  r.B = r.A + al256r((size_t)cap * 3 * r.kp * 2);
+  r.C = r.B + al256r((size_t)K * 3 * r.kp * 2);
+  r.total = r.C + al256r((size_t)cap * r.ldc * 4);
+  return r;
+}
+
+// one warp per code (tasks [0, K)) or listed row (tasks [K, K + n)); D <= 512: a lane holds 4 x 4 entries
+template <typename ZT>
+__global__ void __launch_bounds__(256) refine_prep_kernel(const ZT* __restrict__ z, int Dz, const float* __restrict__ E, int K, int D,
+                                                          int kp, const int* __restrict__ full_list,
+                                                          const int* __restrict__ full_count, int cap, __half* __restrict__ A16,
+                                                          __half* __restrict__ B16, float* __restrict__ invt,
+                                                          RefineRow* __restrict__ rows, int* __restrict__ n_eff) {
+  const int lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *n_eff = refine_count(*full_count, K, cap);   // the GEMM's row count
+  const int gwarp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+  const int n = refine_count(*full_count, K, cap);
+  if (n == 0) return;
+  for (int task = gwarp; task < K + n; task += nwarps) {
+    const bool is_code = task < K;
+    const int i = is_code ? task : task - K;
+    float v[4][4];
+    float amax = 0.f, n2 = 0.f;
+    if (is_code) {
+      const float* src = E + (size_t)i * D;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int j = 4 * (lane + 32 * u) + t;
+          v[u][t] = j < D ? __ldg(src + j) : 0.f;
+        }
+    } else {
+      const ZT* src = z + (size_t)full_list[i] * Dz;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int j = 4 * (lane + 32 * u) + t;
+          v[u][t] = j < Dz ? ld_f32(src + j) : 0.f;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        amax = fmaxf(amax, fabsf(v[u][t]));        // fmaxf drops a NaN: the split below still carries it into the dots
+        n2 = fmaf(v[u][t], v[u][t], n2);
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+    }
+    float sc = 1.f;
+    if (amax > 0.f && isfinite(amax)) {
+      int e;
+      frexpf(amax, &e);
+      sc = ldexpf(1.f, max(min(9 - e, 120), -120));
+    }
+    __half* dst = (is_code ? B16 : A16) + (size_t)i * 3 * kp;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = 4 * (lane + 32 * u);
+      if (c < kp) {
+        __half2 h[2], l[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const float x0 = v[u][2 * q] * sc, x1 = v[u][2 * q + 1] * sc;
+          h[q] = __floats2half2_rn(x0, x1);
+          const float2 hf = __half22float2(h[q]);
+          l[q] = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+        }
+        uint2 hi, lo;
+        hi.x = *reinterpret_cast<const uint32_t*>(&h[0]); hi.y = *reinterpret_cast<const uint32_t*>(&h[1]);
+        lo.x = *reinterpret_cast<const uint32_t*>(&l[0]); lo.y = *reinterpret_cast<const uint32_t*>(&l[1]);
+        *reinterpret_cast<uint2*>(dst + c) = hi;
+        *reinterpret_cast<uint2*>(dst + kp + c) = is_code ? hi : lo;
+        *reinterpret_cast<uint2*>(dst + 2 * kp + c) = is_code ? lo : hi;
+      }
+    }
+    if (lane == 0) {
+      if (is_code) {
+        invt[i] = 1.f / sc;
+      } else {
+        RefineRow r;
+        r.inv_s = 1.f / sc;
+        r.znorm = sqrtf(n2) * 1.0001f;
+        r.pad0 = r.pad1 = 0.f;
+        rows[i] = r;
+      }
+    }
+  }
+}
+
+struct RefineArgs {
+  const float* dots;          // [cap][ldc] raw accumulators, null = pass disabled
+  const float* invt;          // [K]
+  const RefineRow* rows;      // [cap]
+  const float* e2;            // [K] |e_k|^2 (fp64 accumulated, rounded once)
+  int ldc, cap;
+  float beta;                 // dot-product error relative to |z| |e_k|
+};
+
+// one warp per listed row: candidates from the fp32-accurate dots, then fp64 on the candidates
+template <typename ZT>
+__global__ void __launch_bounds__(256, 4) refine_rows_kernel(const ZT* __restrict__ z, const float* __restrict__ E, int K, int D, int Dz,
+                                                             const int* __restrict__ full_list, const int* __restrict__ full_count,
+                                                             const RefineArgs R, int* __restrict__ idx, unsigned long long* stats) {
+  const int lane = threadIdx.x & 31;
+  const int n = refine_count(*full_count, K, R.cap);
+  unsigned long long* n_exact = stats ? stats + G2V_STAT_REFINE_EXACT : nullptr;
+  if (stats && blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(stats + G2V_STAT_REFINE_ROWS, (unsigned long long)n);
+  const int wstride = (int)((gridDim.x * blockDim.x) >> 5);
+  unsigned long long exact = 0;
+  for (int e = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); e < n; e += wstride) {
+    const int row = full_list[e];
+    const RefineRow ri = R.rows[e];
+    const float* dr = R.dots + (size_t)e * R.ldc;
+    const float c1 = (2.f * R.beta + 4.7683716e-7f) * ri.znorm, c2 = 4.7683716e-7f;    // 2^-21: the fp32 steps of the comparison
+    auto bounds = [&](int k, float& lo, float& hi) {
+      const float e2k = __ldg(R.e2 + k);
+      const float dot = (__ldg(dr + k) * ri.inv_s) * __ldg(R.invt + k);
+      const float d = fmaf(-2.f, dot, e2k);
+      const float err = fmaf(c1, sqrtf(e2k) * 1.0001f, c2 * e2k);
+      lo = d - err;
+      hi = d + err;
+    };
+    constexpr int UK = 4;                       // 32-code groups in flight (the loads of a row are a dependent chain otherwise)
+    float U = INFINITY;
+    for (int k0 = lane; k0 < K; k0 += 32 * UK) {
+      float lo[UK], hi[UK];
+#pragma unroll
+      for (int u = 0; u < UK; ++u) {
+        hi[u] = INFINITY;
+        if (k0 + 32 * u < K) bounds(k0 + 32 * u, lo[u], hi[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < UK; ++u) U = fminf(U, hi[u]);      // a NaN bound is ignored here and becomes a candidate below
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) U = fminf(U, __shfl_xor_sync(0xffffffffu, U, o));
+    const ZT* zr = z + (size_t)row * Dz;
+    double best = INFINITY;
+    int besti = 0x7fffffff;
+    for (int k0 = 0; k0 < K; k0 += 32 * UK) {
+      bool cand[UK];
+#pragma unroll
+      for (int u = 0; u < UK; ++u) {
+        const int k = k0 + 32 * u + lane;
+        cand[u] = false;
+        if (k < K) {
+          float lo, hi;
+          bounds(k, lo, hi);
+          cand[u] = !(lo > U);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UK; ++u) {
+        unsigned mask = __ballot_sync(0xffffffffu, cand[u]);
+        while (mask) {
+          const int kk = k0 + 32 * u + __ffs((int)mask) - 1;
+          mask &= mask - 1;
+          const float* er = E + (size_t)kk * D;
+          double s = 0.0;
+          for (int j0 = lane; j0 < D; j0 += 32 * 8) {
+            float zv[8], ev[8];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+              const int j = j0 + 32 * v;
+              zv[v] = j < Dz ? ld_f32(zr + j) : 0.f;
+              ev[v] = j < D ? __ldg(er + j) : 0.f;
+            }
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+              const double df = (double)zv[v] - (double)ev[v];
+              s = fma(df, df, s);
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          if (s < best) { best = s; besti = kk; }       // ascending k: the first of equal distances stays
+          ++exact;
+        }
+      }
+    }
+    if (lane == 0) idx[row] = besti == 0x7fffffff ? 0 : besti;    // every distance NaN: index 0, as torch.argmin
+  }
+  if (n_exact && lane == 0 && exact) atomicAdd(n_exact, exact);
+}
+
 // One launch for every exact re-rank of the tensor-core pass: the listed whole rows first (fp64 over all K
 // codes; each row split into `slices` CTAs that combine through `scratch`, the last one to arrive writes the
 // index), then the chain entries, then the two/three-candidate entries.  All CTAs walk all three lists, so
@@ -1465,6 +1728,10 @@ struct RerankSlot {
   int pad;
 };
 constexpr int kRerankMaxSlices = 32;
+#ifndef G2V_PAIR_LANES
+#define G2V_PAIR_LANES 8
+#endif
+constexpr int kPairLanes = G2V_PAIR_LANES;        // lanes per two/three-candidate entry (measured: see DESIGN.md)
 constexpr size_t kRerankScratchBytes = (size_t)kFull64Cap * kRerankMaxSlices * sizeof(RerankSlot);
 constexpr size_t kRerankArriveBytes = (size_t)kFull64Cap * sizeof(int);
 
@@ -1473,13 +1740,15 @@ __global__ void __launch_bounds__(256, 4) rerank_kernel(const ZT* __restrict__ z
                                                      const int* __restrict__ pair_list, const int* __restrict__ chain_list,
                                                      const int* __restrict__ full_list, const int* __restrict__ counters,
                                                      int slices, RerankSlot* scratch, int* arrive, int* __restrict__ idx,
-                                                     unsigned long long* stats) {
+                                                     unsigned long long* stats, const int refined /* cap of the refine pass, 0 = none */) {
   extern __shared__ __align__(16) unsigned char rr_smem[];
   float* zs = reinterpret_cast<float*>(rr_smem);            // one row, zero padded to a multiple of 32
   __shared__ double bv[8];
   __shared__ int bi[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n_pair = counters[0], n_full = min(counters[1], kFull64Cap), n_chain = counters[2];
+  const int n_pair = counters[0], n_chain = counters[2];
+  // whole rows: straight fp64 here unless the refine pass takes them (refine_rows_kernel, on its own stream)
+  const int n_full = (refined && refine_count(counters[1], K, refined) > 0) ? 0 : min(counters[1], kFull64Cap);
 
   // ---- whole rows ----
   const int Dp = (D + 31) & ~31;
@@ -1535,7 +1804,7 @@ __global__ void __launch_bounds__(256, 4) rerank_kernel(const ZT* __restrict__ z
       for (int w = 1; w < 8; ++w)
         if (bv[w] < v || (bv[w] == v && bi[w] < id)) { v = bv[w]; id = bi[w]; }
       if (slices == 1) {
-        idx[row] = id;
+        idx[row] = id == 0x7fffffff ? 0 : id;       // every distance NaN: index 0, as torch.argmin
       } else {
         RerankSlot* slot = scratch + (size_t)e * slices;
         slot[sl].v = v;
@@ -1550,7 +1819,7 @@ __global__ void __launch_bounds__(256, 4) rerank_kernel(const ZT* __restrict__ z
             const int qi = vs[q].i;
             if (qv < v || (qv == v && qi < id)) { v = qv; id = qi; }
           }
-          idx[row] = id;
+          idx[row] = id == 0x7fffffff ? 0 : id;
           arrive[e] = 0;                                     // ready for the next search on this workspace
         }
       }
@@ -1559,7 +1828,7 @@ __global__ void __launch_bounds__(256, 4) rerank_kernel(const ZT* __restrict__ z
   // ---- chains, then candidate pairs / triples ----
   if (K >= 2048) chain_entries<ZT, true>(z, E, K, D, Dz, chain_list, n_chain, idx, bv, bi);
   else chain_entries<ZT, false>(z, E, K, D, Dz, chain_list, n_chain, idx, bv, bi);
-  pair_entries<ZT>(z, E, D, Dz, pair_list, n_pair, idx);
+  pair_entries<ZT, kPairLanes>(z, E, D, Dz, pair_list, n_pair, idx);
   if (stats && blockIdx.x == 0 && threadIdx.x == 0) {
     atomicAdd(stats + G2V_STAT_PAIR_RECHECK, (unsigned long long)(n_pair + n_chain));
     atomicAdd(stats + G2V_STAT_FALLBACK_ROWS, (unsigned long long)counters[1]);
@@ -1600,10 +1869,33 @@ const Tuning& tuning() {
   return t;
 }
 
-struct TcWs {
-  size_t z16, rowinfo, pairs, fulls, chains, counters, scratch, total;
+// one side stream + fork / join events per (host thread, device), created on first use and kept
+struct SideStream {
+  cudaStream_t s;
+  cudaEvent_t fork, join;
 };
-TcWs tc_ws(int64_t N, int D) {
+SideStream* side_stream() {
+  constexpr int kMaxDev = 64;
+  thread_local SideStream tab[kMaxDev];
+  thread_local bool made[kMaxDev] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
+  if (!made[dev]) {
+    SideStream t;
+    if (cudaStreamCreateWithFlags(&t.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&t.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&t.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    tab[dev] = t;
+    made[dev] = true;
+  }
+  return &tab[dev];
+}
+
+struct TcWs {
+  size_t z16, rowinfo, pairs, fulls, chains, counters, scratch, refine, total;
+  RefineWs rf;
+};
+TcWs tc_ws(int64_t N, int K, int D) {
   const int Dp = round_up(D, 16);
   TcWs w;
   w.z16 = 0;
@@ -1613,7 +1905,9 @@ TcWs tc_ws(int64_t N, int D) {
   w.chains = w.fulls + al256((size_t)N * 4);
   w.counters = w.chains + al256((size_t)N * 16);       // 256 bytes of list counters, then the re-rank arrive counters
   w.scratch = w.counters + 256 + al256(kRerankArriveBytes);
-  w.total = w.scratch + al256(kRerankScratchBytes);
+  w.refine = w.scratch + al256(kRerankScratchBytes);
+  w.rf = refine_ws(N, K, D);
+  w.total = w.refine + w.rf.total;
   return w;
 }
 
@@ -1622,8 +1916,39 @@ TcWs tc_ws(int64_t N, int D) {
 template <typename ZT>
 int run_recheck(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, int K, int D, int Dz, int* pairs, int* chains,
                 int* fulls, int* counters, void* scratch, int32_t* idx, unsigned long long* stats, unsigned flags,
-                cudaStream_t st) {
+                cudaStream_t st, const RefineWs& rf, char* rbase) {
   if (flags & G2V_NO_RECHECK) return G2V_OK;
+  // The refine pass of the listed whole rows runs on a side stream next to the pair / chain re-rank (they write
+  // disjoint rows of idx): three small dependent launches that would otherwise sit in front of the main kernel.
+  const bool refine = rf.cap > 0 && !(flags & G2V_NO_REFINE);
+  SideStream* side = nullptr;
+  if (refine) {
+    side = side_stream();
+    if (!side) return G2V_ERR_CUDA;
+    G2V_CUDA_CHECK(cudaEventRecord(side->fork, st));
+    G2V_CUDA_CHECK(cudaStreamWaitEvent(side->s, side->fork, 0));
+    float* invt = reinterpret_cast<float*>(rbase + rf.invt);
+    RefineRow* rows = reinterpret_cast<RefineRow*>(rbase + rf.rows);
+    __half* A16 = reinterpret_cast<__half*>(rbase + rf.A);
+    __half* B16 = reinterpret_cast<__half*>(rbase + rf.B);
+    float* dots = reinterpret_cast<float*>(rbase + rf.C);
+    // codes + a guess of the listed rows (a few per cent of N); the grid-stride loop takes whatever is listed
+    const long long tasks = (long long)K + std::min<long long>(rf.cap, N / 16 + 1024);
+    const int pgrid = (int)std::max<long long>(1, std::min<long long>((tasks + 7) / 8, (long long)num_sms() * 8));
+    int* n_eff = counters + 8;              // inside the 256 bytes of list counters that every search zeroes
+    refine_prep_kernel<ZT><<<pgrid, 256, 0, side->s>>>(z, Dz, E, K, D, rf.kp, fulls, counters + 1, (int)rf.cap, A16, B16, invt, rows, n_eff);
+    G2V_LAUNCH_CHECK("refine_prep_kernel");
+    const int rc = launch_gemm_prepared(A16, n_eff, rf.cap, B16, K, (long long)3 * rf.kp, dots, rf.ldc, side->s);
+    if (rc) return rc;
+    RefineArgs RA;
+    RA.dots = dots; RA.invt = invt; RA.rows = rows;
+    RA.e2 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_e2_offset());
+    RA.ldc = rf.ldc; RA.cap = (int)rf.cap;
+    RA.beta = 7.3e-7f + 1.003f * (1.9073486e-6f + (float)(3 * rf.kp / 16 + 2) * 1.1920929e-7f);
+    refine_rows_kernel<ZT><<<num_sms() * 4, 256, 0, side->s>>>(z, E, K, D, Dz, fulls, counters + 1, RA, idx, stats);
+    G2V_LAUNCH_CHECK("refine_rows_kernel");
+    G2V_CUDA_CHECK(cudaEventRecord(side->join, side->s));
+  }
   // a whole row costs K x D fp64 operations on one CTA: split it so that a handful of rows does not become
   // the latency of the step (~64 codes per warp pass)
   int slices = K / 256;
@@ -1636,9 +1961,12 @@ int run_recheck(const ZT* z, int z_dtype, const float* E, const void* cb, int64_
   const long long want = (N + 7) / 8, cap = (long long)num_sms() * 4;
   const int rgrid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
   rerank_kernel<ZT><<<rgrid, 256, smem, st>>>(z, E, K, D, Dz, pairs, chains, fulls, counters, slices,
-                                                     reinterpret_cast<RerankSlot*>(scratch), arrive, idx, stats);
+                                                     reinterpret_cast<RerankSlot*>(scratch), arrive, idx, stats, refine ? (int)rf.cap : 0);
   G2V_LAUNCH_CHECK("rerank_kernel");
-  return launch_full_recheck(z, z_dtype, E, cb, K, D, Dz, fulls, counters + 1, N, idx, stats, true, st);
+  const int rc = launch_full_recheck(z, z_dtype, E, cb, K, D, Dz, fulls, counters + 1, N, idx, stats, true, st,
+                                     refine ? (int64_t)rf.cap : (int64_t)kFull64Cap);
+  if (refine) G2V_CUDA_CHECK(cudaStreamWaitEvent(st, side->join, 0));
+  return rc;
 }
 
 // "tmem" variant: geometry, or false if the shape does not qualify (fp32 rows read through TMA: D % 4 == 0
@@ -1721,7 +2049,7 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
            unsigned long long* stats, void* ws, unsigned flags, cudaStream_t st) {
   const int Dp = round_up(D, 16), Kp = round_up(K, 256);
   const unsigned variant = flags & G2V_TC_VARIANT_MASK;      // test / benchmark aid: pin the sweep kernel
-  const TcWs w = tc_ws(N, D);
+  const TcWs w = tc_ws(N, K, D);
   char* base = reinterpret_cast<char*>(ws);
   __half* z16 = reinterpret_cast<__half*>(base + w.z16);
   RowInfo* rowinfo = reinterpret_cast<RowInfo*>(base + w.rowinfo);
@@ -1762,7 +2090,7 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
       const int rc = launch_tmem<ZT>(R, z, e16, Kp, st);
       if (rc) return rc;
       if (pev1) G2V_CUDA_CHECK(cudaEventRecord(pev1, st));
-      return run_recheck(z, z_dtype, E, cb, N, K, D, Dz, pairs, chains, fulls, counters, base + w.scratch, idx, stats, flags, st);
+      return run_recheck(z, z_dtype, E, cb, N, K, D, Dz, pairs, chains, fulls, counters, base + w.scratch, idx, stats, flags, st, w.rf, base + w.refine);
     }
   }
   if (Dz != D) {
@@ -1886,7 +2214,7 @@ int run_tc(const ZT* z, int z_dtype, const float* E, const void* cb, int64_t N, 
   G2V_LAUNCH_CHECK("tc_search_kernel");
   if (pev1) G2V_CUDA_CHECK(cudaEventRecord(pev1, st));
 
-  return run_recheck(z, z_dtype, E, cb, N, K, D, Dz, pairs, chains, fulls, counters, base + w.scratch, idx, stats, flags, st);
+  return run_recheck(z, z_dtype, E, cb, N, K, D, Dz, pairs, chains, fulls, counters, base + w.scratch, idx, stats, flags, st, w.rf, base + w.refine);
 }
 
 }  // namespace
@@ -1901,7 +2229,7 @@ bool tc_supported(int K, int D) {
 
 size_t tc_workspace_bytes(int64_t N, int K, int D, int z_dtype) {
   (void)K; (void)z_dtype;
-  return tc_ws(N, D).total;
+  return tc_ws(N, K, D).total;
 }
 
 int launch_search_tc(const void* z, int z_dtype, const float* E, const void* cb, int64_t N, int K, int D,
@@ -1909,7 +2237,7 @@ int launch_search_tc(const void* z, int z_dtype, const float* E, const void* cb,
                      cudaStream_t st, int Dz) {
   if (Dz <= 0) Dz = D;
   if (!tc_supported(K, D)) return G2V_ERR_UNSUPPORTED;
-  if (ws_bytes < tc_ws(N, D).total) return G2V_ERR_WORKSPACE;
+  if (ws_bytes < tc_ws(N, K, D).total) return G2V_ERR_WORKSPACE;
   switch (z_dtype) {
     case G2V_F32: return run_tc(reinterpret_cast<const float*>(z), z_dtype, E, cb, N, K, D, Dz, idx, stats, ws, flags, st);
     case G2V_F16: return run_tc(reinterpret_cast<const __half*>(z), z_dtype, E, cb, N, K, D, Dz, idx, stats, ws, flags, st);

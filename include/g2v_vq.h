@@ -51,6 +51,8 @@ extern "C" {
 #define G2V_ALGO_TC 2u          /* tcgen05 tensor-core path, error if unsupported */
 #define G2V_ALGO_MASK 3u
 #define G2V_NO_RECHECK 4u       /* keep the fast-pass winner (bf16/fp16 "fast" variant) */
+#define G2V_NO_REFINE 8u        /* test / benchmark aid: whole-row re-ranks go straight to fp64 instead of through the
+                                 * tensor-core refine pass (results are identical) */
 /* test / benchmark aid: pin the tensor-core sweep kernel (results are identical; a variant that does not cover
  * the shape falls back to the automatic choice) */
 #define G2V_TC_VARIANT_MASK (7u << 8)
@@ -64,6 +66,8 @@ extern "C" {
 #define G2V_STAT_PAIR_RECHECK 1 /* rows whose top-2 were re-ranked exactly (fp64)     */
 #define G2V_STAT_FULL_RECHECK 2 /* rows whose whole distance row was recomputed (fp64) */
 #define G2V_STAT_FALLBACK_ROWS 3/* rows the tensor-core pass handed to the fp32 path   */
+#define G2V_STAT_REFINE_ROWS 4  /* listed whole rows that took the fp32-accurate tensor-core refine pass */
+#define G2V_STAT_REFINE_EXACT 5 /* fp64 code evaluations the refine pass needed for them */
 
 int g2v_version(void);
 const char* g2v_strerror(int code);

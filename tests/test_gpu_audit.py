@@ -173,3 +173,57 @@ def test_narrow_rows_against_a_wider_codebook(N, K, D, extra, dtype):
     exact = g.vq_search_exact(zw, E)
     a = S.audit(zw, E, idx, exact, eps_tie=2.0 ** -40)
     assert a["hard"] == 0, (a, stats.cpu().tolist())
+
+
+def test_dead_codes_do_not_push_live_rows_into_the_exact_fallback():
+    """A codebook whose largest entries sit 2^22 above the codes that win rows (dead EMA codes, or the norm
+    coordinate of a folded codebook): the fp16 copy is scaled to the top of the fp16 range and its residual is
+    split into a relative and an absolute part, so live rows still certify in the tensor-core pass."""
+    g, L = _g()
+    K, D, N = 512, 400, 131072
+    E = S.codebook("uniform1", K, D, DEV, seed=8) * 0.2
+    E[::23] *= 4.0e6                                            # 23 codes nobody can reach
+    E[7] *= 1e-3                                                # and one with a tiny norm
+    z = S.latents("gru", N, D, DEV, seed=9) * 0.3
+    want = g.vq_search_exact(z, E)
+    cb = g.prepare_codebook(E)
+    for name in ("auto", "prep", "simt"):
+        stats = torch.zeros(8, dtype=torch.int64, device=DEV)
+        idx = g.vq_search(z, E, cb, flags=_variants(L)[name], stats=stats)
+        a = S.audit(z, E, idx, want, eps_tie=2.0 ** -40)
+        assert a["hard"] == 0, (name, a)
+        st = stats.cpu().numpy()
+        if name != "simt":
+            assert st[L.STAT_FALLBACK_ROWS] < N // 10, (name, st)
+
+
+@pytest.mark.parametrize("cbk,lat,K", [("normal", "iid", 400), ("ema_degenerate", "gru", 512), ("uniform1", "clustered", 1000)])
+def test_refine_pass_gives_the_same_indices_as_straight_fp64(cbk, lat, K):
+    """Whole-row re-ranks take a second, fp32-accurate tensor-core pass (split-fp16 operands) before fp64 touches
+    them; G2V_NO_REFINE sends them straight to fp64.  Both are exact, so the indices are identical."""
+    g, L = _g()
+    D, N = 400, 131072
+    E = S.codebook(cbk, K, D, DEV, seed=21)
+    z = S.latents(lat, N, D, DEV, E=E, seed=22)
+    cb = g.prepare_codebook(E)
+    on, off = (torch.zeros(8, dtype=torch.int64, device=DEV) for _ in range(2))
+    a = g.vq_search(z, E, cb, stats=on)
+    b = g.vq_search(z, E, cb, flags=L.NO_REFINE, stats=off)
+    assert torch.equal(a, b)
+    on, off = on.cpu().numpy(), off.cpu().numpy()
+    assert on[L.STAT_REFINE_ROWS] == on[L.STAT_FALLBACK_ROWS] == off[L.STAT_FALLBACK_ROWS] and off[L.STAT_REFINE_ROWS] == 0
+    if on[L.STAT_REFINE_ROWS]:
+        assert on[L.STAT_REFINE_EXACT] >= on[L.STAT_REFINE_ROWS]
+    want = g.vq_search_exact(z, E)
+    assert S.audit(z, E, a, want, eps_tie=2.0 ** -40)["hard"] == 0
+
+
+def test_refine_pass_keeps_the_first_index_on_exact_ties():
+    g, L = _g()
+    D, N = 64, 65536
+    E = S.codebook("normal", 32, D, DEV, seed=1).repeat(8, 1)              # every code 8 times: all rows tie
+    z = S.latents("gru", N, D, DEV, seed=2)
+    st = torch.zeros(8, dtype=torch.int64, device=DEV)
+    idx = g.vq_search(z, E, stats=st)
+    assert int(idx.max()) < 32
+    assert torch.equal(idx, g.vq_search_exact(z, E))

@@ -1,0 +1,38 @@
+"""Per-kernel device timeline of the tokenization step (torch.profiler / CUPTI: kernel durations and the idle gaps
+between consecutive kernels).  Usage: python tools/timeline.py [K] [f32|bf16] [flags]"""
+import os, sys
+import torch
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import gesture2vec_b200 as g
+import gpu_synth as S
+from torch.profiler import profile, ProfilerActivity
+
+K = int(sys.argv[1]) if len(sys.argv) > 1 else 400
+dt = torch.bfloat16 if len(sys.argv) > 2 and sys.argv[2] == "bf16" else torch.float32
+flags = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+dev = torch.device("cuda:0")
+N, D = 1_000_000, 400
+E = S.codebook("normal", K, D, dev, seed=3)
+zs = [S.latents("iid", N, D, dev, seed=4 + i).to(dt) for i in range(3)]
+cb = g.prepare_codebook(E)
+for z in zs:
+    g.vq_search(z, E, cb, flags=flags)
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for i in range(9):
+        g.vq_search(zs[i % 3], E, cb, flags=flags)
+    torch.cuda.synchronize()
+evs = sorted([e for e in prof.events() if e.device_time > 0], key=lambda e: e.time_range.start)
+agg, gaps, prev_end = {}, {}, None
+for e in evs:
+    name = e.name.replace("(anonymous namespace)::", "").replace("void ", "").split("<")[0].split("(")[0].split("::")[-1][:40]
+    agg.setdefault(name, []).append(e.device_time)
+    if prev_end is not None:
+        gaps.setdefault(name, []).append(e.time_range.start - prev_end)
+    prev_end = e.time_range.end
+span = evs[-1].time_range.end - evs[0].time_range.start
+print(f"K={K} {dt} flags={flags}: {span / 9:.1f} us per step over 9 steps")
+for k, v in agg.items():
+    gp = gaps.get(k, [0])
+    print(f"  {k:40s} n={len(v):3d} mean {sum(v) / len(v):8.1f} us   gap before: mean {sum(gp) / len(gp):6.1f} us")
