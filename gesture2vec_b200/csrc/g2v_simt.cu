@@ -521,14 +521,39 @@ __device__ __forceinline__ unsigned warp_sort_u32(unsigned v, int lane) {
   return v;
 }
 
-__global__ void __launch_bounds__(APPLY_WARPS * 32) apply_runs_kernel(
+// The rows of a batch are fetched ahead of use with cp.async into a per-warp ring in shared memory (RUNS_PF rows
+// in flight per warp: 16 warps x 4 x 1.6 KB per SM covers the HBM latency-bandwidth product; one row held in
+// registers did not).  A lane reads back exactly the 16-byte slots it wrote itself, so the ring needs no barrier --
+// cp.async.wait_group orders a lane's own copies, and a slot is re-filled one full iteration after its last read.
+constexpr int RUNS_PF = 4;                 // rows in flight per warp
+constexpr int RUNS_SLOTS = RUNS_PF + 1;
+constexpr int RUNS_SLOT_F4 = RUNS_MAX_D / 4;      // float4 per ring slot (128)
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+size_t apply_runs_smem(int K, int use_hist) {
+  const size_t hist = use_hist ? ((size_t)K * sizeof(int) + 15) / 16 * 16 : 0;
+  return hist + (size_t)APPLY_WARPS * RUNS_SLOTS * RUNS_SLOT_F4 * sizeof(float4);
+}
+
+template <bool HAS_ZS>
+__global__ void __launch_bounds__(APPLY_WARPS * 32, 2) apply_runs_kernel(
     const float* __restrict__ x, const float* __restrict__ zs, const float* __restrict__ E,
     const int* __restrict__ idx, long long N, int K, int D, float* __restrict__ out, double* sse,
     int* counts, float* dwr, int dwr_replicas, int use_hist) {
-  extern __shared__ int hist[];
+  extern __shared__ __align__(16) unsigned char runs_smem[];
+  int* hist = reinterpret_cast<int*>(runs_smem);
   __shared__ double wsum[APPLY_WARPS];
   dwr += (size_t)(blockIdx.x % dwr_replicas) * K * D;               // this block's private copy
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4* ring = reinterpret_cast<float4*>(runs_smem + (use_hist ? ((size_t)K * sizeof(int) + 15) / 16 * 16 : 0)) +
+                 (size_t)warp * RUNS_SLOTS * RUNS_SLOT_F4;
   if (use_hist) {
     for (int k = threadIdx.x; k < K; k += blockDim.x) hist[k] = 0;
     __syncthreads();
@@ -548,15 +573,22 @@ __global__ void __launch_bounds__(APPLY_WARPS * 32) apply_runs_kernel(
       }
     }
     const unsigned key = warp_sort_u32(((unsigned)k << 5) | (unsigned)lane, lane);
-    float4 a[4], ev[4], xn[4];
+    float4 a[4], ev[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) a[u] = ev[u] = zero4;
     int cur = -1;
-    auto load_row = [&](const float* src, int i, float4 (&v)[4]) {
-      const unsigned ki = __shfl_sync(0xffffffffu, key, i);
-      const float* r = src + (size_t)(base + (ki & 31u)) * D;
+    // fetch row i of the sorted batch into its ring slot (a group is committed even when there is no row i, so
+    // that wait_group counts the same for every i)
+    auto fetch = [&](int i) {
+      if (i < nvalid) {
+        const unsigned ki = __shfl_sync(0xffffffffu, key, i);
+        const float* r = x + (size_t)(base + (ki & 31u)) * D;
+        float4* slot = ring + (i % RUNS_SLOTS) * RUNS_SLOT_F4;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = (lane + 32 * u < nq) ? lds4(r + 4 * (lane + 32 * u)) : zero4;
+        for (int u = 0; u < 4; ++u)
+          if (lane + 32 * u < nq) cp_async16(slot + lane + 32 * u, r + 4 * (lane + 32 * u));
+      }
+      cp_async_commit();
     };
     auto flush = [&]() {
       float* drow = dwr + (size_t)cur * D;
@@ -564,15 +596,18 @@ __global__ void __launch_bounds__(APPLY_WARPS * 32) apply_runs_kernel(
       for (int u = 0; u < 4; ++u)
         if (lane + 32 * u < nq) red_add_v4(drow + 4 * (lane + 32 * u), a[u].x, a[u].y, a[u].z, a[u].w);
     };
-    load_row(x, 0, xn);
+#pragma unroll
+    for (int i = 0; i < RUNS_PF; ++i) fetch(i);
     for (int i = 0; i < nvalid; ++i) {
       const unsigned ki = __shfl_sync(0xffffffffu, key, i);
       const int code = (int)(ki >> 5);
       const long long row = base + (ki & 31u);
-      float4 xv[4];
+      float4 zv[4];
+      if (HAS_ZS) {
+        const float* r = zs + (size_t)row * D;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) xv[u] = xn[u];
-      if (i + 1 < nvalid) load_row(x, i + 1, xn);                   // next row in flight while this one is summed
+        for (int u = 0; u < 4; ++u) zv[u] = (lane + 32 * u < nq) ? lds4(r + 4 * (lane + 32 * u)) : zero4;
+      }
       if (code != cur) {                                            // warp-uniform
         if (cur >= 0) flush();
         cur = code;
@@ -583,8 +618,12 @@ __global__ void __launch_bounds__(APPLY_WARPS * 32) apply_runs_kernel(
           a[u] = zero4;
         }
       }
-      float4 zv[4];
-      if (zs) load_row(zs, i, zv);
+      cp_async_wait<RUNS_PF - 1>();                                 // row i has landed (this lane's part of it)
+      const float4* slot = ring + (i % RUNS_SLOTS) * RUNS_SLOT_F4;
+      float4 xv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) xv[u] = (lane + 32 * u < nq) ? slot[lane + 32 * u] : zero4;
+      fetch(i + RUNS_PF);                                           // into the slot read one iteration ago
       float* orow = out ? out + (size_t)row * D : nullptr;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -594,7 +633,7 @@ __global__ void __launch_bounds__(APPLY_WARPS * 32) apply_runs_kernel(
         if (orow && lane + 32 * u < nq)
           __stcs(reinterpret_cast<float4*>(orow + 4 * (lane + 32 * u)),
                  make_float4(xv[u].x + d.x, xv[u].y + d.y, xv[u].z + d.z, xv[u].w + d.w));
-        if (zs) {
+        if (HAS_ZS) {
           a[u].x += zv[u].x - ev[u].x; a[u].y += zv[u].y - ev[u].y;
           a[u].z += zv[u].z - ev[u].z; a[u].w += zv[u].w - ev[u].w;
         } else {
@@ -602,6 +641,7 @@ __global__ void __launch_bounds__(APPLY_WARPS * 32) apply_runs_kernel(
         }
       }
     }
+    cp_async_wait<0>();                                             // (only empty groups are left)
     if (cur >= 0) flush();
   }
   if (sse) {
@@ -737,6 +777,43 @@ __global__ void __launch_bounds__(256) backward_kernel(const float* __restrict__
       for (int j = lane; j < D; j += 32) {
         float g = gr ? __ldg(gr + j) : 0.f;
         o[j] = fmaf(c, __ldg(xr + j) - __ldg(er + j), g);
+      }
+    }
+  }
+}
+
+// The same over the matrix as ONE stream of float4 (rows are D / 4 of them): a CTA takes 256 * BW_U consecutive
+// float4 per pass, every thread issues all of its loads (x, g_out, the code entry from L1 / L2) before the first
+// store, no lane idles on a row tail (D = 400 is 100 float4: a warp-per-row loop leaves 28 lanes idle every
+// fourth pass).  Pure HBM stream: 3 x 4 D bytes per row.
+constexpr int BW_U = 4;
+__global__ void __launch_bounds__(256) backward_flat_kernel(const float4* __restrict__ x, const float4* __restrict__ E,
+                                                            const int* __restrict__ idx, const float4* __restrict__ g_out,
+                                                            const float* __restrict__ g_loss, float coef_x,
+                                                            unsigned total4, int K, unsigned D4, float4* __restrict__ g_x) {
+  const float c = __ldg(g_loss) * coef_x;
+  const unsigned span = 256u * BW_U;
+  for (unsigned long long base = (unsigned long long)blockIdx.x * span; base < total4; base += (unsigned long long)gridDim.x * span) {
+    float4 xv[BW_U], gv[BW_U], ev[BW_U];
+#pragma unroll
+    for (int u = 0; u < BW_U; ++u) {
+      const unsigned long long i64 = base + 256u * u + threadIdx.x;
+      if (i64 < total4) {
+        const unsigned i = (unsigned)i64;
+        const unsigned row = i / D4, col = i - row * D4;
+        const int k = min(max(__ldg(idx + row), 0), K - 1);
+        xv[u] = __ldcs(x + i);
+        gv[u] = g_out ? __ldcs(g_out + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ev[u] = __ldg(E + (size_t)k * D4 + col);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < BW_U; ++u) {
+      const unsigned long long i64 = base + 256u * u + threadIdx.x;
+      if (i64 < total4) {
+        const float4 r = make_float4(fmaf(c, xv[u].x - ev[u].x, gv[u].x), fmaf(c, xv[u].y - ev[u].y, gv[u].y),
+                                     fmaf(c, xv[u].z - ev[u].z, gv[u].z), fmaf(c, xv[u].w - ev[u].w, gv[u].w));
+        __stcs(g_x + i64, r);
       }
     }
   }
@@ -974,10 +1051,17 @@ int launch_apply(const float* x, const float* zs, const float* E, const int32_t*
   static const bool runs_on = [] { const char* e = getenv("G2V_APPLY_RUNS"); return !(e && atoi(e) == 0); }();
   // (small batches: a warp per row keeps every SM busy; the run walk serialises 32 rows per warp)
   if (vec && dwr && D <= RUNS_MAX_D && K < (1 << 26) && runs_on && N >= 16384) {      // sort key = code << 5 | lane
-    const int g = grid_for((N + 31) / 32, APPLY_WARPS, 8);
-    apply_runs_kernel<<<g, APPLY_WARPS * 32, smem, st>>>(x, zs, E, idx, N, K, D, out, sse, counts, dwr, dwr_replicas, use_hist);
-    G2V_LAUNCH_CHECK("apply_runs_kernel");
-    return G2V_OK;
+    const size_t rsmem = apply_runs_smem(K, use_hist);
+    const int g = grid_for((N + 31) / 32, APPLY_WARPS, 2);          // two resident CTAs per SM (registers, ring)
+    if (rsmem <= 200 * 1024) {
+      // (the attribute is per device and a call sets it: always the same value, so concurrent callers agree)
+      if (zs) G2V_CUDA_CHECK(cudaFuncSetAttribute(apply_runs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      else G2V_CUDA_CHECK(cudaFuncSetAttribute(apply_runs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      if (zs) apply_runs_kernel<true><<<g, APPLY_WARPS * 32, rsmem, st>>>(x, zs, E, idx, N, K, D, out, sse, counts, dwr, dwr_replicas, use_hist);
+      else apply_runs_kernel<false><<<g, APPLY_WARPS * 32, rsmem, st>>>(x, zs, E, idx, N, K, D, out, sse, counts, dwr, dwr_replicas, use_hist);
+      G2V_LAUNCH_CHECK("apply_runs_kernel");
+      return G2V_OK;
+    }
   }
   if (vec)
     apply_kernel<true><<<grid, APPLY_WARPS * 32, smem, st>>>(x, zs, E, idx, N, K, D, out, sse, counts, dwr, dwr_replicas, use_hist);
@@ -1019,6 +1103,16 @@ int launch_backward(const float* x, const float* E, const int32_t* idx, const fl
                     float coef_x, int64_t N, int K, int D, float* g_x, cudaStream_t st) {
   const bool vec = (D % 4 == 0) && aligned16(x) && aligned16(E) && aligned16(g_x) && (!g_out || aligned16(g_out));
   const int grid = grid_for(N, 8, 8);
+  const unsigned long long total4 = (unsigned long long)N * (unsigned long long)(D / 4);
+  if (vec && total4 < 0xffffffffull) {
+    const int fgrid = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((total4 + 256 * BW_U - 1) / (256 * BW_U),
+                                                                                      (unsigned long long)num_sms() * 8));
+    backward_flat_kernel<<<fgrid, 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(E), idx,
+                                               reinterpret_cast<const float4*>(g_out), g_loss, coef_x, (unsigned)total4, K,
+                                               (unsigned)(D / 4), reinterpret_cast<float4*>(g_x));
+    G2V_LAUNCH_CHECK("backward_flat_kernel");
+    return G2V_OK;
+  }
   if (vec) backward_kernel<true><<<grid, 256, 0, st>>>(x, E, idx, g_out, g_loss, coef_x, N, K, D, g_x);
   else backward_kernel<false><<<grid, 256, 0, st>>>(x, E, idx, g_out, g_loss, coef_x, N, K, D, g_x);
   G2V_LAUNCH_CHECK("backward_kernel");

@@ -211,9 +211,13 @@ def test_refine_pass_gives_the_same_indices_as_straight_fp64(cbk, lat, K):
     b = g.vq_search(z, E, cb, flags=L.NO_REFINE, stats=off)
     assert torch.equal(a, b)
     on, off = on.cpu().numpy(), off.cpu().numpy()
-    assert on[L.STAT_REFINE_ROWS] == on[L.STAT_FALLBACK_ROWS] == off[L.STAT_FALLBACK_ROWS] and off[L.STAT_REFINE_ROWS] == 0
-    if on[L.STAT_REFINE_ROWS]:
+    # the pass is taken when rows x codes is worth three launches (else rerank_kernel's own fp64 path covers them)
+    assert on[L.STAT_FALLBACK_ROWS] == off[L.STAT_FALLBACK_ROWS] and off[L.STAT_REFINE_ROWS] == 0
+    if on[L.STAT_FALLBACK_ROWS] * K >= 131072:
+        assert on[L.STAT_REFINE_ROWS] == on[L.STAT_FALLBACK_ROWS] and on[L.STAT_FULL_RECHECK] == 0
         assert on[L.STAT_REFINE_EXACT] >= on[L.STAT_REFINE_ROWS]
+    else:
+        assert on[L.STAT_REFINE_ROWS] == 0 and on[L.STAT_FULL_RECHECK] == on[L.STAT_FALLBACK_ROWS]
     want = g.vq_search_exact(z, E)
     assert S.audit(z, E, a, want, eps_tie=2.0 ** -40)["hard"] == 0
 

@@ -1,5 +1,6 @@
-"""Per-kernel device timeline of the tokenization step (torch.profiler / CUPTI: kernel durations and the idle gaps
-between consecutive kernels).  Usage: python tools/timeline.py [K] [f32|bf16] [flags]"""
+"""Per-kernel device timeline of the tokenization step, or with a 4th argument `train` of the fwd+bwd+EMA step of
+the drop-in EMA module (torch.profiler / CUPTI: kernel durations and the idle gaps between consecutive kernels).
+Usage: python tools/timeline.py [K] [f32|bf16] [flags] [train]"""
 import os, sys
 import torch
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
@@ -14,14 +15,31 @@ flags = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 dev = torch.device("cuda:0")
 N, D = 1_000_000, 400
 E = S.codebook("normal", K, D, dev, seed=3)
-zs = [S.latents("iid", N, D, dev, seed=4 + i).to(dt) for i in range(3)]
-cb = g.prepare_codebook(E)
-for z in zs:
-    g.vq_search(z, E, cb, flags=flags)
+train = len(sys.argv) > 4 and sys.argv[4] == "train"
+if train:
+    layer = g.DAE_VQ_Payam_EMA(K, D, 0.25, 0.85).to(dev).train()
+    with torch.no_grad():
+        layer._embedding.weight.copy_(E)
+    layer.return_encodings = False
+    zf = S.latents("clustered", N, D, dev, E=E, seed=4).requires_grad_(True)
+    gq = torch.randn(N, D, device=dev)
+
+    def step(i):
+        zf.grad = None
+        loss, q, ppl, _ = layer(zf)
+        torch.autograd.backward([loss, q], [torch.ones_like(loss), gq])
+else:
+    zs = [S.latents("iid", N, D, dev, seed=4 + i).to(dt) for i in range(3)]
+    cb = g.prepare_codebook(E)
+
+    def step(i):
+        g.vq_search(zs[i % 3], E, cb, flags=flags)
+for i in range(3):
+    step(i)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     for i in range(9):
-        g.vq_search(zs[i % 3], E, cb, flags=flags)
+        step(i)
     torch.cuda.synchronize()
 evs = sorted([e for e in prof.events() if e.device_time > 0], key=lambda e: e.time_range.start)
 agg, gaps, prev_end = {}, {}, None
