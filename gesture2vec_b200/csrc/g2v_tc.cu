@@ -952,7 +952,7 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
         const uint32_t rows = (uint32_t)(last ? P.n_last : P.ntile);        // codes of the tile; this CTA fetches half
         const int row = nt * P.ntile + (int)(cta_rank * (rows / 2));
         for (int sc = 0; sc < n_sc; ++sc) {
-          mbar_wait(bar_bempty(s), sph ^ 1u);
+          mbar_wait_idle(bar_bempty(s), sph ^ 1u);
           const int p0 = 2 * sc, np = min(2, n_full - p0);
           const int nt_here = (sc == n_sc - 1) ? P.n_tail : 0;
           if (elect_one()) {
@@ -1043,7 +1043,7 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
       // a slot = 128 rows x 128 bytes: 32 fp32 columns (two slots per 64-column panel) or 64 16-bit columns (one)
       const int n_main = (Z32 ? 2 : 1) * n_full, n_slots = n_main + P.n_tail;
       for (int u = 0; u < n_slots; ++u) {
-        mbar_wait(bar_zempty(slot), ph ^ 1u);
+        mbar_wait_idle(bar_zempty(slot), ph ^ 1u);
         TRACE(2, u);
         if (P.flags & kDbgNoZ) {
           if (elect_one()) mbar_arrive(bar_zfull(slot));
@@ -1072,7 +1072,7 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
     for (int tile = group; tile < P.n_row_tiles; tile += n_groups, ++ti) {
       // Only the two key constants of the row stay in registers across the sweep (the key/top-2 chains need
       // every register they can get); the full per-row constants are rebuilt from the statistics afterwards.
-      mbar_wait(bar_rsfull(ti % RS_RING), (ti / RS_RING) & 1u);
+      mbar_wait_idle(bar_rsfull(ti % RS_RING), (ti / RS_RING) & 1u);
       float key_cS, key_S;
       {
         const RowInfo r0 = make_rowinfo(rowstat[(ti % RS_RING) * TM + r].x, 0.f, 1.f, 0.f, 0.f, P.hdr->e2min, P.hdr->scale_e, P.n_ksteps);
@@ -1088,7 +1088,7 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
         const int e_valid = min(s0 + ((nt == P.n_ntiles - 1) ? P.n_last : P.ntile), P.K);
         const int g0 = (s0 - 16 * eh + 31) >> 5, g1 = (e_valid - 16 * eh + 31) >> 5;     // pieces g0 .. g1-1
         if (warp == EPI_WARP0) TRACE(3, 100 + nt);
-        mbar_wait(bar_accfull(as), around & 1u);
+        mbar_wait_idle(bar_accfull(as), around & 1u);
         if (warp == EPI_WARP0) TRACE(3, 200 + nt);
         tc_fence_after();
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col_of(as) + (uint32_t)(16 * eh - s0);
@@ -1166,7 +1166,7 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
         const bool sc_last = (c == n_chunks - 1) || (c < n_full - 1 && (c & 1) == 1) || (c == n_full - 1 && sc < n_sc - 1);
         if (sc_first) {
           if (cw == 0) TRACE(4, 100 + sc);
-          mbar_wait(bar_aempty(ab, sc), ((ti >> absh) & 1u) ^ 1u);   // the MMAs of the buffer's previous row tile have read these panels
+          mbar_wait_idle(bar_aempty(ab, sc), ((ti >> absh) & 1u) ^ 1u);   // the MMAs of the buffer's previous row tile have read these panels
           if (cw == 0) TRACE(4, 200 + sc);
           tc_fence_after();
         }
@@ -1174,7 +1174,7 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
           // 16-bit rows: one slot per panel, a row is 64 elements = 128 bytes (SWIZZLE_128B); K step s of row r is
           // the 16-byte chunks 2s, 2s+1 (xor r % 8); this lane takes 8 bytes (4 elements) of it
           uint32_t w[16];
-          mbar_wait(bar_zfull(slot), ph);
+          mbar_wait_idle(bar_zfull(slot), ph);
           const unsigned char* zs = gbase + sp.z_off + slot * TME_ZSLOT;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -1198,7 +1198,7 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
           if (++slot == NZ) { slot = 0; ph ^= 1u; }
           tc_st_16x256b_x4(t_buf + 32u * c, w);
         } else if (!Z32) {
-          mbar_wait(bar_zfull(slot), ph);
+          mbar_wait_idle(bar_zfull(slot), ph);
           const unsigned char* zs = gbase + sp.z_off + slot * TME_ZSLOT;                 // tail slot: 32-byte rows, no swizzle
           const uint32_t ot = (uint32_t)ra_l * 32u + kq * 8u;
           const uint2 a0 = *reinterpret_cast<const uint2*>(zs + ot), b0 = *reinterpret_cast<const uint2*>(zs + ot + 8 * 32);
@@ -1213,7 +1213,7 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
           uint32_t w[16];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            mbar_wait(bar_zfull(slot), ph);
+            mbar_wait_idle(bar_zfull(slot), ph);
             const unsigned char* zs = gbase + sp.z_off + slot * TME_ZSLOT;
             // odd rows fetch their second K step first: the two rows of a quarter-warp then sit in different
             // halves of the swizzled 128-byte line (no bank conflict); the words are put back in order below
@@ -1234,7 +1234,7 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
           }
           tc_st_16x256b_x4(t_buf + 32u * c, w);
         } else {
-          mbar_wait(bar_zfull(slot), ph);
+          mbar_wait_idle(bar_zfull(slot), ph);
           const unsigned char* zs = gbase + sp.z_off + slot * TME_ZSLOT;
           const float4 a0 = *reinterpret_cast<const float4*>(zs + off_t), b0 = *reinterpret_cast<const float4*>(zs + off_t + 8 * 64);
           uint32_t w0, w1, w2, w3;

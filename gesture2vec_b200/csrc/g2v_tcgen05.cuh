@@ -84,6 +84,36 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
       : "memory");
 #endif
 }
+// Wait of a warp that is NOT the one everybody else is waiting for (epilogue / converter / producer warps of
+// tc_tmem_kernel).  try_wait comes back at once on this part whatever its time hint says (ncu: 56 M of the 306 M
+// warp-instructions of the K=400 sweep are SYNCS / YIELD / BRA polls, 11 M polls by the epilogue warps alone), and
+// the polling warps share a scheduler with the warps they wait for.  -DG2V_WAIT_SLEEP_NS=<ns> puts a nanosleep
+// behind every failed poll.  Measured (1 M rows, K=400 / 512 / 2048, bf16 512): 20, 40 and 100 ns are all ~1 %
+// SLOWER than plain polling (421.5 vs 417.1 us at K=400) -- the polls only use issue slots nobody else wants, so
+// the default stays 0.
+#ifndef G2V_WAIT_SLEEP_NS
+#define G2V_WAIT_SLEEP_NS 0
+#endif
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity) {
+#if G2V_WAIT_SLEEP_NS > 0
+  while (!mbar_try(bar, parity)) asm volatile("nanosleep.u32 %0;" ::"r"((uint32_t)G2V_WAIT_SLEEP_NS));
+#else
+  mbar_wait(bar, parity);
+#endif
+}
 // make generic-proxy shared-memory writes visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
