@@ -32,13 +32,34 @@ constexpr int GM_A_STAGE = GM_TM * GM_KC * 2;   // 16384
 // ------------------------------------------------------------------------------------------
 // operand preparation
 // ------------------------------------------------------------------------------------------
+// largest magnitude of a [rows, cols] matrix with row pitch ld; contiguous 16-byte aligned matrices (the usual case)
+// are read as one float4 stream, 4 loads in flight per thread
 __global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, long long rows, long long cols, long long ld,
                                                    float* amax) {
   float m = 0.f;
   const long long n = rows * cols;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / cols, c = i - r * cols;
-    m = fmaxf(m, fabsf(x[r * ld + c]));
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+  if (ld == cols && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const long long n4 = n >> 2;
+    long long i = tid;
+    for (; i + 3 * nthr < n4; i += 4 * nthr) {
+      const float4 a = __ldg(x4 + i), b = __ldg(x4 + i + nthr), c = __ldg(x4 + i + 2 * nthr), d = __ldg(x4 + i + 3 * nthr);
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w))));
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w))));
+    }
+    for (; i < n4; i += nthr) {
+      const float4 a = __ldg(x4 + i);
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+    }
+    for (long long j = (n4 << 2) + tid; j < n; j += nthr) m = fmaxf(m, fabsf(__ldg(x + j)));
+  } else {
+    for (long long i = tid; i < n; i += nthr) {
+      const long long r = i / cols, c = i - r * cols;
+      m = fmaxf(m, fabsf(x[r * ld + c]));
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));

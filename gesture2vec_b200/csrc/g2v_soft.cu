@@ -18,6 +18,8 @@
 
 #include <math.h>
 
+#include <algorithm>
+
 namespace g2v {
 namespace {
 
@@ -69,6 +71,73 @@ __global__ void __launch_bounds__(SW * 32) soft_assign_kernel(const float* __res
       atomicAdd(&cs[k], v);
     }
   }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x)
+    if (cs[k] != 0.f) atomicAdd(colsum + k, cs[k]);
+}
+
+// K <= 32 KI: a lane keeps its K / 32 codes of the row AND its share of the column sums in registers -- p is written
+// once (already normalised) and the per-element shared-memory atomics of the generic kernel (one per (row, code):
+// they were 4/5 of its time) become one per (warp, code).
+template <int KI>
+__global__ void __launch_bounds__(SW * 32) soft_assign_reg_kernel(const float* __restrict__ m, float* __restrict__ dot,
+                                                                  const float* __restrict__ lv, const float* __restrict__ e2,
+                                                                  long long N, int K, int D, float* __restrict__ p,
+                                                                  float* colsum) {
+  extern __shared__ float cs[];                 // [K] column sums of this block
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) cs[k] = 0.f;
+  __syncthreads();
+  float csum[KI], e2r[KI];
+#pragma unroll
+  for (int i = 0; i < KI; ++i) {
+    csum[i] = 0.f;
+    e2r[i] = (lane + 32 * i < K) ? e2[lane + 32 * i] : 0.f;
+  }
+  for (long long row = (long long)blockIdx.x * SW + warp; row < N; row += (long long)gridDim.x * SW) {
+    const float* mr = m + (size_t)row * D;
+    float* dr = dot + (size_t)row * K;
+    const float* lr = lv + (size_t)row * K;
+    float* pr = p + (size_t)row * K;
+    float dv[KI], lvv[KI];
+#pragma unroll
+    for (int i = 0; i < KI; ++i) {
+      const int k = lane + 32 * i;
+      dv[i] = k < K ? __ldcs(dr + k) : 0.f;
+      lvv[i] = k < K ? __ldcs(lr + k) : 0.f;
+    }
+    float m2 = 0.f;
+    for (int j = lane; j < D; j += 32) m2 = fmaf(mr[j], mr[j], m2);
+    m2 = wsum(m2);
+    float prob[KI];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < KI; ++i) {
+      const int k = lane + 32 * i;
+      prob[i] = 0.f;
+      if (k < K) {
+        const float d = (m2 + e2r[i]) - 2.f * dv[i];             // the reference's order: (|m|^2 + |e|^2) - 2 m.e
+        const float ex = expf(lvv[i]);
+        const float s = 1.f / (ex * ex);                         // smooth = 1 / exp(logvar)^2      (:1399)
+        prob[i] = expf(-((d / kSoftScale) * (0.5f * s))) / sqrtf(s);
+        dr[k] = d;
+        sum += prob[i];                                          // (same lane order as the generic kernel)
+      }
+    }
+    sum = wsum(sum);
+#pragma unroll
+    for (int i = 0; i < KI; ++i) {
+      const int k = lane + 32 * i;
+      if (k < K) {
+        const float v = prob[i] / sum;
+        pr[k] = v;
+        csum[i] += v;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < KI; ++i)
+    if (lane + 32 * i < K && csum[i] != 0.f) atomicAdd(&cs[lane + 32 * i], csum[i]);
   __syncthreads();
   for (int k = threadIdx.x; k < K; k += blockDim.x)
     if (cs[k] != 0.f) atomicAdd(colsum + k, cs[k]);
@@ -150,6 +219,70 @@ __global__ void __launch_bounds__(SW * 32) soft_bwd_kernel(const float* __restri
   }
 }
 
+template <int KI>
+__global__ void __launch_bounds__(SW * 32) soft_bwd_reg_kernel(const float* __restrict__ p, const float* __restrict__ dp,
+                                                               const float* __restrict__ d, const float* __restrict__ lv,
+                                                               long long N, int K, float* __restrict__ gd,
+                                                               float* __restrict__ glv, float* __restrict__ rowsum_gd,
+                                                               float* col_gd, float* col_glv) {
+  extern __shared__ float cs[];                 // [2K]: column sums of gd, glv of this block
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = threadIdx.x; k < 2 * K; k += blockDim.x) cs[k] = 0.f;
+  __syncthreads();
+  float ca[KI], cb[KI];
+#pragma unroll
+  for (int i = 0; i < KI; ++i) ca[i] = cb[i] = 0.f;
+  for (long long row = (long long)blockIdx.x * SW + warp; row < N; row += (long long)gridDim.x * SW) {
+    const size_t o = (size_t)row * K;
+    float pv[KI], dpv[KI], dv[KI], lvv[KI];
+#pragma unroll
+    for (int i = 0; i < KI; ++i) {
+      const int k = lane + 32 * i;
+      const bool in = k < K;
+      pv[i] = in ? __ldcs(p + o + k) : 0.f;
+      dpv[i] = in ? __ldcs(dp + o + k) : 0.f;
+      dv[i] = in ? __ldcs(d + o + k) : 0.f;
+      lvv[i] = in ? __ldcs(lv + o + k) : 0.f;
+    }
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < KI; ++i) t = fmaf(pv[i], dpv[i], t);
+    t = wsum(t);
+    float rs = 0.f;
+#pragma unroll
+    for (int i = 0; i < KI; ++i) {
+      const int k = lane + 32 * i;
+      if (k < K) {
+        const float g = pv[i] * (dpv[i] - t);                    // d/d(log p~) of sum_k p_k dp_k
+        const float ex = expf(lvv[i]);
+        const float s = 1.f / (ex * ex);
+        const float a = -g * s / (2.f * kSoftScale);             // d log p~ / d d   = -s / 800
+        const float b = g * (dv[i] * s / kSoftScale + 1.f);      // d log p~ / d lv  = d s / 400 + 1
+        __stcs(gd + o + k, a);
+        __stcs(glv + o + k, b);
+        rs += a;
+        ca[i] += a;
+        cb[i] += b;
+      }
+    }
+    rs = wsum(rs);
+    if (lane == 0) rowsum_gd[row] = rs;
+  }
+#pragma unroll
+  for (int i = 0; i < KI; ++i) {
+    const int k = lane + 32 * i;
+    if (k < K) {
+      if (ca[i] != 0.f) atomicAdd(&cs[k], ca[i]);
+      if (cb[i] != 0.f) atomicAdd(&cs[K + k], cb[i]);
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    if (cs[k] != 0.f) atomicAdd(col_gd + k, cs[k]);
+    if (cs[K + k] != 0.f) atomicAdd(col_glv + k, cs[K + k]);
+  }
+}
+
 // gx = c[0] * gmw + a[0] * (x - q) + g_out (g_out optional); c, a are device scalars
 __global__ void __launch_bounds__(256) soft_gx_kernel(const float* __restrict__ gmw, const float* __restrict__ x,
                                                       const float* __restrict__ q, const float* __restrict__ g_out,
@@ -170,7 +303,12 @@ inline int grid_rows(long long rows, int per_block) {
 
 int launch_soft_assign(const float* m, float* dot, const float* lv, const float* e2, int64_t N, int K, int D, float* p,
                        float* colsum, cudaStream_t st) {
-  soft_assign_kernel<<<grid_rows(N, SW), SW * 32, (size_t)K * sizeof(float), st>>>(m, dot, lv, e2, N, K, D, p, colsum);
+  // a persistent grid: the per-warp column sums are flushed once per warp
+  const int g = (int)std::max<long long>(1, std::min<long long>((N + SW - 1) / SW, (long long)num_sms() * 4));
+  if (K <= 256) soft_assign_reg_kernel<8><<<g, SW * 32, (size_t)K * sizeof(float), st>>>(m, dot, lv, e2, N, K, D, p, colsum);
+  else if (K <= 512) soft_assign_reg_kernel<16><<<g, SW * 32, (size_t)K * sizeof(float), st>>>(m, dot, lv, e2, N, K, D, p, colsum);
+  else if (K <= 1024) soft_assign_reg_kernel<32><<<g, SW * 32, (size_t)K * sizeof(float), st>>>(m, dot, lv, e2, N, K, D, p, colsum);
+  else soft_assign_kernel<<<grid_rows(N, SW), SW * 32, (size_t)K * sizeof(float), st>>>(m, dot, lv, e2, N, K, D, p, colsum);
   G2V_LAUNCH_CHECK("soft_assign_kernel");
   return G2V_OK;
 }
@@ -187,8 +325,11 @@ int launch_soft_tail(const float* x, const float* q, int64_t N, int K, int D, fl
 
 int launch_soft_bwd(const float* p, const float* dp, const float* d, const float* lv, int64_t N, int K, float* gd, float* glv,
                     float* rowsum_gd, float* col_gd, float* col_glv, cudaStream_t st) {
-  soft_bwd_kernel<<<grid_rows(N, SW), SW * 32, (size_t)2 * K * sizeof(float), st>>>(p, dp, d, lv, N, K, gd, glv, rowsum_gd,
-                                                                                    col_gd, col_glv);
+  const int g = (int)std::max<long long>(1, std::min<long long>((N + SW - 1) / SW, (long long)num_sms() * 4));
+  const size_t sm = (size_t)2 * K * sizeof(float);
+  if (K <= 256) soft_bwd_reg_kernel<8><<<g, SW * 32, sm, st>>>(p, dp, d, lv, N, K, gd, glv, rowsum_gd, col_gd, col_glv);
+  else if (K <= 512) soft_bwd_reg_kernel<16><<<g, SW * 32, sm, st>>>(p, dp, d, lv, N, K, gd, glv, rowsum_gd, col_gd, col_glv);
+  else soft_bwd_kernel<<<grid_rows(N, SW), SW * 32, sm, st>>>(p, dp, d, lv, N, K, gd, glv, rowsum_gd, col_gd, col_glv);
   G2V_LAUNCH_CHECK("soft_bwd_kernel");
   return G2V_OK;
 }

@@ -16,7 +16,19 @@ dev = torch.device("cuda:0")
 N, D = 1_000_000, 400
 E = S.codebook("normal", K, D, dev, seed=3)
 train = len(sys.argv) > 4 and sys.argv[4] == "train"
-if train:
+soft = len(sys.argv) > 4 and sys.argv[4] == "soft"
+if soft:
+    N = 131072
+    layer = g.VQVAE_VQ_Payam_GSSoft(K, D, 0.25).to(dev)
+    xs = torch.tanh(0.8 * torch.randn(N, D, device=dev)).requires_grad_(True)
+    gq = torch.randn(N, D, device=dev)
+
+    def step(i):
+        xs.grad = None
+        layer.zero_grad(set_to_none=True)
+        loss, q, ppl, p = layer(xs)
+        torch.autograd.backward([loss, q], [torch.ones_like(loss), gq])
+elif train:
     layer = g.DAE_VQ_Payam_EMA(K, D, 0.25, 0.85).to(dev).train()
     with torch.no_grad():
         layer._embedding.weight.copy_(E)
@@ -53,4 +65,4 @@ span = evs[-1].time_range.end - evs[0].time_range.start
 print(f"K={K} {dt} flags={flags}: {span / 9:.1f} us per step over 9 steps")
 for k, v in agg.items():
     gp = gaps.get(k, [0])
-    print(f"  {k:40s} n={len(v):3d} mean {sum(v) / len(v):8.1f} us   gap before: mean {sum(gp) / len(gp):6.1f} us")
+    print(f"  {k:40s} n={len(v):3d} mean {sum(v) / len(v):8.1f} us   per step {sum(v) / 9:8.1f} us   gap before: mean {sum(gp) / len(gp):6.1f} us")
