@@ -211,3 +211,27 @@ def test_pre_linear_fold_matches_the_explicit_projection():
     x = torch.from_numpy(O.synth_latents("gru", 5000, D, seed=50)).to(DEV)
     assert np.array_equal(tok.encode_rows(x), a.tokenize(x).cpu().numpy())
     assert np.array_equal(tok.encode_rows(x.cpu().numpy()), a.tokenize(x).cpu().numpy())
+
+
+def test_cuda_graph_capture_of_a_bulk_search_with_the_refine_side_stream():
+    """A 65 536-row search forks the refine pass of its whole-row re-ranks onto the library's side stream and joins
+    it again (events): the fork / join is capturable, and the replay on new rows gives the eager indices."""
+    import gesture2vec_b200 as g
+    K, D, N = 1024, 400, 65536
+    E = torch.randn(K, D, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
+    cb = g.prepare_codebook(E)
+    zs = [torch.randn(N, D, device=DEV, generator=torch.Generator(device=DEV).manual_seed(10 + s)) for s in range(3)]
+    static_z, static_idx = zs[0].clone(), torch.empty(N, dtype=torch.int32, device=DEV)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                       # warm-up: workspace, tensor maps, the side stream itself
+        g.vq_search(static_z, E, cb, out=static_idx)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        g.vq_search(static_z, E, cb, out=static_idx)
+    for s in range(1, 3):
+        static_z.copy_(zs[s])
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(static_idx, g.vq_search(zs[s], E, cb))

@@ -61,6 +61,23 @@ def main():
     ids = g.tokenize_host(zh, E, chunk_rows=2048)
     assert int((ids.to(dev) != g.vq_search_exact(zh.to(dev), E)).sum()) <= 2
     g.KMeans(n_clusters=16, init=zh[:16].numpy(), max_iter=2, device=dev).fit(zh[:3000].numpy())
+    # the refine pass of whole-row re-ranks (side stream: split operands, tcgen05 GEMM with a device-side row count,
+    # candidate selection) and the flat backward / cp.async row pass at a bulk size: every code four times, so every
+    # row ties in two of the 32 column chains and is listed as a whole row
+    E = torch.randn(48, 128, device=dev, generator=gen).repeat(4, 1)
+    z = torch.randn(32768, 128, device=dev, generator=gen)
+    st = torch.zeros(8, dtype=torch.int64, device=dev)
+    idx = g.vq_search(z, E, stats=st)
+    assert int(st[L.STAT_REFINE_ROWS]) > 0, st.tolist()
+    assert int((idx != g.vq_search_exact(z, E)).sum()) == 0
+    layer = g.DAE_VQ_Payam_EMA(256, 64, 0.25, 0.85).to(dev).train()
+    xb = torch.randn(32768, 64, device=dev, generator=gen, requires_grad=True)
+    loss, q, ppl, enc = layer(xb)
+    (loss + q.sum()).backward()
+    soft = g.VQVAE_VQ_Payam_GSSoft(64, 64, 0.25).to(dev)
+    xs = torch.randn(4, 64, 32, device=dev, generator=gen, requires_grad=True)
+    loss, q, ppl, enc = soft(xs)
+    (loss + q.sum()).backward()
     torch.cuda.synchronize()
     print(f"sanitize smoke ok: {n_checked} search variants checked")
 
