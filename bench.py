@@ -596,25 +596,46 @@ def soft_record(cx: Ctx, g2v, lib, pk) -> dict:
 
 def vqvae_ema_record(cx: Ctx, g2v, lib, pk) -> dict:
     """The flavour Autoencoder_VQVAE.__init__ constructs at :801 (search and EMA sums on pre_linear(z)): fwd+bwd+EMA
-    at 1 M rows, K=512 -- pre_linear is folded into the codebook (no N x D x D projection at all)."""
+    at 1 M rows, K=512 -- pre_linear is folded into the codebook (no N x D x D projection at all).  Two regimes:
+    latents whose projection is clustered around the codes with Zipf usage (the training record's distribution; an
+    orthogonal pre_linear so that such latents exist at ordinary norms), and the collapse case -- a freshly
+    initialised layer fed iid rows, where the EMA codebook degenerates (dead codes at |e| ~ 1e5, live ones within
+    rounding distance of each other) and most rows need the exact re-rank."""
     dev, K, D, N = cx.dev, 512, D_LATENT, 1_000_000
     gen = torch.Generator(device=dev).manual_seed(21 + cx.rank)
-    E = torch.rand(K, D, device=dev, generator=torch.Generator(device=dev).manual_seed(0)) * 2 - 1
-    layer = g2v.VQVAE_VQ_Payam_EMA(K, D, 0.25, 0.85).to(dev).train()
-    with torch.no_grad():
-        layer._embedding.weight.copy_(E)
-    layer.return_encodings = False
-    if cx.world > 1:
-        g2v.enable_data_parallel_ema(layer, overlap=True)
-    zf = torch.tanh(0.8 * torch.randn(N, D, device=dev, generator=gen)).requires_grad_(True)
     gq = torch.randn(N, D, device=dev, generator=gen)
 
-    def step():
-        zf.grad = None
-        loss, q, ppl, _ = layer(zf)
-        torch.autograd.backward([loss, q], [torch.ones_like(loss), gq])
-    ms = cx.timed(step, 10)
+    def run(clustered: bool) -> float:
+        g0 = torch.Generator(device=dev).manual_seed(0)
+        layer = g2v.VQVAE_VQ_Payam_EMA(K, D, 0.25, 0.85).to(dev).train()
+        with torch.no_grad():
+            if clustered:
+                E = torch.randn(K, D, device=dev, generator=g0)
+                torch.nn.init.orthogonal_(layer.pre_linear.weight)
+                t = zipf_clustered(E, N, gen)                                  # what pre_linear(z) should look like
+                z = (t - layer.pre_linear.bias) @ layer.pre_linear.weight      # z W^T + b = t  for orthogonal W
+                layer._embedding.weight.copy_(E)
+                layer._ema_w.copy_(E * (N / K))                                # a codebook in EMA equilibrium
+                layer._ema_cluster_size.fill_(N / K)
+            else:
+                layer._embedding.weight.copy_(torch.rand(K, D, device=dev, generator=g0) * 2 - 1)
+                z = torch.tanh(0.8 * torch.randn(N, D, device=dev, generator=gen))
+        layer.return_encodings = False
+        if cx.world > 1:
+            g2v.enable_data_parallel_ema(layer, overlap=True)
+        zf = z.contiguous().requires_grad_(True)
+
+        def step():
+            zf.grad = None
+            loss, q, ppl, _ = layer(zf)
+            torch.autograd.backward([loss, q], [torch.ones_like(loss), gq])
+        return cx.timed(step, 10)
+    ms = run(True)
+    ms_collapse = run(False)
     return {"codes_K": K, "rows_per_gpu": N, "ms_per_step": ms, "value": N * cx.world / (ms * 1e-3), "unit": UNIT,
+            "latents": "pre_linear(z) clustered around the codes, Zipf(1.1) usage (as the train record); orthogonal pre_linear",
+            "collapsed_codebook": {"ms_per_step": ms_collapse, "value": N * cx.world / (ms_collapse * 1e-3),
+                                   "latents": "fresh layer on iid tanh rows: the EMA codebook degenerates, most rows take the exact re-rank"},
             "pre_linear": "folded into a [K, D+4] codebook (K*D*D work per step); the raw rows are searched"}
 
 

@@ -823,6 +823,7 @@ struct TmeParams {
   int n_full, n_tail, n_chunks;   // K panels of the A operand: 64 columns, then 16-column tails
   int ntile, n_ntiles, n_last;    // codes per accumulator stage; code tiles; codes of the last tile (multiple of 16)
   int a_bufs, acc_col0;           // A operand buffers in TMEM (1 or 2); first accumulator column in TMEM
+  int ahead;                      // converters turn super-chunk 0 of the next tile into registers before the A buffer is free
   int n_row_tiles;                // tiles of 256 rows (128 per CTA)
   int n_ksteps;
   int Kpad;                       // (n_ntiles - 1) * ntile + n_last
@@ -916,7 +917,7 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
     for (int s = 0; s < TME_MAX_BST; ++s) { mbar_init(bar_bfull(s), 1); mbar_init(bar_bempty(s), 1); }
     for (int s = 0; s < TME_MAX_ZSLOTS; ++s) { mbar_init(bar_zfull(s), 1); mbar_init(bar_zempty(s), TME_CONV_WARPS); }
     for (int b = 0; b < 2; ++b)
-      for (int c = 0; c < MAX_CHUNKS; ++c) { mbar_init(bar_aconv(b, c), TME_CONV_WARPS); mbar_init(bar_apeer(b, c), 1); mbar_init(bar_aempty(b, c), 1); }
+      for (int c = 0; c < MAX_CHUNKS; ++c) { mbar_init(bar_aconv(b, c), 2 * TME_CONV_WARPS); mbar_init(bar_apeer(b, c), 1); mbar_init(bar_aempty(b, c), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(bar_accfull(a), 1); mbar_init(bar_accempty(a), 16); }
     for (int s = 0; s < RS_RING; ++s) mbar_init(bar_rsfull(s), TME_CONV_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -989,10 +990,10 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
           const uint32_t rows_b = (uint32_t)(last_nt ? P.n_last : P.ntile) / 2u;     // code rows per CTA in a stage
           for (int sc = 0; sc < n_sc; ++sc) {
             if (nt == 0) {
-              mbar_wait(bar_aconv(ab, sc), apar);
+              // the converter warps of BOTH CTAs arrive here (the peer's with a remote arrive: one hop less per
+              // super-chunk than a relay warp in the peer; the hand-over chain is the critical path of a tile)
+              mbar_wait_cluster(bar_aconv(ab, sc), apar);
               TRACE(1, 300 + sc);
-              mbar_wait_cluster(bar_apeer(ab, sc), apar);
-              TRACE(1, 400 + sc);
             }
             mbar_wait(bar_bfull(s), sph);
             if (nt == 0) TRACE(1, 500 + sc);
@@ -1021,16 +1022,6 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
             __syncwarp();
             if (++s == NB) { s = 0; sph ^= 1u; }
           }
-        }
-      }
-    } else {
-      // =========================== peer: forward "panel written" to the leader ===========================
-      uint32_t ti = 0;
-      for (int tile = group; tile < P.n_row_tiles; tile += n_groups, ++ti) {
-        for (int sc = 0; sc < n_sc; ++sc) {
-          mbar_wait(bar_aconv((int)(ti & abm), sc), (ti >> absh) & 1u);
-          if (elect_one()) mbar_arrive_cluster(bar_apeer((int)(ti & abm), sc), 0);
-          __syncwarp();
         }
       }
     }
@@ -1156,49 +1147,133 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
       w1 = *reinterpret_cast<const uint32_t*>(&h23);
     };
     uint32_t slot = 0, ph = 0, ti = 0;
+    // one 64-column panel of the tile (a "chunk": two fp32 slots or one 16-bit slot) -> 16 packed fp16 words
+    auto convert_main = [&](uint32_t (&w)[16]) {
+      if constexpr (!Z32) {
+        // 16-bit rows: one slot per panel, a row is 64 elements = 128 bytes (SWIZZLE_128B); K step s of row r is
+        // the 16-byte chunks 2s, 2s+1 (xor r % 8); this lane takes 8 bytes (4 elements) of it
+        mbar_wait(bar_zfull(slot), ph);
+        const unsigned char* zs = gbase + sp.z_off + slot * TME_ZSLOT;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t sf = 2u * h + (odd ? 1u : 0u), ss = 2u * h + (odd ? 0u : 1u);   // odd rows: second K step first
+          const uint32_t of = (uint32_t)ra_l * 128u + (((2u * sf + (kq >> 1)) ^ sw) << 4) + 8u * (kq & 1u);
+          const uint32_t os = (uint32_t)ra_l * 128u + (((2u * ss + (kq >> 1)) ^ sw) << 4) + 8u * (kq & 1u);
+          const uint2 af = *reinterpret_cast<const uint2*>(zs + of), bf = *reinterpret_cast<const uint2*>(zs + of + 8 * 128);
+          const uint2 as = *reinterpret_cast<const uint2*>(zs + os), bs = *reinterpret_cast<const uint2*>(zs + os + 8 * 128);
+          uint32_t f0, f1, f2, f3, s0, s1, s2, s3;
+          cvt(unpack16<ZT>(af), z2a, r2a, f0, f1);
+          cvt(unpack16<ZT>(bf), z2b, r2b, f2, f3);
+          cvt(unpack16<ZT>(as), z2a, r2a, s0, s1);
+          cvt(unpack16<ZT>(bs), z2b, r2b, s2, s3);
+          w[8 * h + 0] = odd ? s0 : f0; w[8 * h + 1] = odd ? s1 : f1;
+          w[8 * h + 2] = odd ? s2 : f2; w[8 * h + 3] = odd ? s3 : f3;
+          w[8 * h + 4] = odd ? f0 : s0; w[8 * h + 5] = odd ? f1 : s1;
+          w[8 * h + 6] = odd ? f2 : s2; w[8 * h + 7] = odd ? f3 : s3;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_zempty(slot));
+        if (++slot == NZ) { slot = 0; ph ^= 1u; }
+      } else {
+        // fp32 rows: the panel is two slots.  Both are awaited and loaded before any arithmetic, and the two halves
+        // accumulate their norms separately: a converter warp is bound by the latency of its own dependent
+        // instructions (5.1 us per tile with nothing else running, ncu: 85 instructions per slot at ~5.5 cycles
+        // each), so the eight conversions of a panel have to be independent work the scheduler can interleave.
+        const uint32_t s1 = (slot + 1 == NZ) ? 0u : slot + 1u, ph1 = (slot + 1 == NZ) ? (ph ^ 1u) : ph;
+        mbar_wait(bar_zfull(slot), ph);
+        mbar_wait(bar_zfull(s1), ph1);
+        if (P.flags & kDbgSkipConv) {              // trace builds: hand-shakes only
+#pragma unroll
+          for (int i = 0; i < 16; ++i) w[i] = 0u;
+          __syncwarp();
+          if (lane == 0) { mbar_arrive(bar_zempty(slot)); mbar_arrive(bar_zempty(s1)); }
+          slot += 2;
+          if (slot >= NZ) { slot -= NZ; ph ^= 1u; }
+          return;
+        }
+        const unsigned char* zs0 = gbase + sp.z_off + slot * TME_ZSLOT;
+        const unsigned char* zs1 = gbase + sp.z_off + s1 * TME_ZSLOT;
+        // odd rows fetch their second K step first: the two rows of a quarter-warp then sit in different
+        // halves of the swizzled 128-byte line (no bank conflict); the words are put back in order below
+        float4 af[2], bf[2], as[2], bs[2];
+        af[0] = *reinterpret_cast<const float4*>(zs0 + off_f); bf[0] = *reinterpret_cast<const float4*>(zs0 + off_f + 8 * 128);
+        as[0] = *reinterpret_cast<const float4*>(zs0 + off_s); bs[0] = *reinterpret_cast<const float4*>(zs0 + off_s + 8 * 128);
+        af[1] = *reinterpret_cast<const float4*>(zs1 + off_f); bf[1] = *reinterpret_cast<const float4*>(zs1 + off_f + 8 * 128);
+        as[1] = *reinterpret_cast<const float4*>(zs1 + off_s); bs[1] = *reinterpret_cast<const float4*>(zs1 + off_s + 8 * 128);
+        float2 za[2], ra[2], zb[2], rb[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          za[h] = ra[h] = zb[h] = rb[h] = make_float2(0.f, 0.f);
+          uint32_t f0, f1, f2, f3, s0, s1w, s2, s3;
+          cvt(af[h], za[h], ra[h], f0, f1);
+          cvt(bf[h], zb[h], rb[h], f2, f3);
+          cvt(as[h], za[h], ra[h], s0, s1w);
+          cvt(bs[h], zb[h], rb[h], s2, s3);
+          w[8 * h + 0] = odd ? s0 : f0; w[8 * h + 1] = odd ? s1w : f1;
+          w[8 * h + 2] = odd ? s2 : f2; w[8 * h + 3] = odd ? s3 : f3;
+          w[8 * h + 4] = odd ? f0 : s0; w[8 * h + 5] = odd ? f1 : s1w;
+          w[8 * h + 6] = odd ? f2 : s2; w[8 * h + 7] = odd ? f3 : s3;
+        }
+        z2a.x += za[0].x + za[1].x; z2a.y += za[0].y + za[1].y;
+        r2a.x += ra[0].x + ra[1].x; r2a.y += ra[0].y + ra[1].y;
+        z2b.x += zb[0].x + zb[1].x; z2b.y += zb[0].y + zb[1].y;
+        r2b.x += rb[0].x + rb[1].x; r2b.y += rb[0].y + rb[1].y;
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(bar_zempty(slot)); mbar_arrive(bar_zempty(s1)); }
+        slot += 2;
+        if (slot >= NZ) { slot -= NZ; ph ^= 1u; }
+      }
+    };
+    auto publish = [&](int ab, int sc) {          // the super-chunk's TMEM stores are done: hand it to the MMA issuer
+      if (cw == 0) TRACE(4, 300 + sc);
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(bar_aconv(ab, sc));
+        else mbar_arrive_cluster(bar_aconv(ab, sc), 0);
+      }
+      if (cw == 0) TRACE(4, 400 + sc);
+    };
+    // With at least two super-chunks, super-chunk 0 (panels 0 and 1) is converted into REGISTERS before the A
+    // buffer is free: the converters otherwise idle ~3 us per tile waiting for the last code tile's MMAs to release
+    // it, and the conversion that follows is the critical path of the tile (profiles/r2_trace_tc_tmem_k400.txt).
+    const bool ahead = (n_sc >= 2) && P.ahead != 0;
     for (int tile = group; tile < P.n_row_tiles; tile += n_groups, ++ti) {
       const int ab = (int)(ti & abm);
       const uint32_t t_buf = t_lane + (uint32_t)ab * a_cols;
-      for (int c = 0; c < n_chunks; ++c) {
+      const uint32_t a_par = ((ti >> absh) & 1u) ^ 1u;
+      int c_first = 0;
+      if (ahead) {
+        uint32_t w0[16], w1[16];
+        convert_main(w0);
+        convert_main(w1);
+        if (cw == 0) TRACE(4, 100);
+        mbar_wait(bar_aempty(ab, 0), a_par);      // the MMAs of the buffer's previous row tile have read these panels
+        if (cw == 0) TRACE(4, 200);
+        tc_fence_after();
+        tc_st_16x256b_x4(t_buf, w0);
+        tc_st_16x256b_x4(t_buf + 32u, w1);
+        publish(ab, 0);
+        c_first = 2;
+      }
+      for (int c = c_first; c < n_chunks; ++c) {
         // barriers work on super-chunks: panels 2 sc and 2 sc + 1, the tails belong to the last one
         const int sc = min(c >> 1, n_sc - 1);
         const bool sc_first = (c < n_full) && ((c & 1) == 0);
         const bool sc_last = (c == n_chunks - 1) || (c < n_full - 1 && (c & 1) == 1) || (c == n_full - 1 && sc < n_sc - 1);
         if (sc_first) {
           if (cw == 0) TRACE(4, 100 + sc);
-          mbar_wait_idle(bar_aempty(ab, sc), ((ti >> absh) & 1u) ^ 1u);   // the MMAs of the buffer's previous row tile have read these panels
+          mbar_wait(bar_aempty(ab, sc), a_par);   // the MMAs of the buffer's previous row tile have read these panels
           if (cw == 0) TRACE(4, 200 + sc);
           tc_fence_after();
         }
-        if (!Z32 && c < n_full) {
-          // 16-bit rows: one slot per panel, a row is 64 elements = 128 bytes (SWIZZLE_128B); K step s of row r is
-          // the 16-byte chunks 2s, 2s+1 (xor r % 8); this lane takes 8 bytes (4 elements) of it
+        if (c < n_full) {
           uint32_t w[16];
-          mbar_wait_idle(bar_zfull(slot), ph);
-          const unsigned char* zs = gbase + sp.z_off + slot * TME_ZSLOT;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint32_t sf = 2u * h + (odd ? 1u : 0u), ss = 2u * h + (odd ? 0u : 1u);   // odd rows: second K step first
-            const uint32_t of = (uint32_t)ra_l * 128u + (((2u * sf + (kq >> 1)) ^ sw) << 4) + 8u * (kq & 1u);
-            const uint32_t os = (uint32_t)ra_l * 128u + (((2u * ss + (kq >> 1)) ^ sw) << 4) + 8u * (kq & 1u);
-            const uint2 af = *reinterpret_cast<const uint2*>(zs + of), bf = *reinterpret_cast<const uint2*>(zs + of + 8 * 128);
-            const uint2 as = *reinterpret_cast<const uint2*>(zs + os), bs = *reinterpret_cast<const uint2*>(zs + os + 8 * 128);
-            uint32_t f0, f1, f2, f3, s0, s1, s2, s3;
-            cvt(unpack16<ZT>(af), z2a, r2a, f0, f1);
-            cvt(unpack16<ZT>(bf), z2b, r2b, f2, f3);
-            cvt(unpack16<ZT>(as), z2a, r2a, s0, s1);
-            cvt(unpack16<ZT>(bs), z2b, r2b, s2, s3);
-            w[8 * h + 0] = odd ? s0 : f0; w[8 * h + 1] = odd ? s1 : f1;
-            w[8 * h + 2] = odd ? s2 : f2; w[8 * h + 3] = odd ? s3 : f3;
-            w[8 * h + 4] = odd ? f0 : s0; w[8 * h + 5] = odd ? f1 : s1;
-            w[8 * h + 6] = odd ? f2 : s2; w[8 * h + 7] = odd ? f3 : s3;
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_zempty(slot));
-          if (++slot == NZ) { slot = 0; ph ^= 1u; }
+          convert_main(w);
           tc_st_16x256b_x4(t_buf + 32u * c, w);
         } else if (!Z32) {
-          mbar_wait_idle(bar_zfull(slot), ph);
+          mbar_wait(bar_zfull(slot), ph);
           const unsigned char* zs = gbase + sp.z_off + slot * TME_ZSLOT;                 // tail slot: 32-byte rows, no swizzle
           const uint32_t ot = (uint32_t)ra_l * 32u + kq * 8u;
           const uint2 a0 = *reinterpret_cast<const uint2*>(zs + ot), b0 = *reinterpret_cast<const uint2*>(zs + ot + 8 * 32);
@@ -1209,32 +1284,8 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
           if (lane == 0) mbar_arrive(bar_zempty(slot));
           if (++slot == NZ) { slot = 0; ph ^= 1u; }
           tc_st_16x256b_x1(t_buf + 32u * n_full + 8u * (c - n_full), w0, w1, w2, w3);
-        } else if (c < n_full) {
-          uint32_t w[16];
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            mbar_wait_idle(bar_zfull(slot), ph);
-            const unsigned char* zs = gbase + sp.z_off + slot * TME_ZSLOT;
-            // odd rows fetch their second K step first: the two rows of a quarter-warp then sit in different
-            // halves of the swizzled 128-byte line (no bank conflict); the words are put back in order below
-            const float4 af = *reinterpret_cast<const float4*>(zs + off_f), bf = *reinterpret_cast<const float4*>(zs + off_f + 8 * 128);
-            const float4 as = *reinterpret_cast<const float4*>(zs + off_s), bs = *reinterpret_cast<const float4*>(zs + off_s + 8 * 128);
-            uint32_t f0, f1, f2, f3, s0, s1, s2, s3;
-            cvt(af, z2a, r2a, f0, f1);
-            cvt(bf, z2b, r2b, f2, f3);
-            cvt(as, z2a, r2a, s0, s1);
-            cvt(bs, z2b, r2b, s2, s3);
-            w[8 * h + 0] = odd ? s0 : f0; w[8 * h + 1] = odd ? s1 : f1;
-            w[8 * h + 2] = odd ? s2 : f2; w[8 * h + 3] = odd ? s3 : f3;
-            w[8 * h + 4] = odd ? f0 : s0; w[8 * h + 5] = odd ? f1 : s1;
-            w[8 * h + 6] = odd ? f2 : s2; w[8 * h + 7] = odd ? f3 : s3;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_zempty(slot));
-            if (++slot == NZ) { slot = 0; ph ^= 1u; }
-          }
-          tc_st_16x256b_x4(t_buf + 32u * c, w);
         } else {
-          mbar_wait_idle(bar_zfull(slot), ph);
+          mbar_wait(bar_zfull(slot), ph);
           const unsigned char* zs = gbase + sp.z_off + slot * TME_ZSLOT;
           const float4 a0 = *reinterpret_cast<const float4*>(zs + off_t), b0 = *reinterpret_cast<const float4*>(zs + off_t + 8 * 64);
           uint32_t w0, w1, w2, w3;
@@ -1245,14 +1296,7 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
           if (++slot == NZ) { slot = 0; ph ^= 1u; }
           tc_st_16x256b_x1(t_buf + 32u * n_full + 8u * (c - n_full), w0, w1, w2, w3);
         }
-        if (sc_last) {
-          if (cw == 0) TRACE(4, 300 + sc);
-          tc_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_aconv(ab, sc));
-          if (cw == 0) TRACE(4, 400 + sc);
-        }
+        if (sc_last) publish(ab, sc);
       }
       // row statistics of the finished tile: sum over the four lanes that share a row
       float sza = z2a.x + z2a.y, sra = r2a.x + r2a.y, szb = z2b.x + z2b.y, srb = r2b.x + r2b.y;
@@ -1843,7 +1887,7 @@ inline size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 
 // Experiment knobs, read from the environment ONCE per process (-1 = not set).  None of them changes results.
 struct Tuning {
-  int tmem_mode, a_bufs, bstages, zslots, fused, cg, tmem16;
+  int tmem_mode, a_bufs, bstages, zslots, fused, cg, tmem16, ahead;
   unsigned dbg_flags;          // -DG2V_TRACE=1 builds only
   long long* trace;            // -DG2V_TRACE=1 builds only: device buffer the role timeline is written to
 };
@@ -1858,6 +1902,7 @@ const Tuning& tuning() {
     u.fused = geti("G2V_TC_FUSED");
     u.cg = geti("G2V_TC_CG");
     u.tmem16 = geti("G2V_TC_TMEM16");
+    u.ahead = geti("G2V_TC_AHEAD");
     u.dbg_flags = 0;
     u.trace = nullptr;
 #if G2V_TRACE
@@ -1997,6 +2042,7 @@ bool plan_tmem(const void* z, int z_dtype, int64_t N, int K, int D, int Dz, int 
   if (R->n_chunks > MAX_CHUNKS) return false;
   R->ntile = best_nt; R->n_ntiles = best_n; R->n_last = best_last; R->Kpad = best_pad;
   R->a_bufs = a_bufs; R->acc_col0 = acc_col0;
+  R->ahead = tuning().ahead == 0 ? 0 : 1;      // G2V_TC_AHEAD=0: convert only into a free A buffer (round-1 behaviour)
   R->n_ksteps = Dp / KT;
   R->b_stage = (uint32_t)round_up((best_nt / 2) * (std::min(2, R->n_full) * KC + R->n_tail * KT) * 2, 1024);
   R->n_row_tiles = (int)((N + 2 * TM - 1) / (2 * TM));
