@@ -992,7 +992,7 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
             if (nt == 0) {
               // the converter warps of BOTH CTAs arrive here (the peer's with a remote arrive: one hop less per
               // super-chunk than a relay warp in the peer; the hand-over chain is the critical path of a tile)
-              mbar_wait_cluster(bar_aconv(ab, sc), apar);
+              mbar_wait_cluster_idle(bar_aconv(ab, sc), apar);
               TRACE(1, 300 + sc);
             }
             mbar_wait(bar_bfull(s), sph);

@@ -114,6 +114,26 @@ __device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity) {
   mbar_wait(bar, parity);
 #endif
 }
+__device__ __forceinline__ bool mbar_try_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster_idle(uint32_t bar, uint32_t parity) {
+#if G2V_WAIT_SLEEP_NS > 0
+  while (!mbar_try_cluster(bar, parity)) asm volatile("nanosleep.u32 %0;" ::"r"((uint32_t)G2V_WAIT_SLEEP_NS));
+#else
+  mbar_wait_cluster(bar, parity);
+#endif
+}
 // make generic-proxy shared-memory writes visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
