@@ -231,3 +231,53 @@ def test_refine_pass_keeps_the_first_index_on_exact_ties():
     idx = g.vq_search(z, E, stats=st)
     assert int(idx.max()) < 32
     assert torch.equal(idx, g.vq_search_exact(z, E))
+
+
+@pytest.mark.parametrize("N,K0,rep,D,dtype", [(40000, 75, 4, 60, torch.float32), (33001, 40, 4, 404, torch.float32),
+                                               (50003, 48, 4, 180, torch.bfloat16), (32768, 80, 4, 496, torch.float16)])
+def test_refine_pass_ragged_shapes(N, K0, rep, D, dtype):
+    """The refine pass at shapes off its fast paths: D not a multiple of 64 (zero-padded operand panels), K not a
+    multiple of the GEMM tile, ragged N, 16-bit rows.  Every code appears four times, spread over the 32 column
+    chains so that a row's best distance ties in four chains (or twice in two): such rows are listed whole."""
+    g, L = _g()
+    E = S.codebook("normal", K0, D, DEV, seed=31).repeat(rep, 1).contiguous()
+    z = S.latents("gru", N, D, DEV, seed=32).to(dtype)
+    st = torch.zeros(8, dtype=torch.int64, device=DEV)
+    idx = g.vq_search(z, E, stats=st)
+    st = st.cpu().numpy()
+    assert st[L.STAT_REFINE_ROWS] > N // 2, st
+    want = g.vq_search_exact(z, E)
+    assert torch.equal(idx, want) and int(idx.max()) < K0           # exact ties: the first copy wins
+
+
+@pytest.mark.parametrize("N,K,D", [(16384 + 17, 70, 52), (20000, 300, 404), (16385, 512, 400), (40001, 33, 8)])
+def test_bulk_row_pass_and_backward_ragged_shapes(N, K, D):
+    """The bulk kernels of the training step (run-aggregated row pass behind its cp.async ring, N >= 16384; the
+    backward as one float4 stream) at ragged N and D off the 128-column grid, against torch fp64 on the same GPU."""
+    g, L = _g()
+    E = S.codebook("normal", K, D, DEV, seed=41)
+    x = S.latents("clustered", N, D, DEV, E=E, seed=42)
+    idx = g.vq_search(x, E)
+    out, packed = g.vq_apply(x, E, idx, want_out=True, want_stats=True, want_dwr=True)
+    lay = g.packed_layout(K, D)
+    q = E[idx.long()]
+    assert torch.equal(out, x + (q - x))
+    counts = packed[lay["counts"][0]:lay["counts"][1]]
+    assert torch.equal(counts.long(), torch.bincount(idx.long(), minlength=K))
+    sse = ((q.double() - x.double()) ** 2).sum()
+    np.testing.assert_allclose(float(packed[lay["sse"]]), float(sse), rtol=2e-5)
+    dwr = packed[:K * D].view(K, D).double()
+    ref = torch.zeros(K, D, device=DEV, dtype=torch.float64).index_add_(0, idx.long(), x.double() - q.double())
+    tol = 2e-5 * ref.abs().amax(dim=1, keepdim=True) + 1e-4
+    assert bool(((dwr - ref).abs() <= tol).all()), float((dwr - ref).abs().max())
+    # backward: g_x = g_out + c (x - E[idx]) with c = g_loss * coef
+    layer = g.DAE_VQ_Payam(K, D, 0.25).to(DEV)
+    with torch.no_grad():
+        layer._embedding.weight.copy_(E)
+    xs = x.clone().requires_grad_(True)
+    gq = torch.randn(N, D, device=DEV, generator=torch.Generator(device=DEV).manual_seed(5))
+    loss, qq, ppl, enc = layer(xs)
+    torch.autograd.backward([loss, qq], [torch.tensor(2.0, device=DEV), gq])
+    c = 2.0 * 0.25 * 2.0 / (N * D)                                   # d(beta * mse(x, q.detach())) / dx, times g_loss
+    want = gq.double() + c * (x.double() - q.double())
+    assert bool(((xs.grad.double() - want).abs() <= 1e-6 * want.abs() + 1e-7).all())
