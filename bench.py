@@ -798,9 +798,9 @@ def main():
     # ---- end-to-end through the host-buffer entry point ----
     e2e = None
     if a.workload == "tokenize" and not a.no_e2e:
-        zh = torch.empty(N, D, dtype=tdt, pin_memory=True)
+        zh = g2v.pinned_empty(N, D, dtype=tdt, device=dev)       # page-locked on the GPU's NUMA node
         zh.copy_(z)
-        ih = torch.empty(N, dtype=torch.int32, pin_memory=True)
+        ih = g2v.pinned_empty(N, dtype=torch.int32, device=dev)
         cb = g2v.prepare_codebook(E)
         e_steps = max(3, min(a.steps, 5))
         g2v.tokenize_host(zh, E, cb, chunk_rows=131072, out=ih, flags=flags)

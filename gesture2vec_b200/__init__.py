@@ -4,7 +4,7 @@ Only what the path needs: the C-ABI CUDA library (csrc/, include/g2v_vq.h), its 
 and the host-side mirror of the reference's quantizer modules.
 """
 from . import _lib  # noqa: F401
-from .functional import (prepare_codebook, vq_search, vq_apply, quantize, tokenize, tokenize_host,  # noqa: F401
+from .functional import (prepare_codebook, vq_search, vq_apply, quantize, tokenize, tokenize_host, pinned_empty,  # noqa: F401
                          one_hot, stats_finalize, ema_update, packed_numel, step_finalize, vq_search_exact,
                          vq_search_wide, pad_rows, gemm, linear)
 from .quantizers import (DAE_VQ_Payam, DAE_VQ_Payam_EMA, VQVAE_VQ_Payam, VQVAE_VQ_Payam_EMA,  # noqa: F401

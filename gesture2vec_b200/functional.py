@@ -550,6 +550,43 @@ def tokenize(z: torch.Tensor, E: torch.Tensor, cb: Optional[torch.Tensor] = None
     return vq_search(z.contiguous(), E, cb, flags=flags, stats=stats)
 
 
+def pinned_empty(*shape, dtype=torch.float32, device=None) -> torch.Tensor:
+    """Page-locked host tensor for the host-buffer entry points, allocated on the NUMA node of `device`.
+
+    cudaHostAlloc backs the pages where the CALLING thread runs; on a multi-socket box a rank whose staging buffer
+    sits on the far socket crosses the inter-socket link on every host->device copy.  The calling thread is bound
+    to the GPU's ideal CPUs (NVML's nvmlDeviceSetCpuAffinity) for the duration of the allocation and the first
+    touch, then its affinity mask is restored.  Falls back to a plain pinned allocation where NVML or the affinity
+    call is unavailable (e.g. a cgroup that does not contain those CPUs)."""
+    import os
+    if len(shape) == 1 and isinstance(shape[0], (tuple, list, torch.Size)):
+        shape = tuple(shape[0])
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    old = None
+    try:
+        old = os.sched_getaffinity(0)
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(dev).uuid)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + uuid)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+    except Exception:
+        pass
+    try:
+        t = torch.empty(*shape, dtype=dtype, pin_memory=True)
+        t.zero_()                                   # first touch on the bound CPUs
+    finally:
+        if old is not None:
+            try:
+                os.sched_setaffinity(0, old)
+            except Exception:
+                pass
+    return t
+
+
 def tokenize_host(z_host: torch.Tensor, E: torch.Tensor, cb: Optional[torch.Tensor] = None, *,
                   chunk_rows: int = 131072, out: Optional[torch.Tensor] = None,
                   flags: int = _lib.ALGO_AUTO, return_stats: bool = False):
@@ -566,7 +603,7 @@ def tokenize_host(z_host: torch.Tensor, E: torch.Tensor, cb: Optional[torch.Tens
     dt = _DT[z_host.dtype]
     chunk_rows = max(1, min(int(chunk_rows), max(N, 1)))
     if out is None:
-        out = torch.empty(N, dtype=torch.int32, pin_memory=True)
+        out = pinned_empty(N, dtype=torch.int32, device=E.device)
     stats = torch.zeros(8, dtype=torch.int64)
     torch.cuda.current_stream(E.device).synchronize()   # cb / E were produced on the caller's stream
     with torch.cuda.device(E.device):

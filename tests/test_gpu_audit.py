@@ -281,3 +281,38 @@ def test_bulk_row_pass_and_backward_ragged_shapes(N, K, D):
     c = 2.0 * 0.25 * 2.0 / (N * D)                                   # d(beta * mse(x, q.detach())) / dx, times g_loss
     want = gq.double() + c * (x.double() - q.double())
     assert bool(((xs.grad.double() - want).abs() <= 1e-6 * want.abs() + 1e-7).all())
+
+
+def test_six_million_rows_need_64_bit_offsets():
+    """N x D = 2.4e9 elements (9.6 GB of fp32 rows): row * D no longer fits 32 bits for the last 630 000 rows.
+    The search, the row pass and the backward are checked on blocks from both ends against the same kernels run on
+    the blocks alone (they are exact, so the indices agree bit for bit) and against the fp64 checker."""
+    g, L = _g()
+    K, D, N = 400, 400, 6_000_000
+    E = S.codebook("normal", K, D, DEV, seed=51)
+    z = torch.empty(N, D, device=DEV)
+    gen = torch.Generator(device=DEV).manual_seed(52)
+    for i in range(0, N, 1_000_000):
+        z[i:i + 1_000_000].normal_(generator=gen)
+    cb = g.prepare_codebook(E)
+    idx = g.vq_search(z, E, cb)
+    assert int(idx.min()) >= 0 and int(idx.max()) < K
+    for lo in (0, N - 70_000):
+        blk = z[lo:lo + 70_000]
+        assert torch.equal(idx[lo:lo + 70_000], g.vq_search(blk.contiguous(), E, cb))
+        a = S.audit(blk, E, idx[lo:lo + 70_000], g.vq_search_exact(blk.contiguous(), E), eps_tie=2.0 ** -40)
+        assert a["hard"] == 0, a
+    out, packed = g.vq_apply(z, E, idx, want_out=True, want_stats=True, want_dwr=True)
+    lay = g.packed_layout(K, D)
+    assert float(packed[lay["rows"]]) == N
+    tail = slice(N - 50_000, N)
+    q = E[idx[tail].long()]
+    assert torch.equal(out[tail], z[tail] + (q - z[tail]))
+    del out
+    gx = torch.empty_like(z)
+    one = torch.ones((), device=DEV)
+    from gesture2vec_b200 import _lib as LL
+    lib = LL.load()
+    LL.check(lib.g2v_vq_backward(z.data_ptr(), E.data_ptr(), idx.data_ptr(), None, one.data_ptr(), 0.5, N, K, D,
+                                 gx.data_ptr(), torch.cuda.current_stream().cuda_stream), "g2v_vq_backward")
+    assert torch.allclose(gx[tail], 0.5 * (z[tail] - q), rtol=1e-6, atol=1e-7)
