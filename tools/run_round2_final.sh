@@ -1,5 +1,6 @@
 # round-2 evidence run: full GPU suite, 1 M-row audit, sanitizers, ncu launch lists and --set full captures, bench
 O=gpurun_out/${1:-r2z}; mkdir -p $O
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $O/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $O/smoke.log
 timeout 900 python -m pytest tests -m gpu -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 $O/pytest_gpu.log
 timeout 600 python tools/audit_exact.py --out $O/audit_exact.log > $O/audit_stdout.log 2>&1; echo "audit rc=$?"; tail -1 $O/audit_stdout.log
 for tool in memcheck racecheck synccheck; do
@@ -23,5 +24,6 @@ A=torch.randn(262144,400,device='cuda'); W=torch.randn(400,400,device='cuda')*0.
 for _ in range(4): g.functional.gemm(A,W)
 torch.cuda.synchronize()" > $O/ncu_full7.log 2>&1; echo "ncu full gemm rc=$?"
 timeout 900 python bench.py > $O/bench.json 2> $O/bench.err; echo "bench rc=$?"; python tools/bench_summary.py $O/bench.json 2>/dev/null | head -12
+timeout 600 python bench.py --workload kmeans --codes 300 --extras none > $O/bench_kmeans300.json 2> $O/bench_kmeans.err; echo "bench kmeans rc=$?"; python tools/bench_summary.py $O/bench_kmeans300.json 2>/dev/null | head -4 | cut -c1-300
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_ref.json 2> $O/bench_ref.err; echo "bench ref rc=$?"; cut -c1-400 $O/bench_ref.json
 ls -la $O | head -50
