@@ -17,7 +17,26 @@ N, D = 1_000_000, 400
 E = S.codebook("normal", K, D, dev, seed=3)
 train = len(sys.argv) > 4 and sys.argv[4] == "train"
 soft = len(sys.argv) > 4 and sys.argv[4] == "soft"
-if soft:
+vqvae = len(sys.argv) > 4 and sys.argv[4] == "vqvae"
+if vqvae:
+    # VQVAE_VQ_Payam_EMA (pre_linear folded): latents whose projection is clustered around the codes
+    layer = g.VQVAE_VQ_Payam_EMA(K, D, 0.25, 0.85).to(dev).train()
+    with torch.no_grad():
+        torch.nn.init.orthogonal_(layer.pre_linear.weight)
+        t = S.latents("clustered", N, D, dev, E=E, seed=4)
+        z0 = (t - layer.pre_linear.bias) @ layer.pre_linear.weight
+        layer._embedding.weight.copy_(E)
+        layer._ema_w.copy_(E * (N / K))
+        layer._ema_cluster_size.fill_(N / K)
+    layer.return_encodings = False
+    zf = z0.contiguous().requires_grad_(True)
+    gq = torch.randn(N, D, device=dev)
+
+    def step(i):
+        zf.grad = None
+        loss, q, ppl, _ = layer(zf)
+        torch.autograd.backward([loss, q], [torch.ones_like(loss), gq])
+elif soft:
     N = 131072
     layer = g.VQVAE_VQ_Payam_GSSoft(K, D, 0.25).to(dev)
     xs = torch.tanh(0.8 * torch.randn(N, D, device=dev)).requires_grad_(True)
