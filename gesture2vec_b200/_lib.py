@@ -39,6 +39,8 @@ SIGNATURES = {
     "g2v_vq_search": (_i, [_p, _i, _p, _p, _i64, _i, _i, _p, _p, _p, _sz, _u, _p]),
     "g2v_vq_search_wide": (_i, [_p, _i, _i, _p, _p, _i64, _i, _i, _p, _p, _p, _sz, _u, _p]),
     "g2v_vq_apply": (_i, [_p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _i, _p]),
+    "g2v_apply_workspace_bytes": (_sz, [_i64, _i]),
+    "g2v_vq_apply_ws": (_i, [_p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _i, _p, _sz, _p]),
     "g2v_fold_projection": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "g2v_pad_rows": (_i, [_p, _i64, _i, _i, _p, _p]),
     "g2v_vq_stats_deterministic": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _p]),

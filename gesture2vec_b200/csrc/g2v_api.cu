@@ -178,6 +178,21 @@ int g2v_vq_apply(const float* x, const float* zs, const float* E, const int32_t*
   return launch_apply(x, zs, E, idx, N, K, D, out, sse, counts, dwr, dwr_replicas, (cudaStream_t)stream);
 }
 
+size_t g2v_apply_workspace_bytes(int64_t N, int K) {
+  if (N < 0 || K <= 0) return 0;
+  return apply_ws_bytes(N, K);
+}
+
+int g2v_vq_apply_ws(const float* x, const float* zs, const float* E, const int32_t* idx, int64_t N, int K, int D,
+                    float* out, double* sse, int32_t* counts, float* dwr, int dwr_replicas, void* ws, size_t ws_bytes,
+                    void* stream) {
+  if (bad_shape(N, K, D) || !E || (N > 0 && (!x || !idx)) || (dwr && dwr_replicas < 1)) return G2V_ERR_INVALID;
+  if (N == 0) return G2V_OK;
+  int rc = check_arch();
+  if (rc) return rc;
+  return launch_apply(x, zs, E, idx, N, K, D, out, sse, counts, dwr, dwr_replicas, (cudaStream_t)stream, ws, ws_bytes);
+}
+
 int g2v_fold_projection(const float* E, const float* W, const float* b, int K, int D, int ld_out, float* out, double* g,
                         void* stream) {
   if (K <= 0 || D <= 0 || ld_out < D || !E || !W || !b || !out || !g || (size_t)D * 4 > 48 * 1024) return G2V_ERR_INVALID;

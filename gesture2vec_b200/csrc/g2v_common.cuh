@@ -102,7 +102,10 @@ int launch_full_recheck(const void* z, int z_dtype, const float* E, const void* 
                         const int32_t* count, int64_t max_rows, int32_t* idx, unsigned long long* stats,
                         bool overflow_only, cudaStream_t st, int64_t handled = kFull64Cap);
 int launch_apply(const float* x, const float* zs, const float* E, const int32_t* idx, int64_t N, int K,
-                 int D, float* out, double* sse, int32_t* counts, float* dwr, int dwr_replicas, cudaStream_t st);
+                 int D, float* out, double* sse, int32_t* counts, float* dwr, int dwr_replicas, cudaStream_t st,
+                 void* ws = nullptr, size_t ws_bytes = 0);
+// scratch of the sorted row pass (0: the shape does not take it)
+size_t apply_ws_bytes(int64_t N, int K);
 int launch_pad_rows(const float* x, int64_t N, int D, int Dp, float* out, cudaStream_t st);
 // deterministic (atomics-free, fixed-order, fp64-accumulated) residual sums and squared error from rows sorted by code
 int launch_stats_deterministic(const float* x, const float* zs, const float* E, const int32_t* order, const long long* seg,

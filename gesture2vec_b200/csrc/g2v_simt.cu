@@ -13,6 +13,8 @@
 // g2v_tc.cu.
 #include "g2v_common.cuh"
 
+#include <cooperative_groups.h>
+
 #include <stdlib.h>
 
 #include <algorithm>
@@ -525,7 +527,10 @@ __device__ __forceinline__ unsigned warp_sort_u32(unsigned v, int lane) {
 // in flight per warp: 16 warps x 4 x 1.6 KB per SM covers the HBM latency-bandwidth product; one row held in
 // registers did not).  A lane reads back exactly the 16-byte slots it wrote itself, so the ring needs no barrier --
 // cp.async.wait_group orders a lane's own copies, and a slot is re-filled one full iteration after its last read.
-constexpr int RUNS_PF = 4;                 // rows in flight per warp
+#ifndef G2V_RUNS_PF
+#define G2V_RUNS_PF 4
+#endif
+constexpr int RUNS_PF = G2V_RUNS_PF;       // rows in flight per warp
 constexpr int RUNS_SLOTS = RUNS_PF + 1;
 constexpr int RUNS_SLOT_F4 = RUNS_MAX_D / 4;      // float4 per ring slot (128)
 
@@ -542,11 +547,14 @@ size_t apply_runs_smem(int K, int use_hist) {
   return hist + (size_t)APPLY_WARPS * RUNS_SLOTS * RUNS_SLOT_F4 * sizeof(float4);
 }
 
-template <bool HAS_ZS>
+// SORTED: the warp's 32 rows are 32 consecutive positions of `order`, the rows grouped by code on the device
+// beforehand (code_sort_kernel) -- runs then span whole batches and the per-run vector reductions, which are what
+// bounds the unsorted pass (1 M row-sized reductions cost ~0.77 ms of L2 atomic throughput), all but disappear.
+template <bool HAS_ZS, bool SORTED>
 __global__ void __launch_bounds__(APPLY_WARPS * 32, 2) apply_runs_kernel(
     const float* __restrict__ x, const float* __restrict__ zs, const float* __restrict__ E,
-    const int* __restrict__ idx, long long N, int K, int D, float* __restrict__ out, double* sse,
-    int* counts, float* dwr, int dwr_replicas, int use_hist) {
+    const int* __restrict__ idx, const int* __restrict__ order, long long N, int K, int D, float* __restrict__ out,
+    double* sse, int* counts, float* dwr, int dwr_replicas, int use_hist) {
   extern __shared__ __align__(16) unsigned char runs_smem[];
   int* hist = reinterpret_cast<int*>(runs_smem);
   __shared__ double wsum[APPLY_WARPS];
@@ -565,14 +573,16 @@ __global__ void __launch_bounds__(APPLY_WARPS * 32, 2) apply_runs_kernel(
   for (long long base = ((long long)blockIdx.x * APPLY_WARPS + warp) * 32; base < N; base += stride) {
     const int nvalid = (int)min((long long)32, N - base);
     int k = K;                                                      // rows past the end sort last
+    long long myrow = base + lane;
     if (lane < nvalid) {
-      k = min(max(__ldg(idx + base + lane), 0), K - 1);
-      if (counts) {
+      if (SORTED) myrow = __ldg(order + base + lane);
+      k = min(max(__ldg(idx + myrow), 0), K - 1);
+      if (!SORTED && counts) {                                      // (the sort has counted the rows already)
         if (use_hist) atomicAdd(&hist[k], 1);
         else atomicAdd(counts + k, 1);
       }
     }
-    const unsigned key = warp_sort_u32(((unsigned)k << 5) | (unsigned)lane, lane);
+    const unsigned key = SORTED ? (((unsigned)k << 5) | (unsigned)lane) : warp_sort_u32(((unsigned)k << 5) | (unsigned)lane, lane);
     float4 a[4], ev[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) a[u] = ev[u] = zero4;
@@ -582,7 +592,8 @@ __global__ void __launch_bounds__(APPLY_WARPS * 32, 2) apply_runs_kernel(
     auto fetch = [&](int i) {
       if (i < nvalid) {
         const unsigned ki = __shfl_sync(0xffffffffu, key, i);
-        const float* r = x + (size_t)(base + (ki & 31u)) * D;
+        const long long ri = __shfl_sync(0xffffffffu, myrow, (int)(ki & 31u));
+        const float* r = x + (size_t)ri * D;
         float4* slot = ring + (i % RUNS_SLOTS) * RUNS_SLOT_F4;
 #pragma unroll
         for (int u = 0; u < 4; ++u)
@@ -601,7 +612,7 @@ __global__ void __launch_bounds__(APPLY_WARPS * 32, 2) apply_runs_kernel(
     for (int i = 0; i < nvalid; ++i) {
       const unsigned ki = __shfl_sync(0xffffffffu, key, i);
       const int code = (int)(ki >> 5);
-      const long long row = base + (ki & 31u);
+      const long long row = __shfl_sync(0xffffffffu, myrow, (int)(ki & 31u));
       float4 zv[4];
       if (HAS_ZS) {
         const float* r = zs + (size_t)row * D;
@@ -660,6 +671,70 @@ __global__ void __launch_bounds__(APPLY_WARPS * 32, 2) apply_runs_kernel(
       if (v) atomicAdd(counts + k, v);
     }
   }
+}
+
+// Group the rows by code: order[0 .. N) lists the row indices code by code (within a code in no particular order).
+// One cooperative launch: (1) per-block histograms of contiguous row chunks -> total[K]; (2) after a grid sync every
+// block scans total[] into the segment starts; (3) each block claims, per code, a range inside the segment with ONE
+// global atomic (cursor[k] += its count) and places its rows there with shared-memory counters -- a hot code costs a
+// block one global atomic, not one per row.  total and cursor are zero on entry.
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_MAX_K = 4096;             // 2 K ints of shared memory
+
+__global__ void __launch_bounds__(SORT_THREADS) code_sort_kernel(const int* __restrict__ idx, long long N, int K, int* total,
+                                                                 int* cursor, int* __restrict__ order, int* counts) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ int sort_sm[];
+  int* hist = sort_sm;                         // [K] this block's rows per code, later its write position per code
+  int* segs = sort_sm + K;                     // [K] first position of every code
+  __shared__ int wsum[SORT_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long per = (N + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * per, r1 = min(N, r0 + per);
+  for (int k = tid; k < K; k += SORT_THREADS) hist[k] = 0;
+  __syncthreads();
+  for (long long r = r0 + tid; r < r1; r += SORT_THREADS) atomicAdd(&hist[min(max(__ldg(idx + r), 0), K - 1)], 1);
+  __syncthreads();
+  for (int k = tid; k < K; k += SORT_THREADS)
+    if (hist[k]) atomicAdd(total + k, hist[k]);
+  grid.sync();
+  // exclusive scan of total[0 .. K): thread t owns a contiguous piece
+  const int piece = (K + SORT_THREADS - 1) / SORT_THREADS;
+  const int k0 = min(tid * piece, K), k1 = min(k0 + piece, K);
+  int mine = 0;
+  for (int k = k0; k < k1; ++k) mine += __ldcg(total + k);
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  int before = incl - mine;
+  for (int w = 0; w < warp; ++w) before += wsum[w];
+  for (int k = k0; k < k1; ++k) {
+    const int c = __ldcg(total + k);
+    segs[k] = before;
+    before += c;
+    if (blockIdx.x == 0 && counts && c) counts[k] += c;
+  }
+  __syncthreads();
+  for (int k = tid; k < K; k += SORT_THREADS) {
+    const int c = hist[k];
+    hist[k] = c ? segs[k] + atomicAdd(cursor + k, c) : 0;
+  }
+  __syncthreads();
+  for (long long r = r0 + tid; r < r1; r += SORT_THREADS) {
+    const int k = min(max(__ldg(idx + r), 0), K - 1);
+    order[atomicAdd(&hist[k], 1)] = (int)r;
+  }
+}
+
+size_t sorted_ws_bytes(int64_t N, int K) {
+  if (N < 16384 || K > SORT_MAX_K || N >= (1ll << 31)) return 0;
+  return ((size_t)2 * K * sizeof(int) + 255) / 256 * 256 + (size_t)N * sizeof(int);
 }
 
 // rows [N, D] -> [N, Dp] with zeros in the extra columns (the raw rows a folded codebook is searched with)
@@ -1039,8 +1114,11 @@ int launch_search_simt(const void* z, int z_dtype, const float* E, const void* c
   }
 }
 
+size_t apply_ws_bytes(int64_t N, int K) { return sorted_ws_bytes(N, K); }
+
 int launch_apply(const float* x, const float* zs, const float* E, const int32_t* idx, int64_t N, int K, int D,
-                 float* out, double* sse, int32_t* counts, float* dwr, int dwr_replicas, cudaStream_t st) {
+                 float* out, double* sse, int32_t* counts, float* dwr, int dwr_replicas, cudaStream_t st, void* ws,
+                 size_t ws_bytes) {
   const bool vec = (D % 4 == 0) && aligned16(x) && aligned16(E) && (!zs || aligned16(zs)) &&
                    (!out || aligned16(out)) && (!dwr || aligned16(dwr));
   const int use_hist = (counts && K <= 8192) ? 1 : 0;
@@ -1049,16 +1127,45 @@ int launch_apply(const float* x, const float* zs, const float* E, const int32_t*
   // EMA / codebook-gradient sums wanted: aggregate runs of equal codes in registers first (G2V_APPLY_RUNS=0:
   // one reduction per row, the older kernel)
   static const bool runs_on = [] { const char* e = getenv("G2V_APPLY_RUNS"); return !(e && atoi(e) == 0); }();
+  static const bool sorted_on = [] { const char* e = getenv("G2V_APPLY_SORTED"); return !(e && atoi(e) == 0); }();
   // (small batches: a warp per row keeps every SM busy; the run walk serialises 32 rows per warp)
   if (vec && dwr && D <= RUNS_MAX_D && K < (1 << 26) && runs_on && N >= 16384) {      // sort key = code << 5 | lane
-    const size_t rsmem = apply_runs_smem(K, use_hist);
+    const size_t need = sorted_ws_bytes(N, K);
+    const bool sorted = sorted_on && ws && need && ws_bytes >= need && aligned16(ws);
     const int g = grid_for((N + 31) / 32, APPLY_WARPS, 2);          // two resident CTAs per SM (registers, ring)
+    const int* order = nullptr;
+    if (sorted) {
+      int* total = reinterpret_cast<int*>(ws);
+      int* cursor = total + K;
+      int* ord = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + ((size_t)2 * K * sizeof(int) + 255) / 256 * 256);
+      G2V_CUDA_CHECK(cudaMemsetAsync(ws, 0, (size_t)2 * K * sizeof(int), st));
+      const size_t ssm = (size_t)2 * K * sizeof(int);
+      int per_sm = 0;
+      G2V_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, code_sort_kernel, SORT_THREADS, ssm));
+      if (per_sm < 1) per_sm = 1;
+      const int sgrid = (int)std::max<long long>(1, std::min<long long>((long long)per_sm * num_sms(), (N + 2047) / 2048));
+      long long n64 = N;
+      int k32 = K;
+      int32_t* cnt = counts;
+      void* args[] = {(void*)&idx, (void*)&n64, (void*)&k32, (void*)&total, (void*)&cursor, (void*)&ord, (void*)&cnt};
+      G2V_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)code_sort_kernel, dim3(sgrid), dim3(SORT_THREADS), args, ssm, st));
+      G2V_LAUNCH_CHECK("code_sort_kernel");
+      order = ord;
+    }
+    const size_t rsmem = apply_runs_smem(K, sorted ? 0 : use_hist);
     if (rsmem <= 200 * 1024) {
       // (the attribute is per device and a call sets it: always the same value, so concurrent callers agree)
-      if (zs) G2V_CUDA_CHECK(cudaFuncSetAttribute(apply_runs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      else G2V_CUDA_CHECK(cudaFuncSetAttribute(apply_runs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      if (zs) apply_runs_kernel<true><<<g, APPLY_WARPS * 32, rsmem, st>>>(x, zs, E, idx, N, K, D, out, sse, counts, dwr, dwr_replicas, use_hist);
-      else apply_runs_kernel<false><<<g, APPLY_WARPS * 32, rsmem, st>>>(x, zs, E, idx, N, K, D, out, sse, counts, dwr, dwr_replicas, use_hist);
+#define G2V_RUNS_LAUNCH(ZS, SO)                                                                                          \
+  do {                                                                                                                  \
+    G2V_CUDA_CHECK(cudaFuncSetAttribute(apply_runs_kernel<ZS, SO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+    apply_runs_kernel<ZS, SO><<<g, APPLY_WARPS * 32, rsmem, st>>>(x, zs, E, idx, order, N, K, D, out, sse, counts, dwr,   \
+                                                                  dwr_replicas, SO ? 0 : use_hist);                      \
+  } while (0)
+      if (zs && sorted) G2V_RUNS_LAUNCH(true, true);
+      else if (zs) G2V_RUNS_LAUNCH(true, false);
+      else if (sorted) G2V_RUNS_LAUNCH(false, true);
+      else G2V_RUNS_LAUNCH(false, false);
+#undef G2V_RUNS_LAUNCH
       G2V_LAUNCH_CHECK("apply_runs_kernel");
       return G2V_OK;
     }

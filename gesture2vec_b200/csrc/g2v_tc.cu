@@ -898,8 +898,7 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
   auto bar_zempty = [&](int s) { return bars + 8u * (2 * TME_MAX_BST + TME_MAX_ZSLOTS + s); };
   constexpr int A0 = 2 * TME_MAX_BST + 2 * TME_MAX_ZSLOTS;
   // per A buffer b and super-chunk c
-  auto bar_aconv = [&](int b, int c) { return bars + 8u * (A0 + b * MAX_CHUNKS + c); };              // this CTA's converters wrote it
-  auto bar_apeer = [&](int b, int c) { return bars + 8u * (A0 + (2 + b) * MAX_CHUNKS + c); };        // leader: the peer's converters did
+  auto bar_aconv = [&](int b, int c) { return bars + 8u * (A0 + b * MAX_CHUNKS + c); };              // leader: the converters of both CTAs wrote it
   auto bar_aempty = [&](int b, int c) { return bars + 8u * (A0 + (4 + b) * MAX_CHUNKS + c); };       // the MMAs finished reading it
   auto bar_accfull = [&](int a) { return bars + 8u * (A0 + 6 * MAX_CHUNKS + a); };
   auto bar_accempty = [&](int a) { return bars + 8u * (A0 + 6 * MAX_CHUNKS + 2 + a); };
@@ -917,7 +916,7 @@ tc_tmem_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
     for (int s = 0; s < TME_MAX_BST; ++s) { mbar_init(bar_bfull(s), 1); mbar_init(bar_bempty(s), 1); }
     for (int s = 0; s < TME_MAX_ZSLOTS; ++s) { mbar_init(bar_zfull(s), 1); mbar_init(bar_zempty(s), TME_CONV_WARPS); }
     for (int b = 0; b < 2; ++b)
-      for (int c = 0; c < MAX_CHUNKS; ++c) { mbar_init(bar_aconv(b, c), 2 * TME_CONV_WARPS); mbar_init(bar_apeer(b, c), 1); mbar_init(bar_aempty(b, c), 1); }
+      for (int c = 0; c < MAX_CHUNKS; ++c) { mbar_init(bar_aconv(b, c), 2 * TME_CONV_WARPS); mbar_init(bar_aempty(b, c), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(bar_accfull(a), 1); mbar_init(bar_accempty(a), 16); }
     for (int s = 0; s < RS_RING; ++s) mbar_init(bar_rsfull(s), TME_CONV_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

@@ -239,10 +239,14 @@ def _apply_rows(x, zs, E, idx, out, acc: Optional[_Accum], want_dwr: bool, deter
                                                 _stream(x.device)), "g2v_vq_apply")
         return
     dwr = acc.dwr if (acc is not None and want_dwr) else None
-    _lib.check(_lib.load().g2v_vq_apply(
+    lib = _lib.load()
+    # bulk passes with residual sums group the rows by code first (scratch: the order array)
+    wsb = lib.g2v_apply_workspace_bytes(N, K) if dwr is not None else 0
+    ws = _scratch.get(x.device, "apply", wsb) if wsb else None
+    _lib.check(lib.g2v_vq_apply_ws(
         _ptr(x), _ptr(zs), _ptr(E), _ptr(idx), N, K, D, _ptr(out),
         _ptr(acc.sse) if acc is not None else None, _ptr(acc.counts) if acc is not None else None,
-        _ptr(dwr), acc.reps if dwr is not None else 0, _stream(x.device)), "g2v_vq_apply")
+        _ptr(dwr), acc.reps if dwr is not None else 0, _ptr(ws), wsb, _stream(x.device)), "g2v_vq_apply_ws")
 
 
 def _deterministic_stats(x, zs, E, idx, acc: _Accum) -> None:

@@ -137,6 +137,16 @@ int g2v_vq_apply(const float* x, const float* zs, const float* E, const int32_t*
                  int64_t N, int K, int D, float* out, double* sse, int32_t* counts,
                  float* dwr, int dwr_replicas, void* stream);
 
+/* The same with scratch for the bulk path (N >= 16384 and residual sums wanted): the rows are first grouped by code
+ * on the device (one cooperative launch), so that the row pass sums whole runs of equal codes in registers and issues
+ * a handful of vector reductions per code instead of one per run of a 32-row batch -- the reductions, not DRAM, bound
+ * the unsorted pass.  Results are the same up to the order of the fp32 additions.  ws: g2v_apply_workspace_bytes(N, K)
+ * bytes (0 = this shape takes the unsorted pass; ws may then be NULL), 16-byte aligned. */
+size_t g2v_apply_workspace_bytes(int64_t N, int K);
+int g2v_vq_apply_ws(const float* x, const float* zs, const float* E, const int32_t* idx,
+                    int64_t N, int K, int D, float* out, double* sse, int32_t* counts,
+                    float* dwr, int dwr_replicas, void* ws, size_t ws_bytes, void* stream);
+
 /* Fold the linear layer in front of a search into the codebook (pre_linear, Autoencoder_VQVAE_model.py:1230):
  * argmin_k |W z + b - e_k|^2 = argmin_k (c_k - 2 z.(W^T e_k)), c_k = |e_k|^2 - 2 b.e_k.  Writes out[k, 0..D) =
  * W^T e_k (fp64 accumulation, one rounding; W is nn.Linear's [D_out, D_in] weight read as rows i, columns j) and
