@@ -50,6 +50,15 @@ def test_size_queries_and_validation_without_gpu(lib):
     assert lib.g2v_workspace_bytes(-1, 4, 4, 0, 0) == 0
     assert lib.g2v_workspace_bytes(1000, 512, 400, 0, 1) >= 1000 * 4          # SIMT: the re-rank list
     assert lib.g2v_workspace_bytes(1000, 512, 400, 0, 0) >= 1000 * 400 * 2      # TC: fp16 operand rows
+    # bulk searches reserve the refine pass's region (split operands + fp32 dots of the listed rows), capped at 4 GiB;
+    # batches below 32768 rows do not
+    small, bulk = lib.g2v_workspace_bytes(32767, 512, 400, 0, 0), lib.g2v_workspace_bytes(32768, 512, 400, 0, 0)
+    assert bulk - small > 32768 * 512 * 4
+    assert lib.g2v_workspace_bytes(1 << 24, 512, 400, 0, 0) - lib.g2v_workspace_bytes(1 << 23, 512, 400, 0, 0) < (1 << 23) * 2000
+    # the sorted row pass: scratch only for bulk batches and K <= 4096
+    assert lib.g2v_apply_workspace_bytes(16383, 512) == 0 and lib.g2v_apply_workspace_bytes(1 << 20, 8192) == 0
+    assert lib.g2v_apply_workspace_bytes(1 << 20, 512) >= (1 << 20) * 4 + 2 * 512 * 4
+    assert lib.g2v_vq_apply_ws(None, None, None, None, 10, 4, 4, None, None, None, None, 0, None, 0, None) == -1
     assert lib.g2v_search_path(512, 400, 0) == 2 and lib.g2v_search_path(512, 400, 1) == 1
     assert lib.g2v_search_path(80, 40, 0) == 1                                  # tiny frame-level shape -> fp32 path
     assert lib.g2v_search_path(80, 40, 2) == -7
