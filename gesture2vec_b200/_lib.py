@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("G2V_LIB_PATH") or os.path.join(HERE, "csrc", "libg2v_
 
 # dtype / flag codes (mirror include/g2v_vq.h)
 F32, BF16, F16 = 0, 1, 2
-ALGO_AUTO, ALGO_SIMT, ALGO_TC, NO_RECHECK, NO_REFINE = 0, 1, 2, 4, 8
+ALGO_AUTO, ALGO_SIMT, ALGO_TC, NO_RECHECK, NO_REFINE, LIST_ALL_ROWS = 0, 1, 2, 4, 8, 16
 ALGO_MASK = 3
 ERR_UNSUPPORTED = -7
 GEMM_ACCUMULATE, GEMM_FP16 = 1, 2

@@ -286,7 +286,9 @@ __device__ __forceinline__ void finish_row(const Cand& c1, const Cand& c2, const
   const float tauf = (4.f * (ri.a1 * cu + ri.a0) + 2.3841858e-7f * cu * cu) * ri.S + 4.f;
   const uint32_t tau = (uint32_t)fminf(tauf, 4194304.f);
   auto near = [&](uint32_t key) { return (key >> 9) - v1 <= tau; };   // keys are >= t1
-  if (!(flags & G2V_NO_RECHECK) && (near(c2.key) || near(c1.key2))) {
+  if (flags & G2V_LIST_ALL_ROWS) {          // test aid: every row goes through the whole-row path (refine pass / fp64)
+    full_list[atomicAdd(counters + 1, 1)] = (int)row;
+  } else if (!(flags & G2V_NO_RECHECK) && (near(c2.key) || near(c1.key2))) {
     // Exact candidates are known only if no chain hides a code: a chain's third-best is unknown,
     // so a runner-up within tau (of any of the three chains) or a fourth chain within tau means
     // the whole row must be re-ranked.  Otherwise the candidates are the chain minima within tau.

@@ -53,6 +53,8 @@ extern "C" {
 #define G2V_NO_RECHECK 4u       /* keep the fast-pass winner (bf16/fp16 "fast" variant) */
 #define G2V_NO_REFINE 8u        /* test / benchmark aid: whole-row re-ranks go straight to fp64 instead of through the
                                  * tensor-core refine pass (results are identical) */
+#define G2V_LIST_ALL_ROWS 16u    /* test aid: the tensor-core pass lists EVERY row as a whole-row re-rank, so the refine pass
+                                 * (or, with G2V_NO_REFINE, the fp64 path) decides all of them -- the audit of its error bound */
 /* test / benchmark aid: pin the tensor-core sweep kernel (results are identical; a variant that does not cover
  * the shape falls back to the automatic choice) */
 #define G2V_TC_VARIANT_MASK (7u << 8)

@@ -316,3 +316,22 @@ def test_six_million_rows_need_64_bit_offsets():
     LL.check(lib.g2v_vq_backward(z.data_ptr(), E.data_ptr(), idx.data_ptr(), None, one.data_ptr(), 0.5, N, K, D,
                                  gx.data_ptr(), torch.cuda.current_stream().cuda_stream), "g2v_vq_backward")
     assert torch.allclose(gx[tail], 0.5 * (z[tail] - q), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("lk,ck,K", [("iid", "normal", 400), ("gru", "uniform1", 512), ("clustered", "normal", 1000),
+                                     ("iid", "ema_degenerate", 512)])
+def test_refine_pass_decides_every_row_exactly(lk, ck, K):
+    """G2V_LIST_ALL_ROWS hands EVERY row to the refine pass (split-fp16 tensor-core dots + a-priori error bound +
+    fp64 on the codes the bound cannot exclude): 131 072 rows per distribution against the fp64 checker.  A bound that
+    was too tight would show up as wrong indices here; one that was loose as many fp64 evaluations per row."""
+    g, L = _g()
+    D, N = 400, 131072
+    E = S.codebook(ck, K, D, DEV, seed=61)
+    z = S.latents(lk, N, D, DEV, E=E, seed=62)
+    st = torch.zeros(8, dtype=torch.int64, device=DEV)
+    idx = g.vq_search(z, E, flags=L.ALGO_TC | L.LIST_ALL_ROWS, stats=st)
+    st = st.cpu().numpy()
+    assert st[L.STAT_REFINE_ROWS] == N, st
+    a = S.audit(z, E, idx, g.vq_search_exact(z, E), eps_tie=2.0 ** -40)
+    assert a["hard"] == 0, a
+    assert st[L.STAT_REFINE_EXACT] < 1.5 * N, st                 # ~1 fp64 evaluation per row: the bound is tight

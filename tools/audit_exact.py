@@ -70,6 +70,16 @@ def main():
                      rerank_rows=st[1], fallback_rows=st[3], fp64_rows=st[2])
             total_hard += r["hard"]
             log(r)
+        # every row through the refine pass (split-fp16 dots, a-priori bound, fp64 on what the bound cannot exclude)
+        if K <= 2048:
+            stats = torch.zeros(8, dtype=torch.int64, device=dev)
+            idx = g.vq_search(z, E, cb, flags=L.ALGO_TC | L.LIST_ALL_ROWS, stats=stats)
+            r = S.audit(z, E, idx, exact, eps_tie=2.0 ** -40)
+            st = stats.cpu().tolist()
+            r.update(latents=lk, codebook=ck, K=K, dtype="f32", variant="refine_all_rows", refine_rows=st[4],
+                     refine_fp64_codes=st[5])
+            total_hard += r["hard"]
+            log(r)
         n16 = min(N, 262144)
         for dt in (torch.bfloat16, torch.float16):
             z16 = z[:n16].to(dt).contiguous()
