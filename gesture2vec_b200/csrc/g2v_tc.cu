@@ -1676,6 +1676,86 @@ struct RefineArgs {
   float beta;                 // dot-product error relative to |z| |e_k|
 };
 
+// fp64 distance of one row to one code, lanes split the dimensions (all lanes get the sum)
+template <typename ZT>
+__device__ __forceinline__ double exact_dist_warp(const ZT* __restrict__ zr, const float* __restrict__ er, int D, int Dz, int lane) {
+  double s = 0.0;
+  for (int j0 = lane; j0 < D; j0 += 32 * 8) {
+    float zv[8], ev[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      const int j = j0 + 32 * v;
+      zv[v] = j < Dz ? ld_f32(zr + j) : 0.f;
+      ev[v] = j < D ? __ldg(er + j) : 0.f;
+    }
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      const double df = (double)zv[v] - (double)ev[v];
+      s = fma(df, df, s);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+
+// K <= 32 KI: a lane keeps the lower bounds of its KI codes in registers -- one pass over the row's dots instead of
+// two (the collapse regime lists most rows: 574 k rows took 1.8 ms with the two-pass kernel below)
+template <typename ZT, int KI>
+__global__ void __launch_bounds__(256, 4) refine_rows_reg_kernel(const ZT* __restrict__ z, const float* __restrict__ E, int K, int D,
+                                                                 int Dz, const int* __restrict__ full_list,
+                                                                 const int* __restrict__ full_count, const RefineArgs R,
+                                                                 int* __restrict__ idx, unsigned long long* stats) {
+  const int lane = threadIdx.x & 31;
+  const int n = refine_count(*full_count, K, R.cap);
+  unsigned long long* n_exact = stats ? stats + G2V_STAT_REFINE_EXACT : nullptr;
+  if (stats && blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(stats + G2V_STAT_REFINE_ROWS, (unsigned long long)n);
+  const int wstride = (int)((gridDim.x * blockDim.x) >> 5);
+  unsigned long long exact = 0;
+  for (int e = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); e < n; e += wstride) {
+    const int row = full_list[e];
+    const RefineRow ri = R.rows[e];
+    const float* dr = R.dots + (size_t)e * R.ldc;
+    const float c1 = (2.f * R.beta + 4.7683716e-7f) * ri.znorm, c2 = 4.7683716e-7f;    // 2^-21: the fp32 steps of the comparison
+    float raw[KI], lo[KI];
+#pragma unroll
+    for (int i = 0; i < KI; ++i) raw[i] = (lane + 32 * i < K) ? __ldcs(dr + lane + 32 * i) : 0.f;
+    float U = INFINITY;
+#pragma unroll
+    for (int i = 0; i < KI; ++i) {
+      const int k = lane + 32 * i;
+      lo[i] = INFINITY;
+      if (k < K) {
+        const float e2k = __ldg(R.e2 + k);
+        const float dot = (raw[i] * ri.inv_s) * __ldg(R.invt + k);
+        const float d = fmaf(-2.f, dot, e2k);
+        const float err = fmaf(c1, sqrtf(e2k) * 1.0001f, c2 * e2k);
+        lo[i] = d - err;
+        U = fminf(U, d + err);                  // a NaN bound is ignored here and becomes a candidate below
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) U = fminf(U, __shfl_xor_sync(0xffffffffu, U, o));
+    const ZT* zr = z + (size_t)row * Dz;
+    double best = INFINITY;
+    int besti = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < KI; ++i) {
+      const bool cand = (lane + 32 * i < K) && !(lo[i] > U);
+      unsigned mask = __ballot_sync(0xffffffffu, cand);
+      while (mask) {
+        const int kk = 32 * i + __ffs((int)mask) - 1;
+        mask &= mask - 1;
+        const double s = exact_dist_warp<ZT>(zr, E + (size_t)kk * D, D, Dz, lane);
+        if (s < best) { best = s; besti = kk; }         // ascending k: the first of equal distances stays
+        ++exact;
+      }
+    }
+    if (lane == 0) idx[row] = besti == 0x7fffffff ? 0 : besti;    // every distance NaN: index 0, as torch.argmin
+  }
+  if (n_exact && lane == 0 && exact) atomicAdd(n_exact, exact);
+}
+
 // one warp per listed row: candidates from the fp32-accurate dots, then fp64 on the candidates
 template <typename ZT>
 __global__ void __launch_bounds__(256, 4) refine_rows_kernel(const ZT* __restrict__ z, const float* __restrict__ E, int K, int D, int Dz,
@@ -1991,7 +2071,9 @@ int run_recheck(const ZT* z, int z_dtype, const float* E, const void* cb, int64_
     RA.e2 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cb) + cb_e2_offset());
     RA.ldc = rf.ldc; RA.cap = (int)rf.cap;
     RA.beta = 7.3e-7f + 1.003f * (1.9073486e-6f + (float)(3 * rf.kp / 16 + 2) * 1.1920929e-7f);
-    refine_rows_kernel<ZT><<<num_sms() * 4, 256, 0, side->s>>>(z, E, K, D, Dz, fulls, counters + 1, RA, idx, stats);
+    if (K <= 512) refine_rows_reg_kernel<ZT, 16><<<num_sms() * 4, 256, 0, side->s>>>(z, E, K, D, Dz, fulls, counters + 1, RA, idx, stats);
+    else if (K <= 1024) refine_rows_reg_kernel<ZT, 32><<<num_sms() * 4, 256, 0, side->s>>>(z, E, K, D, Dz, fulls, counters + 1, RA, idx, stats);
+    else refine_rows_kernel<ZT><<<num_sms() * 4, 256, 0, side->s>>>(z, E, K, D, Dz, fulls, counters + 1, RA, idx, stats);
     G2V_LAUNCH_CHECK("refine_rows_kernel");
     G2V_CUDA_CHECK(cudaEventRecord(side->join, side->s));
   }
