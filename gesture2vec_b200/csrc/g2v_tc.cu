@@ -2,7 +2,7 @@
 // TMEM) fed by TMA, fused with an argmin epilogue, so the [N,K] distance matrix never exists.
 //
 // run_tc() picks one of two sweep kernels, all on the caller's stream:
-//   tc_tmem_kernel<ZT>        few code tiles (K <= 576 at D = 400), fp32 / bf16 / fp16 rows.  CTA pairs
+//   tc_tmem_kernel<ZT>        fp32 rows at any K, bf16 / fp16 rows up to 16 code tiles.  CTA pairs
 //                             (cta_group::2, UMMA M = 256).  Rows stream by TMA into a ring of staging slots;
 //                             8 converter warps round them to fp16 in registers, keep ||z||^2 and the exact
 //                             rounding residual per row, and write the A operand straight into tensor memory
@@ -14,8 +14,10 @@
 // two accumulator stages in TMEM), 8 epilogue warps: tcgen05.ld -> d = e2 - 2 z.e as a 23-bit fixed-point
 // key (packed FFMA2, FMNMX, IMAD) -> 32 running top-2 chains per row (3 VIMNMX per key).
 // A row whose best codes are closer than its error bound tau goes to a candidate list (row + up to three
-// codes), a chain list (one chain of K/32 codes may hide the winner) or the whole-row list; rerank_kernel
-// re-ranks all three exactly in fp64, full_recheck_kernel (g2v_simt.cu) takes an overflowing whole-row list.
+// codes), a chain list (one chain of K/32 codes may hide the winner) or the whole-row list.  rerank_kernel
+// re-ranks the first two exactly in fp64; the whole rows of a bulk search take the refine pass first (split-fp16
+// operands, tc_gemm_kernel, refine_rows_kernel: fp64 only on the codes an fp32-accurate bound cannot exclude) on a
+// side stream next to it; full_recheck_kernel (g2v_simt.cu) takes a whole-row list that overflows the pass.
 //
 // Operand layouts: K-major, SWIZZLE_128B panels of 64 fp16 (TMA box 64 x rows) and, for the
 // D % 64 remainder, SWIZZLE_32B panels of 16 fp16 (one UMMA_K step each).
